@@ -1,0 +1,196 @@
+/* radiorust_b200 -- C ABI of the B200-native IQ sample chain.
+ *
+ * Drop-in boundary for ONE hot path of JanBeh/radiorust 0.5.0: the blocks
+ * FreqShifter -> Filter -> Downsampler (+ Upsampler, FmDemod, de-emphasis,
+ * GainControl).  The reference has no FFI of its own (pure Rust);
+ * these entry points are what an `extern "C"` FFI crate binds so that GPU
+ * versions of the blocks can implement radiorust's Consumer/Producer traits
+ * (src/flow.rs:233-267, src/blocks/mod.rs:111-144).  INTEGRATION.md shows the
+ * Rust side.
+ *
+ * Conventions
+ *  - plain C types, opaque handles, int status (0 = ok, < 0 = rr_status);
+ *    rr_last_error() returns a thread-local message; nothing unwinds or aborts.
+ *  - samples are interleaved complex (re, im): RR_C32 = num::Complex<f32>
+ *    (8 bytes), RR_C64 = num::Complex<f64> (16 bytes) -- #[repr(C)] layout.
+ *  - a chain processes `n_streams` independent streams in lock step; stream s
+ *    lives at base + s*stride (stride in samples).
+ *  - every call selects the handle's CUDA device first (Tokio tasks migrate
+ *    between threads).  A handle is Send but not Sync: one task owns a chain.
+ *  - there is NO CPU fallback: without a CUDA device rr_ctx_create fails.
+ */
+#ifndef RADIORUST_B200_H
+#define RADIORUST_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RR_VERSION_MAJOR 0
+#define RR_VERSION_MINOR 1
+
+typedef struct rr_ctx rr_ctx;
+typedef struct rr_chain rr_chain;
+
+typedef enum rr_status {
+    RR_OK = 0,
+    RR_ERR_INVALID = -1,     /* bad argument / contract violation (reference: assert!/panic in the task) */
+    RR_ERR_CUDA = -2,        /* CUDA runtime error (message holds cudaGetErrorString) */
+    RR_ERR_UNSUPPORTED = -3, /* valid for the reference, not implemented on the device path */
+    RR_ERR_NOMEM = -4,
+    RR_ERR_CAPACITY = -5     /* output buffer too small */
+} rr_status;
+
+typedef enum rr_dtype { RR_C32 = 0, RR_C64 = 1 } rr_dtype;
+
+/* One stage = one reference block. */
+typedef enum rr_stage_kind {
+    RR_STAGE_FREQSHIFT = 1,  /* blocks::FreqShifter   src/blocks/transform.rs:266-391 */
+    RR_STAGE_FILTER = 2,     /* blocks::filters::Filter src/blocks/filters.rs:110-298 */
+    RR_STAGE_DOWNSAMPLE = 3, /* blocks::Downsampler   src/blocks/resampling.rs:14-146 */
+    RR_STAGE_UPSAMPLE = 4,   /* blocks::Upsampler     src/blocks/resampling.rs:149-280 */
+    RR_STAGE_FMDEMOD = 5,    /* blocks::modulation::FmDemod src/blocks/modulation.rs:83-158 */
+    RR_STAGE_GAIN = 6        /* blocks::GainControl   src/blocks/transform.rs:29-92 */
+} rr_stage_kind;
+
+typedef enum rr_window_kind {
+    RR_WINDOW_KAISER = 0,      /* windowing::Kaiser{beta}  src/windowing.rs:24-51 */
+    RR_WINDOW_RECTANGULAR = 1, /* windowing::Rectangular   src/windowing.rs:14-20 */
+    RR_WINDOW_CUSTOM = 2       /* windowing::CustomWindow  src/windowing.rs:58-67 */
+} rr_window_kind;
+
+/* Frequency response closure of Filter (`Fn(isize, f64) -> Complex<f64>`,
+ * src/blocks/filters.rs:128-131): called on the host at (re)design time only. */
+typedef void (*rr_freq_resp_fn)(void* user, int64_t bin, double freq_hz, double* out_re, double* out_im);
+/* Window::relative_value_at (src/windowing.rs:9), x in [-1, 1]. */
+typedef double (*rr_window_fn)(void* user, double x);
+
+typedef struct rr_stage_desc {
+    int32_t kind; /* rr_stage_kind */
+    int32_t window_kind; /* FILTER: rr_window_kind */
+    /* FREQSHIFT: FreqShifter::with_precision_and_shift(precision, shift) */
+    double precision; /* hertz, reference default 1.0 */
+    double shift;     /* hertz, initial value for every stream */
+    /* FILTER: Filter::with_window(freq_resp, window) */
+    rr_freq_resp_fn freq_resp;
+    void* freq_resp_user;
+    double window_beta; /* Kaiser beta; Filter::new uses sqrt(3) (= with_null_at_bin(2.0)) */
+    rr_window_fn window_fn;
+    void* window_user;
+    /* DOWNSAMPLE / UPSAMPLE: ::with_quality(output_chunk_len, output_rate, bandwidth, quality) */
+    uint64_t output_chunk_len;
+    double output_rate;
+    double bandwidth;
+    double quality; /* reference default 3.0 */
+    /* FMDEMOD: FmDemod::new(deviation) */
+    double deviation;
+    /* GAIN: GainControl::new(gain) */
+    double gain;
+} rr_stage_desc;
+
+typedef struct rr_chain_desc {
+    int32_t dtype;     /* rr_dtype */
+    int32_t n_streams; /* independent streams processed per push */
+    int32_t n_stages;
+    int32_t reserved;
+    const rr_stage_desc* stages;
+} rr_chain_desc;
+
+/* ---- library / errors ---------------------------------------------------- */
+const char* rr_last_error(void);
+int rr_version(int* major, int* minor);
+/* number of kernels this library has launched in the calling process */
+uint64_t rr_kernel_launch_count(void);
+
+/* ---- context (one per device) -------------------------------------------- */
+int rr_ctx_create(int device, rr_ctx** out);
+int rr_ctx_destroy(rr_ctx* ctx);
+int rr_ctx_device(const rr_ctx* ctx);
+
+/* ---- pinned chunk pool at the chain edges (replaces bufferpool.rs:187-222) */
+int rr_pinned_alloc(rr_ctx* ctx, size_t bytes, void** out);
+int rr_pinned_free(rr_ctx* ctx, void* p);
+int rr_host_register(rr_ctx* ctx, void* p, size_t bytes); /* pin a recycled Vec in place */
+int rr_host_unregister(rr_ctx* ctx, void* p);
+int rr_device_alloc(rr_ctx* ctx, size_t bytes, void** out);
+int rr_device_free(rr_ctx* ctx, void* p);
+int rr_memcpy_h2d(rr_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int rr_memcpy_d2h(rr_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+
+/* ---- design math, host only (no GPU needed) ------------------------------ */
+double rr_bessel_i0(double x);                      /* math::bessel_I0  src/math.rs:7-20 */
+double rr_sinc(double x);                           /* math::sinc       src/math.rs:42-49 */
+double rr_kaiser_rel_with_beta(double beta, double x); /* src/math.rs:26-28 */
+double rr_kaiser_null_at_bin_to_beta(double n);     /* src/math.rs:37-39 */
+void rr_deemphasis_factor(double tau, double frequency, double* out_re, double* out_im); /* filters.rs:20-27 */
+int rr_freq_to_ratio(double sample_rate, double precision, double frequency, int64_t* numer, int64_t* denom); /* transform.rs:298-302 */
+/* extended_response of Filter (2n complex f64 values, interleaved) -- filters.rs:184-238 */
+int rr_design_filter_response(rr_freq_resp_fn f, void* f_user, int32_t window_kind, double window_beta,
+                              rr_window_fn w, void* w_user, double sample_rate, size_t n, int32_t dtype,
+                              double* out_2n_complex);
+/* Downsampler / Upsampler taps; returns the tap count through *ir_len; pass ir == NULL to query */
+int rr_design_downsampler_taps(double input_rate, double output_rate, double bandwidth, double quality,
+                               size_t* ir_len, double* ir); /* resampling.rs:75-98 */
+int rr_design_upsampler_taps(double input_rate, double output_rate, double bandwidth, double quality,
+                             size_t* ir_len, double* ir);   /* resampling.rs:205-233 */
+
+/* ---- chain ----------------------------------------------------------------- */
+int rr_chain_create(rr_ctx* ctx, const rr_chain_desc* desc, rr_chain** out);
+int rr_chain_destroy(rr_chain* chain);
+
+/* FreqShifter::set_shift (transform.rs:384-386); stream < 0 = all streams.
+ * Takes effect at the next push, phase-continuously (transform.rs:322-327). */
+int rr_chain_set_shift(rr_chain* chain, int stage, int stream, double shift_hz);
+/* one shift per stream in a single call (n must equal n_streams): a channelizer's tuning table */
+int rr_chain_set_shifts(rr_chain* chain, int stage, const double* shifts_hz, int n);
+/* FreqShifter::shift (transform.rs:380-382) */
+int rr_chain_get_shift(rr_chain* chain, int stage, int stream, double* shift_hz);
+/* Filter::update / update_with_window (filters.rs:279-297): redesign at the next
+ * push and drop the history chunk (filters.rs:187). */
+int rr_chain_update_filter(rr_chain* chain, int stage, rr_freq_resp_fn f, void* f_user, int32_t window_kind,
+                           double window_beta, rr_window_fn w, void* w_user, int keep_window);
+/* FmDemod::set_deviation (modulation.rs:154-157) */
+int rr_chain_set_deviation(rr_chain* chain, int stage, double deviation);
+/* GainControl::set (transform.rs:89-91) */
+int rr_chain_set_gain(rr_chain* chain, int stage, double gain);
+
+/* In-band event (signal.rs:19-31).  Interrupt events reset Filter history
+ * (filters.rs:262-267) and FmDemod's previous sample (modulation.rs:133-138);
+ * resamplers and the NCO keep their state. */
+int rr_chain_event(rr_chain* chain, int is_interrupt);
+
+/* Upper bound of output samples per stream for a push of n_chunks*chunk_len
+ * input samples at sample_rate. */
+size_t rr_chain_max_output(rr_chain* chain, double sample_rate, size_t chunk_len, size_t n_chunks);
+
+/* Signal::Samples{sample_rate, chunk} for every stream: `n_chunks` consecutive
+ * chunks of `chunk_len` samples per stream (n_chunks > 1 batches several
+ * reference messages into one launch; results are identical to pushing them one
+ * by one).  HOST buffers (pinned for full asynchrony): H2D, kernels and D2H are
+ * enqueued on the chain's stream; call rr_chain_sync before reading host_out.
+ * *out_count = samples produced per stream (same for all streams);
+ * *out_sample_rate = their rate.  out_count follows the reference: a Filter's
+ * first chunk after start/redesign/interrupt only primes history
+ * (filters.rs:240,260); resamplers emit whole chunks of output_chunk_len
+ * (resampling.rs:121-131). */
+int rr_chain_push(rr_chain* chain, double sample_rate, size_t chunk_len, size_t n_chunks, const void* host_in,
+                  size_t in_stride, void* host_out, size_t out_capacity, size_t out_stride, size_t* out_count,
+                  double* out_sample_rate);
+/* Same with DEVICE buffers (no PCIe traffic; stays device-resident). */
+int rr_chain_push_device(rr_chain* chain, double sample_rate, size_t chunk_len, size_t n_chunks, const void* dev_in,
+                         size_t in_stride, void* dev_out, size_t out_capacity, size_t out_stride, size_t* out_count,
+                         double* out_sample_rate);
+int rr_chain_sync(rr_chain* chain);
+/* raw cudaStream_t of the chain (for event timing by the caller) */
+void* rr_chain_cuda_stream(rr_chain* chain);
+/* name of the execution plan chosen at the last push (diagnostics), e.g.
+ * "fused_os[nco+filter+down]" or "freqshift|big_os|downsample" */
+const char* rr_chain_plan(rr_chain* chain);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RADIORUST_B200_H */

@@ -1,0 +1,145 @@
+#include "rr_design.h"
+
+#include <cmath>
+#include <numeric>
+
+namespace rr {
+
+// src/math.rs:7-20
+double bessel_i0(double x) {
+    const double base = x * x / 4.0;
+    double addend = 1.0, sum = 1.0;
+    for (uint64_t i = 1;; ++i) {
+        addend *= base / (double)(i * i);
+        const double old = sum;
+        sum += addend;
+        if (sum == old || !std::isfinite(sum)) break;
+    }
+    return sum;
+}
+
+// src/math.rs:26-28
+double kaiser_rel_with_beta(double beta, double x) { return bessel_i0(beta * std::sqrt(1.0 - x * x)); }
+
+// src/math.rs:37-39 (sqrt(n^2 - 1); no pi factor, replicated as is)
+double kaiser_null_at_bin_to_beta(double n) { return std::sqrt(n * n - 1.0); }
+
+// src/math.rs:42-49
+double sinc(double x) {
+    if (x == 0.0) return 1.0;
+    const double t = x * M_PI;
+    return std::sin(t) / t;
+}
+
+// src/blocks/filters.rs:20-27 (Complex::finv = conj / norm_sqr)
+std::complex<double> deemphasis_factor(double tau, double frequency) {
+    const double re = 1.0, im = tau * (2.0 * M_PI) * frequency;
+    const double nrm = re * re + im * im;
+    return std::complex<double>(re / nrm, -im / nrm);
+}
+
+// src/blocks/transform.rs:298-302 + num Ratio::new
+bool freq_to_ratio(double sample_rate, double precision, double frequency, int64_t* numer, int64_t* denom) {
+    int64_t d = (int64_t)std::round(sample_rate / precision);  // f64::round: half away from zero
+    int64_t n = (int64_t)std::round((double)d * frequency / sample_rate);
+    if (d == 0) return false;
+    int64_t g = std::gcd(n < 0 ? -n : n, d < 0 ? -d : d);
+    if (g == 0) g = 1;
+    n /= g;
+    d /= g;
+    if (d < 0) {
+        n = -n;
+        d = -d;
+    }
+    *numer = n;
+    *denom = d;
+    return true;
+}
+
+void make_twiddles(size_t N, std::vector<std::complex<double>>* out) {
+    out->resize(N);
+    for (size_t e = 0; e < N; ++e) {
+        // octant-exact angles through long double keep the table at <= 0.5 ulp(f64)
+        const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)e / (long double)N;
+        (*out)[e] = std::complex<double>((double)cosl(a), (double)sinl(a));
+    }
+}
+
+void fft_pow2(std::vector<std::complex<double>>& a, bool inverse) {
+    const size_t n = a.size();
+    if (n <= 1) return;
+    for (size_t i = 1, j = 0; i < n; ++i) {
+        size_t bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) std::swap(a[i], a[j]);
+    }
+    std::vector<std::complex<long double>> tw(n / 2);
+    for (size_t k = 0; k < n / 2; ++k) {
+        const long double ang = (inverse ? 2.0L : -2.0L) * 3.14159265358979323846264338327950288L * (long double)k / (long double)n;
+        tw[k] = std::complex<long double>(cosl(ang), sinl(ang));
+    }
+    for (size_t len = 2; len <= n; len <<= 1) {
+        const size_t step = n / len;
+        for (size_t i = 0; i < n; i += len) {
+            for (size_t k = 0; k < len / 2; ++k) {
+                const std::complex<double> w((double)tw[k * step].real(), (double)tw[k * step].imag());
+                const std::complex<double> u = a[i + k];
+                const std::complex<double> v = a[i + k + len / 2] * w;
+                a[i + k] = u + v;
+                a[i + k + len / 2] = u - v;
+            }
+        }
+    }
+}
+
+// src/blocks/filters.rs:184-238
+bool design_filter_response(const FreqResp& f, const WindowFn& w, double sample_rate, size_t n, bool as_f32,
+                            std::vector<std::complex<double>>* out) {
+    if (n < 2 || (n & (n - 1)) != 0) return false;
+    const double n_flt = (double)n;
+    const double scale = 2.0 * n_flt * n_flt;  // :186
+    std::vector<std::complex<double>> response(n, std::complex<double>(0.0, 0.0));
+    const double freq_step = sample_rate / n_flt;
+    const size_t max_bin_abs = (n - 1) / 2;
+    for (size_t i = 0; i <= max_bin_abs; ++i) {  // :193-199
+        const double freq = (double)i * freq_step;
+        response[i] = f((int64_t)i, freq) / scale;
+        if (i > 0) response[n - i] = f(-(int64_t)i, -freq) / scale;
+    }
+    fft_pow2(response, true);                                               // :200 (unnormalised inverse)
+    for (size_t i = 0; i < n / 2; ++i) std::swap(response[i], response[i + n / 2]);  // :201-203
+    double energy_pre = 0.0, energy_post = 0.0;
+    for (size_t i = 0; i < n; ++i) {  // :204-214
+        energy_pre += std::norm(response[i]);
+        response[i] *= w(2.0 * ((double)i + 0.5) / n_flt - 1.0);
+        energy_post += std::norm(response[i]);
+    }
+    const double scale2 = std::sqrt(energy_pre / energy_post);  // :216
+    for (auto& y : response) y *= scale2;
+    out->assign(2 * n, std::complex<double>(0.0, 0.0));  // :220-226
+    for (size_t i = 0; i < n; ++i) {
+        if (as_f32) (*out)[n + i] = std::complex<double>((double)(float)response[i].real(), (double)(float)response[i].imag());
+        else (*out)[n + i] = response[i];
+    }
+    fft_pow2(*out, false);  // :227-238 (the reference runs this one in Flt; f64 here, rounded once by the caller)
+    return true;
+}
+
+// src/blocks/resampling.rs:84-98 (Downsampler) and :219-233 (Upsampler)
+void design_resampler_taps(size_t ir_len, double ratio, double null_bin, std::vector<double>* out) {
+    const double ir_len_flt = (double)ir_len;
+    const double beta = kaiser_null_at_bin_to_beta(null_bin);
+    out->resize(ir_len);
+    double energy = 0.0;
+    for (size_t i = 0; i < ir_len; ++i) {
+        const double x = ((double)i + 0.5) - ir_len_flt / 2.0;
+        const double y = sinc(x * ratio) * kaiser_rel_with_beta(beta, x * 2.0 / ir_len_flt);
+        (*out)[i] = y;
+        energy += y * y;
+    }
+    const double scale = 1.0 / std::sqrt(energy);
+    for (auto& y : *out) y *= scale;
+}
+
+}  // namespace rr

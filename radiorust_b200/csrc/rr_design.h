@@ -1,0 +1,40 @@
+// Host-side design math (f64), the cold path of the chain: filter response
+// (K6), resampler taps (K7), NCO ratio.  Mirrors the reference bit-for-bit in
+// operation order where it matters (citations in rr_design.cpp).  No CUDA.
+#pragma once
+#include <complex>
+#include <cstdint>
+#include <functional>
+#include <vector>
+
+namespace rr {
+
+double bessel_i0(double x);
+double kaiser_rel_with_beta(double beta, double x);
+double kaiser_null_at_bin_to_beta(double n);
+double sinc(double x);
+std::complex<double> deemphasis_factor(double tau, double frequency);
+
+// reduced numer/denom of round(denom*f/sr) / round(sr/precision); returns
+// false when denom == 0 (Ratio::new would panic)
+bool freq_to_ratio(double sample_rate, double precision, double frequency, int64_t* numer, int64_t* denom);
+
+using FreqResp = std::function<std::complex<double>(int64_t bin, double freq)>;
+using WindowFn = std::function<double(double x)>;
+
+// In-place power-of-two complex FFT, unnormalised; inverse = conjugate kernel.
+void fft_pow2(std::vector<std::complex<double>>& a, bool inverse);
+
+// extended_response (2n bins).  `as_f32`: round the zero-padded impulse
+// response to f32 before the last FFT like the reference does for Flt = f32.
+// Returns false when n is not a power of two >= 2.
+bool design_filter_response(const FreqResp& f, const WindowFn& w, double sample_rate, size_t n, bool as_f32,
+                            std::vector<std::complex<double>>* out);
+
+// unit-energy windowed-sinc taps, f64 (cast by the caller)
+void design_resampler_taps(size_t ir_len, double ratio, double null_bin, std::vector<double>* out);
+
+// exp(-j*2*pi*e/N), e < N
+void make_twiddles(size_t N, std::vector<std::complex<double>>* out);
+
+}  // namespace rr

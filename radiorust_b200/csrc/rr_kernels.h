@@ -1,0 +1,117 @@
+// Host-callable launchers of the sm_100a kernels (C++ linkage, internal to the
+// library; the public boundary is include/radiorust_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rr {
+
+// Per-stream NCO state (device resident).  Mirrors the task-local state of
+// FreqShifter (src/blocks/transform.rs:307-309): the reduced ratio
+// numer/denom, the start phase and the running table index.
+struct NcoStream {
+    uint32_t numer_abs;   // |numer| (< denom)
+    uint32_t denom;       // > 0, < 2^31
+    uint32_t idx;         // phase_idx, < denom
+    int32_t sign;         // sign(numer): -1, 0, +1
+    double start_phase;   // radians (value of Flt precision)
+};
+
+// Decimation geometry for integer-valued rates: in/out = P/Q reduced.
+// j0 = input samples consumed so far (reduced mod P), m0 = outputs emitted so
+// far (reduced consistently); output m fires at input count ceil(m*P/Q)
+// (src/blocks/resampling.rs:109-111 in closed form).
+struct RateState {
+    long long P, Q, j0, m0;
+};
+
+template <typename T> struct ChainOsArgs {
+    const void* in;         // [S][in_stride] complex<T>
+    long long in_stride;    // elements
+    int n_chunks;           // chunks in this launch (including a history-only first chunk)
+    int first_is_history;   // 1: no stored history; chunk 0 only primes the filter
+    int emit;               // 0: state-only run (no samples written, only hist/ztail state)
+    int reserved;
+    const void* hist_in;    // [S][n] complex<T>, post-NCO history chunk (read when !first_is_history)
+    void* hist_out;         // [S][n] new history (never aliases hist_in: CTAs of one launch read and write)
+    const void* hperm;      // [N] complex<T>, H(f) in FftPlan::hperm_index order
+    const void* twN;        // [N] complex<T>, exp(-j*2*pi*e/N)
+    const NcoStream* nco;   // [S] or nullptr (read-only; the host advances idx with launch_nco_advance)
+    long long nco_offset;   // samples between nco[s].idx and sample 0 of `in`
+    void* out;              // [S][out_stride] complex<T>
+    long long out_stride;
+    // decimating epilogue (EPI == 1)
+    const T* ir;            // [L]
+    int L;
+    const void* ztail_in;   // [S][L-1] complex<T>: filter output preceding this launch
+    void* ztail_out;        // [S][L-1]
+    RateState rate;
+};
+
+// n = chunk length (N = 2n).  epi: 0 = write the filter output, 1 = decimating FIR.
+// parts > 1 (EPI == 0 only) splits the chunks of every stream over `parts` CTAs.
+template <typename T>
+cudaError_t launch_chain_os(int n, int epi, int n_streams, int parts, const ChainOsArgs<T>& a, cudaStream_t st);
+// true when (T, n, epi, L) can run in the fused single-CTA kernel
+template <typename T> bool chain_os_supported(int n, int epi, int L);
+template <typename T> int chain_os_threads(int n);
+// index of true bin k in the permuted H table for chunk length n
+template <typename T> int chain_os_hperm_index(int n, int k);
+
+// ---- standalone stages ------------------------------------------------------
+template <typename T>
+cudaError_t launch_freqshift(const void* in, long long in_stride, void* out, long long out_stride, long long len,
+                             int n_streams, NcoStream* nco, cudaStream_t st);
+
+cudaError_t launch_nco_advance(NcoStream* nco, int n_streams, long long len, cudaStream_t st);
+
+template <typename T>
+cudaError_t launch_gain(const void* in, long long in_stride, void* out, long long out_stride, long long len,
+                        int n_streams, double gain, cudaStream_t st);
+
+// FIR decimator on [tail(L-1) | input(len)] (src/blocks/resampling.rs:103-121)
+template <typename T>
+cudaError_t launch_downsample(const void* in, long long in_stride, long long len, const void* tail_in, void* tail_out,
+                              const T* ir, int L, RateState rate, long long n_out, void* out, long long out_stride,
+                              int n_streams, cudaStream_t st);
+
+// zero-stuffing interpolator, gather form (src/blocks/resampling.rs:238-267)
+template <typename T>
+cudaError_t launch_upsample(const void* in, long long in_stride, long long len, const void* acc_in, void* acc_out,
+                            const T* ir, int L, RateState rate, long long n_out, void* out, long long out_stride,
+                            int n_streams, cudaStream_t st);
+
+// FM discriminator (src/blocks/modulation.rs:116-126)
+template <typename T>
+cudaError_t launch_fmdemod(const void* in, long long in_stride, void* out, long long out_stride, long long len,
+                           int n_streams, void* prev_sample, void* last_output, int has_prev, double factor,
+                           cudaStream_t st);
+
+// strided 2-D copy of complex samples (used to stage stream buffers)
+template <typename T>
+cudaError_t launch_copy2d(const void* in, long long in_stride, void* out, long long out_stride, long long len,
+                          int n_streams, cudaStream_t st);
+
+// ---- large overlap-save (four-step FFT through L2-resident scratch) ---------
+template <typename T> struct BigOsArgs {
+    const void* in;         // [S][in_stride]: the pushed chunks
+    long long in_stride;
+    const void* hist;       // [S][n]: chunk preceding `in` (read when block 0 starts at chunk 0)
+    int first_chunk;        // block b convolves chunks (first_chunk + b - 1, first_chunk + b)
+    int n_blocks;           // overlap-save blocks in this launch
+    void* scratch;          // [S*n_blocks][N] complex<T>
+    const void* hbig;       // [Na][Nb] H(f): row k1 holds bins k1 + Na*k2 in the row plan's hperm order
+    const void* twN;        // [N] exp(-j*2*pi*e/N) (four-step twiddles)
+    const void* twA;        // [Na] column-plan twiddles
+    const void* twB;        // [Nb] row-plan twiddles
+    void* out;              // [S][out_stride]
+    long long out_stride;
+};
+template <typename T> bool big_os_supported(int n);
+template <typename T> void big_os_shape(int n, int* Na, int* Nb);
+// position of true bin k in the permuted big-H table
+template <typename T> long long big_os_hperm_index(int n, long long k);
+template <typename T>
+cudaError_t launch_big_os(int n, int n_streams, const BigOsArgs<T>& a, cudaStream_t st);
+
+}  // namespace rr

@@ -1,0 +1,285 @@
+// Stand-alone stage kernels: NCO/mixer, gain, FIR decimator, zero-stuffing
+// interpolator, FM discriminator, strided copy.  Used when a chain cannot be
+// fused (large FFTs, long resampler kernels, FM chains) and as the reference
+// implementation of each stage on the device.  sm_100a.
+#include "rr_chain_os.cuh"
+
+namespace rr {
+
+// ---------------------------------------------------------------------------
+// FreqShifter hot loop, src/blocks/transform.rs:341-348, with phase_vec[idx]
+// (transform.rs:333-338) evaluated on the fly from the integer recurrence.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_freqshift(const cx<T>* __restrict__ in, long long in_stride,
+                                                   cx<T>* __restrict__ out, long long out_stride, long long len,
+                                                   const NcoStream* __restrict__ nco) {
+    const int s = blockIdx.y;
+    const NcoStream ns = nco[s];
+    const cx<T>* src = in + (long long)s * in_stride;
+    cx<T>* dst = out + (long long)s * out_stride;
+    const T start = (T)ns.start_phase;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < len; t += (long long)gridDim.x * blockDim.x) {
+        const uint32_t k = (uint32_t)(((unsigned long long)ns.idx + (unsigned long long)t) % ns.denom);
+        const uint32_t i = mulmod_u32(ns.numer_abs, k, ns.denom);
+        const cx<T> ph = nco_phasor<T>(i, ns.denom, ns.sign, start);
+        st_cx(&dst[t], cmul(ld_cx(&src[t]), ph));
+    }
+}
+
+__global__ void k_nco_advance(NcoStream* nco, int n_streams, long long len) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n_streams) {
+        const NcoStream ns = nco[s];
+        nco[s].idx = (uint32_t)(((unsigned long long)ns.idx + (unsigned long long)len) % ns.denom);
+    }
+}
+
+cudaError_t launch_nco_advance(NcoStream* nco, int n_streams, long long len, cudaStream_t st) {
+    k_nco_advance<<<(n_streams + 127) / 128, 128, 0, st>>>(nco, n_streams, len);
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_freqshift(const void* in, long long in_stride, void* out, long long out_stride, long long len,
+                             int n_streams, NcoStream* nco, cudaStream_t st) {
+    if (len <= 0) return cudaSuccess;
+    long long bx = (len + 255) / 256;
+    if (bx > 4096) bx = 4096;
+    dim3 grid((unsigned)bx, (unsigned)n_streams);
+    k_freqshift<T><<<grid, 256, 0, st>>>(reinterpret_cast<const cx<T>*>(in), in_stride, reinterpret_cast<cx<T>*>(out),
+                                         out_stride, len, nco);
+    k_nco_advance<<<(n_streams + 127) / 128, 128, 0, st>>>(nco, n_streams, len);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// GainControl, src/blocks/transform.rs:60-62
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_gain(const cx<T>* __restrict__ in, long long in_stride, cx<T>* __restrict__ out,
+                                              long long out_stride, long long len, T gain) {
+    const int s = blockIdx.y;
+    const cx<T>* src = in + (long long)s * in_stride;
+    cx<T>* dst = out + (long long)s * out_stride;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < len; t += (long long)gridDim.x * blockDim.x)
+        st_cx(&dst[t], cscale(ld_cx(&src[t]), gain));
+}
+template <typename T>
+cudaError_t launch_gain(const void* in, long long in_stride, void* out, long long out_stride, long long len,
+                        int n_streams, double gain, cudaStream_t st) {
+    if (len <= 0) return cudaSuccess;
+    long long bx = (len + 255) / 256;
+    if (bx > 4096) bx = 4096;
+    dim3 grid((unsigned)bx, (unsigned)n_streams);
+    k_gain<T><<<grid, 256, 0, st>>>(reinterpret_cast<const cx<T>*>(in), in_stride, reinterpret_cast<cx<T>*>(out),
+                                    out_stride, len, (T)gain);
+    return cudaGetLastError();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_copy2d(const cx<T>* __restrict__ in, long long in_stride,
+                                                cx<T>* __restrict__ out, long long out_stride, long long len) {
+    const int s = blockIdx.y;
+    const cx<T>* src = in + (long long)s * in_stride;
+    cx<T>* dst = out + (long long)s * out_stride;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < len; t += (long long)gridDim.x * blockDim.x)
+        st_cx(&dst[t], ld_cx(&src[t]));
+}
+template <typename T>
+cudaError_t launch_copy2d(const void* in, long long in_stride, void* out, long long out_stride, long long len,
+                          int n_streams, cudaStream_t st) {
+    if (len <= 0) return cudaSuccess;
+    long long bx = (len + 255) / 256;
+    if (bx > 4096) bx = 4096;
+    dim3 grid((unsigned)bx, (unsigned)n_streams);
+    k_copy2d<T><<<grid, 256, 0, st>>>(reinterpret_cast<const cx<T>*>(in), in_stride, reinterpret_cast<cx<T>*>(out),
+                                      out_stride, len);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// Downsampler hot loop, src/blocks/resampling.rs:103-121: one warp per output
+// sample, window over [tail | input].
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_downsample(const cx<T>* __restrict__ in, long long in_stride, long long len,
+                                                    const cx<T>* __restrict__ tail_in, const T* __restrict__ ir, int L,
+                                                    RateState rate, long long n_out, cx<T>* __restrict__ out,
+                                                    long long out_stride) {
+    const int s = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const long long o = (long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (o >= n_out) return;
+    const cx<T>* src = in + (long long)s * in_stride;
+    const cx<T>* tl = tail_in + (long long)s * (L - 1);
+    const long long m = rate.m0 + 1 + o;
+    const long long jm = (m * rate.P + rate.Q - 1) / rate.Q;
+    const long long first = jm - rate.j0 - L;  // index (in this push) of the oldest window sample
+    T ax = (T)0, ay = (T)0;
+    for (int t = lane; t < L; t += 32) {
+        const long long idx = first + t;
+        const cx<T> z = (idx < 0) ? ld_cx(&tl[(L - 1) + idx]) : ld_cx(&src[idx]);
+        const T h = ir[t];
+        ax = fma(z.x, h, ax);
+        ay = fma(z.y, h, ay);
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        ax += __shfl_xor_sync(0xffffffffu, ax, d);
+        ay += __shfl_xor_sync(0xffffffffu, ay, d);
+    }
+    if (lane == 0) st_cx(&out[(long long)s * out_stride + o], cx<T>(ax, ay));
+}
+
+// new tail = last L-1 samples of [tail_in | input]
+template <typename T>
+__global__ void k_tail_update(const cx<T>* __restrict__ in, long long in_stride, long long len,
+                              const cx<T>* __restrict__ tail_in, cx<T>* __restrict__ tail_out, int L) {
+    const int s = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L - 1) return;
+    const long long pos = len - (L - 1) + i;
+    const cx<T> v = (pos < 0) ? ld_cx(&tail_in[(long long)s * (L - 1) + (L - 1) + pos])
+                              : ld_cx(&in[(long long)s * in_stride + pos]);
+    st_cx(&tail_out[(long long)s * (L - 1) + i], v);
+}
+
+template <typename T>
+cudaError_t launch_downsample(const void* in, long long in_stride, long long len, const void* tail_in, void* tail_out,
+                              const T* ir, int L, RateState rate, long long n_out, void* out, long long out_stride,
+                              int n_streams, cudaStream_t st) {
+    if (n_out > 0) {
+        dim3 grid((unsigned)((n_out + 7) / 8), (unsigned)n_streams);
+        k_downsample<T><<<grid, 256, 0, st>>>(reinterpret_cast<const cx<T>*>(in), in_stride, len,
+                                              reinterpret_cast<const cx<T>*>(tail_in), ir, L, rate, n_out,
+                                              reinterpret_cast<cx<T>*>(out), out_stride);
+    }
+    if (L > 1) {
+        dim3 grid((unsigned)((L - 1 + 127) / 128), (unsigned)n_streams);
+        k_tail_update<T><<<grid, 128, 0, st>>>(reinterpret_cast<const cx<T>*>(in), in_stride, len,
+                                               reinterpret_cast<const cx<T>*>(tail_in),
+                                               reinterpret_cast<cx<T>*>(tail_out), L);
+    }
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// Upsampler, src/blocks/resampling.rs:238-267 in gather form: output q is the
+// carried partial sum plus sum_p x[p]*ir[q - q_p] over this push's inputs with
+// q_p = ceil(p*Q/P) in (q-L, q], accumulated in input order like the ring.
+// Outputs q >= m1 are the new carried partial sums.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_upsample(const cx<T>* __restrict__ in, long long in_stride, long long len,
+                                                  const cx<T>* __restrict__ acc_in, cx<T>* __restrict__ acc_out,
+                                                  const T* __restrict__ ir, int L, RateState rate, long long n_out,
+                                                  cx<T>* __restrict__ out, long long out_stride) {
+    const int s = blockIdx.y;
+    const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // output index relative to m0
+    if (o >= n_out + L) return;
+    const long long P = rate.P, Q = rate.Q;  // in/out = P/Q
+    const long long q = rate.m0 + o;
+    const cx<T>* src = in + (long long)s * in_stride;
+    cx<T> acc = (o < L) ? ld_cx(&acc_in[(long long)s * L + o]) : cx<T>((T)0, (T)0);
+    // inputs p (global index) with ceil(p*Q/P) <= q  <=>  p <= floor(q*P/Q)
+    long long p_hi = (q * P) / Q;
+    long long p_lo = (q - L < 0) ? rate.j0 : ((q - L) * P) / Q + 1;
+    if (p_lo < rate.j0) p_lo = rate.j0;
+    if (p_hi > rate.j0 + len - 1) p_hi = rate.j0 + len - 1;
+    for (long long p = p_lo; p <= p_hi; ++p) {
+        const long long qp = (p * Q + P - 1) / P;
+        const int t = (int)(q - qp);
+        if (t >= 0 && t < L) {
+            const cx<T> x = ld_cx(&src[p - rate.j0]);
+            const T h = ir[t];
+            acc.x = fma(x.x, h, acc.x);
+            acc.y = fma(x.y, h, acc.y);
+        }
+    }
+    if (o < n_out) st_cx(&out[(long long)s * out_stride + o], acc);
+    else st_cx(&acc_out[(long long)s * L + (o - n_out)], acc);
+}
+
+template <typename T>
+cudaError_t launch_upsample(const void* in, long long in_stride, long long len, const void* acc_in, void* acc_out,
+                            const T* ir, int L, RateState rate, long long n_out, void* out, long long out_stride,
+                            int n_streams, cudaStream_t st) {
+    const long long total = n_out + L;
+    dim3 grid((unsigned)((total + 255) / 256), (unsigned)n_streams);
+    k_upsample<T><<<grid, 256, 0, st>>>(reinterpret_cast<const cx<T>*>(in), in_stride, len,
+                                        reinterpret_cast<const cx<T>*>(acc_in), reinterpret_cast<cx<T>*>(acc_out), ir,
+                                        L, rate, n_out, reinterpret_cast<cx<T>*>(out), out_stride);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// FmDemod, src/blocks/modulation.rs:116-126
+// ---------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ T atan2_t(T y, T x);
+template <> __device__ __forceinline__ float atan2_t<float>(float y, float x) { return atan2f(y, x); }
+template <> __device__ __forceinline__ double atan2_t<double>(double y, double x) { return atan2(y, x); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_fmdemod(const cx<T>* __restrict__ in, long long in_stride,
+                                                 cx<T>* __restrict__ out, long long out_stride, long long len,
+                                                 const cx<T>* __restrict__ prev_sample,
+                                                 const cx<T>* __restrict__ last_output, int has_prev, T factor) {
+    const int s = blockIdx.y;
+    const cx<T>* src = in + (long long)s * in_stride;
+    cx<T>* dst = out + (long long)s * out_stride;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < len; t += (long long)gridDim.x * blockDim.x) {
+        cx<T> o;
+        if (t == 0 && !has_prev) {
+            o = ld_cx(&last_output[s]);  // repeat the previous output value (modulation.rs:119-124)
+        } else {
+            const cx<T> prev = (t == 0) ? ld_cx(&prev_sample[s]) : ld_cx(&src[t - 1]);
+            const cx<T> p = cmulc(ld_cx(&src[t]), prev);
+            o = cx<T>(atan2_t<T>(p.y, p.x) * factor, (T)0);
+        }
+        st_cx(&dst[t], o);
+    }
+}
+template <typename T>
+__global__ void k_fm_state(const cx<T>* __restrict__ in, long long in_stride, const cx<T>* __restrict__ out,
+                           long long out_stride, long long len, cx<T>* prev_sample, cx<T>* last_output, int n_streams) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n_streams) {
+        st_cx(&prev_sample[s], ld_cx(&in[(long long)s * in_stride + len - 1]));
+        st_cx(&last_output[s], ld_cx(&out[(long long)s * out_stride + len - 1]));
+    }
+}
+template <typename T>
+cudaError_t launch_fmdemod(const void* in, long long in_stride, void* out, long long out_stride, long long len,
+                           int n_streams, void* prev_sample, void* last_output, int has_prev, double factor,
+                           cudaStream_t st) {
+    if (len <= 0) return cudaSuccess;
+    long long bx = (len + 255) / 256;
+    if (bx > 4096) bx = 4096;
+    dim3 grid((unsigned)bx, (unsigned)n_streams);
+    k_fmdemod<T><<<grid, 256, 0, st>>>(reinterpret_cast<const cx<T>*>(in), in_stride, reinterpret_cast<cx<T>*>(out),
+                                       out_stride, len, reinterpret_cast<const cx<T>*>(prev_sample),
+                                       reinterpret_cast<const cx<T>*>(last_output), has_prev, (T)factor);
+    k_fm_state<T><<<(n_streams + 127) / 128, 128, 0, st>>>(
+        reinterpret_cast<const cx<T>*>(in), in_stride, reinterpret_cast<const cx<T>*>(out), out_stride, len,
+        reinterpret_cast<cx<T>*>(prev_sample), reinterpret_cast<cx<T>*>(last_output), n_streams);
+    return cudaGetLastError();
+}
+
+#define RR_INST(T)                                                                                                     \
+    template cudaError_t launch_freqshift<T>(const void*, long long, void*, long long, long long, int, NcoStream*,     \
+                                             cudaStream_t);                                                            \
+    template cudaError_t launch_gain<T>(const void*, long long, void*, long long, long long, int, double,              \
+                                        cudaStream_t);                                                                 \
+    template cudaError_t launch_copy2d<T>(const void*, long long, void*, long long, long long, int, cudaStream_t);     \
+    template cudaError_t launch_downsample<T>(const void*, long long, long long, const void*, void*, const T*, int,    \
+                                              RateState, long long, void*, long long, int, cudaStream_t);              \
+    template cudaError_t launch_upsample<T>(const void*, long long, long long, const void*, void*, const T*, int,      \
+                                            RateState, long long, void*, long long, int, cudaStream_t);                \
+    template cudaError_t launch_fmdemod<T>(const void*, long long, void*, long long, long long, int, void*, void*,     \
+                                           int, double, cudaStream_t);
+RR_INST(float)
+RR_INST(double)
+#undef RR_INST
+
+}  // namespace rr
