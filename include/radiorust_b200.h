@@ -184,6 +184,13 @@ int rr_chain_push_device(rr_chain* chain, double sample_rate, size_t chunk_len, 
                          size_t in_stride, void* dev_out, size_t out_capacity, size_t out_stride, size_t* out_count,
                          double* out_sample_rate);
 int rr_chain_sync(rr_chain* chain);
+/* Measurement aid: while enabled, CUDA events on the chain's stream bracket the
+ * dominant kernel of every push (no synchronisation is added).
+ * rr_chain_kernel_time waits for the recorded pairs and returns their summed
+ * duration, their count and the kernel's name; rr_chain_set_timing(.., 1)
+ * restarts the record. */
+int rr_chain_set_timing(rr_chain* chain, int enable);
+int rr_chain_kernel_time(rr_chain* chain, double* total_ms, int* n_launches, const char** kernel_name);
 /* raw cudaStream_t of the chain (for event timing by the caller) */
 void* rr_chain_cuda_stream(rr_chain* chain);
 /* name of the execution plan chosen at the last push (diagnostics), e.g.

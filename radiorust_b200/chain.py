@@ -305,6 +305,17 @@ class Chain:
     def sync(self):
         check(self._lib.rr_chain_sync(self._h))
 
+    def set_timing(self, enable: bool = True):
+        check(self._lib.rr_chain_set_timing(self._h, 1 if enable else 0))
+
+    def kernel_time(self):
+        """(total ms, launches, kernel name) of the dominant kernel since ``set_timing(True)``."""
+        ms = C.c_double()
+        cnt = C.c_int()
+        name = C.c_char_p()
+        check(self._lib.rr_chain_kernel_time(self._h, C.byref(ms), C.byref(cnt), C.byref(name)))
+        return ms.value, cnt.value, (name.value or b"").decode()
+
     @property
     def cuda_stream(self) -> int:
         return int(self._lib.rr_chain_cuda_stream(self._h) or 0)

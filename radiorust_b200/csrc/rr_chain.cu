@@ -192,7 +192,35 @@ struct rr_chain {
     cudaStream_t stream = nullptr;
     DevBuf host_in, host_out;  // device staging of rr_chain_push
     std::string plan;
+    // optional CUDA-event timing of the dominant kernel of a push (bench.py's roofline)
+    bool timing = false;
+    std::vector<cudaEvent_t> evs;  // pairs (start, stop), one per timed launch since rr_chain_set_timing
+    size_t ev_used = 0;
+    std::string timed_kernel;
+    int timing_begin() {
+        if (!timing) return 0;
+        if (ev_used + 2 > evs.size()) {
+            cudaEvent_t a = nullptr, b = nullptr;
+            if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return 0;
+            evs.push_back(a);
+            evs.push_back(b);
+        }
+        cudaEventRecord(evs[ev_used], stream);
+        return 1;
+    }
+    void timing_end(const char* name) {
+        cudaEventRecord(evs[ev_used + 1], stream);
+        ev_used += 2;
+        timed_kernel = name;
+    }
 };
+
+#define RR_TIMED_LAUNCH(c, name, n_kernels, expr)                        \
+    do {                                                                 \
+        const int t__ = (c)->timing_begin();                             \
+        RR_LAUNCH(n_kernels, expr);                                      \
+        if (t__) (c)->timing_end(name);                                  \
+    } while (0)
 
 namespace {
 
@@ -652,7 +680,7 @@ int run_push(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_chunks,
                         k.rate.Q = ds->h.Q;
                         k.rate.j0 = da.j0;
                         k.rate.m0 = da.m0;
-                        RR_LAUNCH(1, rr::launch_chain_os<T>((int)n, 1, S, 1, k, st));
+                        RR_TIMED_LAUNCH(c, "k_chain_os<epi=down>", 1, rr::launch_chain_os<T>((int)n, 1, S, 1, k, st));
                         ds->tail_cur ^= 1;
                         s.hist_cur ^= 1;
                         plan += "fused_os[filter+down]";
@@ -671,7 +699,7 @@ int run_push(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_chunks,
                             parts = want < total ? want : total;
                             if (parts < 1) parts = 1;
                         }
-                        RR_LAUNCH(1, rr::launch_chain_os<T>((int)n, 0, S, parts, k, st));
+                        RR_TIMED_LAUNCH(c, "k_chain_os<epi=none>", 1, rr::launch_chain_os<T>((int)n, 0, S, parts, k, st));
                         s.hist_cur ^= 1;
                         cur.p = d.p;
                         cur.stride = d.stride;
@@ -992,6 +1020,7 @@ int rr_chain_destroy(rr_chain* c) {
     }
     c->host_in.release();
     c->host_out.release();
+    for (cudaEvent_t e : c->evs) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return RR_OK;
@@ -1144,6 +1173,28 @@ int rr_chain_sync(rr_chain* c) {
     if (!c) return fail(RR_ERR_INVALID, "null chain");
     RR_CUDA(cudaSetDevice(c->ctx->device));
     RR_CUDA(cudaStreamSynchronize(c->stream));
+    return RR_OK;
+}
+int rr_chain_set_timing(rr_chain* c, int enable) {
+    if (!c) return fail(RR_ERR_INVALID, "null chain");
+    RR_CUDA(cudaSetDevice(c->ctx->device));
+    c->timing = enable != 0;
+    c->ev_used = 0;
+    return RR_OK;
+}
+int rr_chain_kernel_time(rr_chain* c, double* total_ms, int* n_launches, const char** kernel_name) {
+    if (!c || !total_ms) return fail(RR_ERR_INVALID, "null argument");
+    RR_CUDA(cudaSetDevice(c->ctx->device));
+    double sum = 0.0;
+    for (size_t i = 0; i + 1 < c->ev_used; i += 2) {
+        float ms = 0.f;
+        RR_CUDA(cudaEventSynchronize(c->evs[i + 1]));
+        RR_CUDA(cudaEventElapsedTime(&ms, c->evs[i], c->evs[i + 1]));
+        sum += ms;
+    }
+    *total_ms = sum;
+    if (n_launches) *n_launches = (int)(c->ev_used / 2);
+    if (kernel_name) *kernel_name = c->timed_kernel.c_str();
     return RR_OK;
 }
 void* rr_chain_cuda_stream(rr_chain* c) { return c ? (void*)c->stream : nullptr; }
