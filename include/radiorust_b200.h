@@ -184,6 +184,11 @@ int rr_chain_push_device(rr_chain* chain, double sample_rate, size_t chunk_len, 
                          size_t in_stride, void* dev_out, size_t out_capacity, size_t out_stride, size_t* out_count,
                          double* out_sample_rate);
 int rr_chain_sync(rr_chain* chain);
+/* The polyphase fused Filter -> Downsampler kernel is used whenever the chain
+ * allows it; enable = 0 forces the stateful overlap-save path (same results
+ * within rounding; for tests and comparisons).  Env RR_DISABLE_POLY=1 sets the
+ * default to off. */
+int rr_chain_set_fast_path(rr_chain* chain, int enable);
 /* Measurement aid: while enabled, CUDA events on the chain's stream bracket the
  * dominant kernel of every push (no synchronisation is added).
  * rr_chain_kernel_time waits for the recorded pairs and returns their summed

@@ -50,6 +50,10 @@ def translation_units():
         ("rr_chain_os_dispatch.o", "rr_chain_os_dispatch.cu", []),
         ("rr_poly.o", "rr_poly.cu", []),
     ]
+    for t, tn in (("float", "f32"), ("double", "f64")):
+        for k in (256, 512, 1024):
+            for g in (8, 10):
+                tus.append((f"rr_poly_{tn}_{k}_{g}.o", "rr_poly_inst.cu", [f"-DRR_T={t}", f"-DRR_K={k}", f"-DRR_G={g}"]))
     for n in F32_SIZES:
         tus.append((f"rr_chain_os_f32_{n}.o", "rr_chain_os_inst.cu", ["-DRR_T=float", f"-DRR_N={n}"]))
     for n in F64_SIZES:

@@ -305,6 +305,9 @@ class Chain:
     def sync(self):
         check(self._lib.rr_chain_sync(self._h))
 
+    def set_fast_path(self, enable: bool = True):
+        check(self._lib.rr_chain_set_fast_path(self._h, 1 if enable else 0))
+
     def set_timing(self, enable: bool = True):
         check(self._lib.rr_chain_set_timing(self._h, 1 if enable else 0))
 

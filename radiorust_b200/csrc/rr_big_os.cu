@@ -20,7 +20,7 @@ constexpr int kColG = 8;
 
 template <typename T, int NA>
 __global__ void __launch_bounds__(PlanFor<T, NA, kColG>::type::NT* kColG)
-k_big_cols_fwd(const cx<T>* __restrict__ in, long long in_stride, const cx<T>* __restrict__ hist, int first_chunk, int n_blocks,
+k_big_cols_fwd(const cx<T>* __restrict__ in, long long in_stride, const cx<T>* __restrict__ hist, long long hist_stride, int first_chunk, int n_blocks,
                int Nb, cx<T>* __restrict__ scratch, const cx<T>* __restrict__ twN, const cx<T>* __restrict__ twA) {
     using P = typename PlanFor<T, NA, kColG>::type;
     constexpr int NT = P::NT, R1 = P::R1, B1 = P::B1, S1 = P::S1;
@@ -33,7 +33,7 @@ k_big_cols_fwd(const cx<T>* __restrict__ in, long long in_stride, const cx<T>* _
     // window = [chunk c-1 | chunk c]; chunk -1 is the stored history (filters.rs:241-243)
     const int c = first_chunk + b;
     const cx<T>* cur = in + (long long)s * in_stride + (long long)c * n;
-    const cx<T>* prev = (c > 0) ? cur - n : hist + (long long)s * n;
+    const cx<T>* prev = (c > 0) ? cur - n : hist + (long long)s * hist_stride;
     const int col = blockIdx.x * kColG + g;
 
     P plan;
@@ -190,7 +190,7 @@ template <typename T, int NA> static cudaError_t launch_cols(bool fwd, int Nb, i
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         k<<<grid, P::NT * kColG, smem, st>>>(reinterpret_cast<const cx<T>*>(a.in), a.in_stride, reinterpret_cast<const cx<T>*>(a.hist),
-                                             a.first_chunk, a.n_blocks, Nb, reinterpret_cast<cx<T>*>(a.scratch),
+                                             a.hist_stride, a.first_chunk, a.n_blocks, Nb, reinterpret_cast<cx<T>*>(a.scratch),
                                              reinterpret_cast<const cx<T>*>(a.twN), reinterpret_cast<const cx<T>*>(a.twA));
     } else {
         auto k = k_big_cols_inv<T, NA>;

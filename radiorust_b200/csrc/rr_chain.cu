@@ -15,7 +15,9 @@
 #include <atomic>
 #include <cmath>
 #include <complex>
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <numeric>
@@ -115,7 +117,7 @@ struct StageHost {
     // FILTER
     double f_sr = NAN;
     size_t f_n = 0;
-    bool f_has_hist = false;
+    int f_seg = 0;  // chunks received in the current segment (since start / redesign / interrupt), saturates at 2
     bool f_dirty = true;
     // RESAMPLERS
     double r_in_rate = NAN;
@@ -137,6 +139,7 @@ struct StageAct {
     size_t pending_before = 0;
     long long j0 = 0, m0 = 0;  // resampler counters before the push
     bool nco_recalc = false;
+    int seg_before = 0;        // filter: chunks of the current segment seen before this push
     Shape out;
 };
 
@@ -165,13 +168,23 @@ struct Stage {
     std::vector<rr::NcoStream> nco_stage;  // upload staging
     DevBuf nco_d;
     // FILTER
-    DevBuf hperm, tw, hist[2];
+    DevBuf hperm, tw;
+    DevBuf hist2[2];  // [S][2n] post-NCO samples preceding the next push (older chunk | newer chunk), ping-pong
     int hist_cur = 0;
+    DevBuf ztmp;      // filter-output scratch of the unfused stateful path
+    std::vector<std::complex<double>> taps;  // windowed impulse response (Flt-rounded), for the polyphase tables
+    bool taps_valid = false;
     // big overlap-save tables
     DevBuf big_h, big_twA, big_twB, big_scratch;
     // RESAMPLERS
     DevBuf ir, tail[2], obuf[2];
     int tail_cur = 0, obuf_cur = 0;
+    std::vector<double> ir_host_flt;  // taps as rounded to Flt
+    bool ztail_stale = false;  // the polyphase path ran: tail[] must be rebuilt from the filter's hist2 before reuse
+    // polyphase tables of the fused Filter -> Downsampler path (rebuilt when either block is redesigned)
+    DevBuf gtab, twK;
+    bool poly_valid = false, poly_tried = false;
+    int poly_K = 0, poly_G = 0, poly_Lmax = 0, poly_V = 0;
     size_t obuf_cap = 0;  // samples per stream in obuf
     std::vector<double> ir_host;
     // FMDEMOD
@@ -192,6 +205,7 @@ struct rr_chain {
     cudaStream_t stream = nullptr;
     DevBuf host_in, host_out;  // device staging of rr_chain_push
     std::string plan;
+    bool allow_poly = true;  // rr_chain_set_fast_path
     // optional CUDA-event timing of the dominant kernel of a push (bench.py's roofline)
     bool timing = false;
     std::vector<cudaEvent_t> evs;  // pairs (start, stop), one per timed launch since rr_chain_set_timing
@@ -255,11 +269,12 @@ int advance_stage(const rr_stage_desc& d, StageHost& h, const Shape& in, StageAc
                 h.f_dirty = false;
                 h.f_sr = in.rate;
                 h.f_n = in.chunk_len;
-                h.f_has_hist = false;
+                h.f_seg = 0;
             }
-            a.first_is_history = !h.f_has_hist;  // filters.rs:240,260
+            a.seg_before = h.f_seg;
+            a.first_is_history = (h.f_seg == 0);  // filters.rs:240,260
             a.out.n_chunks = in.n_chunks - (a.first_is_history ? 1 : 0);
-            h.f_has_hist = true;
+            h.f_seg = (int)std::min<size_t>(2, (size_t)h.f_seg + in.n_chunks);
             break;
         }
         case RR_STAGE_DOWNSAMPLE:
@@ -425,7 +440,7 @@ template <typename T> int filter_redesign(rr_chain* c, Stage& s, double sample_r
     };
     rr::WindowFn w = make_window(d.window_kind, d.window_beta, d.window_fn, d.window_user);
     std::vector<std::complex<double>> H;
-    if (!rr::design_filter_response(f, w, sample_rate, n, sizeof(T) == 4, &H))
+    if (!rr::design_filter_response(f, w, sample_rate, n, sizeof(T) == 4, &H, &s.taps))
         return fail(RR_ERR_UNSUPPORTED, "Filter: design failed");
     const size_t N = 2 * n;
     if (rr::chain_os_supported<T>((int)n, 0, 0)) {
@@ -449,9 +464,10 @@ template <typename T> int filter_redesign(rr_chain* c, Stage& s, double sample_r
     } else {
         return fail(RR_ERR_UNSUPPORTED, "Filter: chunk length not supported by the device path");
     }
-    const size_t hb = (size_t)c->S * n * 2 * sizeof(T);
-    RR_TRY(s.hist[0].ensure(hb));
-    RR_TRY(s.hist[1].ensure(hb));
+    const size_t hb = (size_t)c->S * 2 * n * 2 * sizeof(T);
+    RR_TRY(s.hist2[0].ensure(hb));
+    RR_TRY(s.hist2[1].ensure(hb));
+    s.taps_valid = true;
     return RR_OK;
 }
 
@@ -465,6 +481,8 @@ template <typename T> int resampler_redesign(rr_chain* c, Stage& s, double in_ra
     const double null_bin = (double)L * margin / (down ? in_rate : d.output_rate);
     rr::design_resampler_taps((size_t)L, ratio, null_bin, &s.ir_host);
     RR_TRY(upload_real<T>(s.ir, s.ir_host, c->stream));
+    s.ir_host_flt.resize(s.ir_host.size());
+    for (size_t i = 0; i < s.ir_host.size(); ++i) s.ir_host_flt[i] = (double)(T)s.ir_host[i];
     // ring buffer / accumulators restart at zero (resampling.rs:99-101, :234-236)
     const size_t state_len = down ? (size_t)(L > 1 ? L - 1 : 1) : (size_t)L;
     const size_t tb = (size_t)c->S * state_len * 2 * sizeof(T);
@@ -473,6 +491,9 @@ template <typename T> int resampler_redesign(rr_chain* c, Stage& s, double in_ra
         RR_CUDA(cudaMemsetAsync(s.tail[k].p, 0, tb, c->stream));
     }
     s.tail_cur = 0;
+    s.ztail_stale = false;
+    s.poly_valid = false;
+    s.poly_tried = false;
     return RR_OK;
 }
 
@@ -551,6 +572,296 @@ int resampler_emit(rr_chain* c, Stage& s, const StageAct& a, bool last, void* us
     return RR_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Filter (+ Downsampler) execution.  Three device paths:
+//   poly      NCO -> Filter -> Downsampler fused, polyphase (rr_poly.cuh): the
+//             throughput path; needs two chunks of in-segment history
+//   fused_os  NCO -> overlap-save (-> FIR decimator) per stream in one CTA
+//             (rr_chain_os.cuh): the stateful path, any segment position
+//   big_os    four-step FFT overlap-save for long chunks (rr_big_os.cu)
+// State shared by all of them: hist2 (two post-NCO chunks) on the filter stage
+// and tail (the last L-1 filter outputs) on the downsampler stage.
+// ---------------------------------------------------------------------------
+struct FilterIo {
+    const void* in = nullptr;  // pushed samples (pre-NCO when nco != nullptr)
+    long long in_stride = 0;
+    size_t n = 0, n_chunks = 0;
+    Stage* nco = nullptr;
+};
+
+// run the stand-alone NCO kernel over chunks [c0, c0+k) into the NCO stage's buffer
+template <typename T> int materialize_nco(rr_chain* c, Stage& nco, const FilterIo& io, size_t c0, size_t k, const void** out, long long* stride) {
+    const size_t len = k * io.n;
+    RR_TRY(out_reserve<T>(c, nco, len));
+    const char* src = (const char*)io.in + c0 * io.n * 2 * sizeof(T);
+    RR_LAUNCH(1, rr::launch_freqshift<T>(src, io.in_stride, nco.out.p, (long long)nco.out_cap, (long long)len, c->S,
+                                         (const rr::NcoStream*)nco.nco_d.p, (long long)(c0 * io.n), c->stream));
+    *out = nco.out.p;
+    *stride = (long long)nco.out_cap;
+    return RR_OK;
+}
+
+// Overlap-save over the first k chunks of the push; history for chunk 0 is
+// hist2's newer half; `fih`: chunk 0 only primes the filter (filters.rs:240,260).
+// Writes (k - fih) * n filter outputs to dst.
+template <typename T>
+int run_os(rr_chain* c, Stage& s, const FilterIo& io, size_t k, bool fih, void* dst, long long dst_stride) {
+    const size_t n = io.n;
+    const int S = c->S;
+    if (k == 0) return RR_OK;
+    const char* hist_newer = (const char*)s.hist2[s.hist_cur].p + n * 2 * sizeof(T);
+    if (rr::chain_os_supported<T>((int)n, 0, 0)) {
+        rr::ChainOsArgs<T> a{};
+        a.in = io.in;
+        a.in_stride = io.in_stride;
+        a.n_chunks = (int)k;
+        a.first_is_history = fih ? 1 : 0;
+        a.emit = 1;
+        a.hist_in = hist_newer;
+        a.hist_stride = (long long)(2 * n);
+        a.hist_out = nullptr;
+        a.hperm = s.hperm.p;
+        a.twN = s.tw.p;
+        a.nco = io.nco ? (const rr::NcoStream*)io.nco->nco_d.p : nullptr;
+        a.nco_offset = 0;
+        a.out = dst;
+        a.out_stride = dst_stride;
+        int parts = 1;
+        const int total = a.n_chunks - a.first_is_history;
+        if (total > 1) {
+            const int want = (2 * c->ctx->sm_count + S - 1) / S;
+            parts = want < total ? want : total;
+            if (parts < 1) parts = 1;
+        }
+        RR_TIMED_LAUNCH(c, "k_chain_os<epi=none>", 1, rr::launch_chain_os<T>((int)n, 0, S, parts, a, c->stream));
+        return RR_OK;
+    }
+    if (!rr::big_os_supported<T>((int)n)) return fail(RR_ERR_UNSUPPORTED, "Filter: chunk length not supported by the device path");
+    const void* src = io.in;
+    long long src_stride = io.in_stride;
+    if (io.nco) RR_TRY(materialize_nco<T>(c, *io.nco, io, 0, k, &src, &src_stride));  // the four-step kernels take mixed samples
+    const size_t N = 2 * n;
+    const size_t first = fih ? 1 : 0;  // first chunk that produces output
+    const size_t n_blocks = k - first;
+    if (n_blocks == 0) return RR_OK;
+    size_t max_blocks = ((size_t)48 << 20) / (N * 2 * sizeof(T));  // keep the scratch L2 resident
+    if (max_blocks < 1) max_blocks = 1;
+    size_t per_launch = max_blocks / (size_t)S;
+    if (per_launch < 1) per_launch = 1;
+    if (per_launch > n_blocks) per_launch = n_blocks;
+    RR_TRY(s.big_scratch.ensure((size_t)S * per_launch * N * 2 * sizeof(T)));
+    for (size_t b0 = 0; b0 < n_blocks; b0 += per_launch) {
+        const size_t nb = std::min(per_launch, n_blocks - b0);
+        rr::BigOsArgs<T> a{};
+        a.in = src;
+        a.in_stride = src_stride;
+        a.hist = hist_newer;
+        a.hist_stride = (long long)(2 * n);
+        a.first_chunk = (int)(first + b0);
+        a.n_blocks = (int)nb;
+        a.scratch = s.big_scratch.p;
+        a.hbig = s.big_h.p;
+        a.twN = s.tw.p;
+        a.twA = s.big_twA.p;
+        a.twB = s.big_twB.p;
+        a.out = (char*)dst + b0 * n * 2 * sizeof(T);
+        a.out_stride = dst_stride;
+        RR_TIMED_LAUNCH(c, "k_big_os(3 kernels)", 3, rr::launch_big_os<T>((int)n, S, a, c->stream));
+    }
+    return RR_OK;
+}
+
+// rebuild the downsampler's tail (last L-1 filter outputs) from the filter's hist2
+template <typename T> int regen_ztail(rr_chain* c, Stage& f, Stage& ds) {
+    if (!ds.ztail_stale) return RR_OK;
+    const size_t n = f.h.f_n;
+    const int L = ds.h.r_L;
+    if (L > 1) {
+        DevBuf& tmp = f.ztmp;
+        RR_TRY(tmp.ensure((size_t)c->S * n * 2 * sizeof(T)));
+        FilterIo io;
+        io.in = f.hist2[f.hist_cur].p;
+        io.in_stride = (long long)(2 * n);
+        io.n = n;
+        io.n_chunks = 2;
+        io.nco = nullptr;
+        RR_TRY(run_os<T>(c, f, io, 2, true, tmp.p, (long long)n));
+        const char* src = (const char*)tmp.p + (n - (size_t)(L - 1)) * 2 * sizeof(T);
+        RR_LAUNCH(1, rr::launch_copy2d<T>(src, (long long)n, ds.tail[ds.tail_cur].p, (long long)(L - 1), (long long)(L - 1), c->S, c->stream));
+    }
+    ds.ztail_stale = false;
+    return RR_OK;
+}
+
+// (re)build the polyphase tables for the pair (filter f, downsampler ds)
+template <typename T> int poly_prepare(rr_chain* c, Stage& f, Stage& ds) {
+    if (ds.poly_tried) return RR_OK;
+    ds.poly_tried = true;
+    ds.poly_valid = false;
+    if (!f.taps_valid) return RR_OK;
+    const long long P = ds.h.P, Q = ds.h.Q;
+    const long long n = (long long)f.h.f_n, L = ds.h.r_L;
+    if (Q > 4 || P < 2 || L - 1 > n || L < 2) return RR_OK;
+    const long long Lmax = (n + L - 2) / P;
+    int bestK = 0;
+    double best = 0.0;
+    for (int K : {256, 512, 1024}) {
+        const long long V = K - 1 - Lmax;
+        if (V < K / 4) continue;
+        double cost = (5.0 * std::log2((double)K) + 8.0 * (double)Q + 8.0) * (double)K / (double)V;
+        if (K == 1024) cost *= 1.1;  // larger working set: only when clearly better
+        if (bestK == 0 || cost < best) {
+            bestK = K;
+            best = cost;
+        }
+    }
+    if (bestK == 0) return RR_OK;
+    const size_t tab_bytes = (size_t)(Q * P) * (size_t)bestK * 2 * sizeof(T);
+    if (tab_bytes > ((size_t)512 << 20)) return RR_OK;
+    const double e8 = (double)P / (8.0 * (double)((P + 7) / 8)), e10 = (double)P / (10.0 * (double)((P + 9) / 10));
+    const int G = e10 > e8 + 1e-9 ? 10 : 8;
+    if (!rr::poly_supported<T>(bestK, (int)Q, G)) return RR_OK;
+    std::vector<std::complex<double>> tab, perm;
+    const int lm = rr::design_poly_tables(f.taps, ds.ir_host_flt, P, Q, bestK, &tab);
+    if (lm != (int)Lmax) return fail(RR_ERR_INVALID, "internal: polyphase reach mismatch");
+    // f.taps carry the 1/(2n) of the reference's unnormalised 2n-point inverse (filters.rs:186); the
+    // kernel's K-point forward/inverse pair is unnormalised too: rescale by 2n / K
+    const double scale = 2.0 * (double)n / (double)bestK;
+    perm.resize(tab.size());
+    for (long long qp = 0; qp < Q * P; ++qp)
+        for (int k = 0; k < bestK; ++k)
+            perm[(size_t)qp * bestK + (size_t)rr::poly_hperm_index<T>(bestK, k)] = tab[(size_t)qp * bestK + k] * scale;
+    RR_TRY(upload_complex<T>(ds.gtab, perm, c->stream));
+    std::vector<std::complex<double>> tw;
+    rr::make_twiddles((size_t)bestK, &tw);
+    RR_TRY(upload_complex<T>(ds.twK, tw, c->stream));
+    ds.poly_K = bestK;
+    ds.poly_G = G;
+    ds.poly_Lmax = (int)Lmax;
+    ds.poly_V = (int)(bestK - 1 - Lmax);
+    ds.poly_valid = true;
+    return RR_OK;
+}
+
+// Filter stage `f` (with optional folded NCO) followed by Downsampler `ds`:
+// consumes the whole push, leaves new outputs behind ds's pending samples.
+template <typename T>
+int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const StageAct& fa, const StageAct& da, std::string* plan) {
+    const size_t n = io.n;
+    const int S = c->S;
+    cudaStream_t st = c->stream;
+    const int L = ds.h.r_L;
+    void* obase = (char*)ds.obuf[ds.obuf_cur].p + da.pending_before * 2 * sizeof(T);
+    const long long ostride = (long long)ds.obuf_cap;
+
+    if (c->allow_poly) RR_TRY(poly_prepare<T>(c, f, ds));
+    // chunks the stateful path must take: those whose outputs still depend on pre-segment state
+    size_t ca = io.n_chunks;
+    if (c->allow_poly && ds.poly_valid) {
+        const size_t need = (size_t)(2 - std::min(2, fa.seg_before));
+        ca = std::min(need, io.n_chunks);
+    }
+    const size_t fih = fa.first_is_history ? 1 : 0;
+
+    // ---- stateful part: chunks [0, ca) ------------------------------------------
+    long long j0 = da.j0, m0 = da.m0;  // decimator counters at the start of the part being processed
+    if (ca > fih) {
+        const long long zlen = (long long)((ca - fih) * n);
+        const long long tot = floordiv128(j0 + zlen, ds.h.Q, ds.h.P);
+        const long long n_out = tot - m0;
+        if (rr::chain_os_supported<T>((int)n, 1, L)) {
+            rr::ChainOsArgs<T> a{};
+            a.in = io.in;
+            a.in_stride = io.in_stride;
+            a.n_chunks = (int)ca;
+            a.first_is_history = (int)fih;
+            a.emit = 1;
+            a.hist_in = (const char*)f.hist2[f.hist_cur].p + n * 2 * sizeof(T);
+            a.hist_stride = (long long)(2 * n);
+            a.hist_out = nullptr;
+            a.hperm = f.hperm.p;
+            a.twN = f.tw.p;
+            a.nco = io.nco ? (const rr::NcoStream*)io.nco->nco_d.p : nullptr;
+            a.nco_offset = 0;
+            a.out = obase;
+            a.out_stride = ostride;
+            a.ir = (const T*)ds.ir.p;
+            a.L = L;
+            a.ztail_in = ds.tail[ds.tail_cur].p;
+            a.ztail_out = ds.tail[ds.tail_cur ^ 1].p;
+            a.rate.P = ds.h.P;
+            a.rate.Q = ds.h.Q;
+            a.rate.j0 = j0;
+            a.rate.m0 = m0;
+            RR_TIMED_LAUNCH(c, "k_chain_os<epi=down>", 1, rr::launch_chain_os<T>((int)n, 1, S, 1, a, st));
+            ds.tail_cur ^= 1;
+            *plan += "fused_os[filter+down]";
+        } else {
+            RR_TRY(f.ztmp.ensure((size_t)S * (size_t)zlen * 2 * sizeof(T)));
+            RR_TRY(run_os<T>(c, f, io, ca, fih != 0, f.ztmp.p, zlen));
+            rr::RateState rs;
+            rs.P = ds.h.P;
+            rs.Q = ds.h.Q;
+            rs.j0 = j0;
+            rs.m0 = m0;
+            RR_LAUNCH(2, rr::launch_downsample<T>(f.ztmp.p, zlen, zlen, ds.tail[ds.tail_cur].p, ds.tail[ds.tail_cur ^ 1].p, (const T*)ds.ir.p,
+                                                  L, rs, n_out, obase, ostride, S, st));
+            ds.tail_cur ^= 1;
+            *plan += rr::chain_os_supported<T>((int)n, 0, 0) ? "fused_os[filter]|downsample" : "big_os|downsample";
+        }
+        obase = (char*)obase + (size_t)n_out * 2 * sizeof(T);
+        j0 = (j0 + zlen) % ds.h.P;
+        m0 = floordiv128(j0, ds.h.Q, ds.h.P);
+    }
+
+    // ---- polyphase part: chunks [ca, n_chunks) ----------------------------------------
+    if (ca < io.n_chunks) {
+        const long long Pq = ds.h.P, Qq = ds.h.Q;
+        const long long zlen = (long long)((io.n_chunks - ca) * n);  // filter outputs covered by this part
+        // outputs m (1-based, counted with the reduced counters) firing inside this part
+        const long long m_lo = m0 + 1;
+        const long long m_hi = floordiv128(j0 + zlen, Qq, Pq);
+        if (m_hi >= m_lo) {
+            rr::PolyArgs<T> a{};
+            // filter output k aligns with push sample k; the part starts at push sample ca*n, and the
+            // kernel reads the (mixed on the fly) push chunks before it, or hist2 below offset 0
+            a.in = io.in;
+            a.in_stride = io.in_stride;
+            a.len = (long long)(io.n_chunks * n);
+            a.n = (long long)n;
+            a.nco = io.nco ? (const rr::NcoStream*)io.nco->nco_d.p : nullptr;
+            a.gtab = ds.gtab.p;
+            a.twK = ds.twK.p;
+            a.P = Pq;
+            a.Q = Qq;
+            a.Lmax = ds.poly_Lmax;
+            a.V = ds.poly_V;
+            a.J0 = j0 - (long long)(ca * n);  // counters referred to push sample 0 (may be negative)
+            a.m0 = m0;
+            a.m_lo = m_lo;
+            a.m_hi = m_hi;
+            a.I_lo = m_lo / Qq;
+            const long long I_hi = m_hi / Qq;
+            a.n_blocks = (int)((I_hi - a.I_lo) / a.V + 1);
+            // blocks per CTA: one round of inverse transforms (G jobs) when the grid stays large enough
+            int nbpc = std::max(1, ds.poly_G / (int)Qq);
+            while (nbpc > 1 && rr::poly_smem_bytes<T>(ds.poly_K, (int)Qq, ds.poly_G, nbpc) > (size_t)100 * 1024) --nbpc;
+            while (nbpc > 1 && (long long)S * ((a.n_blocks + nbpc - 1) / nbpc) < 2LL * c->ctx->sm_count) --nbpc;
+            const int nsb = (a.n_blocks + nbpc - 1) / nbpc;
+            nbpc = (a.n_blocks + nsb - 1) / nsb;  // balance
+            a.nbpc = nbpc;
+            a.out = obase;
+            a.out_stride = ostride;
+            a.hist2 = f.hist2[f.hist_cur].p;
+            RR_TIMED_LAUNCH(c, "k_poly", 1, rr::launch_poly<T>(ds.poly_K, (int)Qq, ds.poly_G, S, a, st));
+        }
+        ds.ztail_stale = true;
+        if (!plan->empty() && plan->back() != '+' && plan->back() != '|' && ca > 0) *plan += "|";
+        *plan += "poly[filter+down]";
+    }
+    return RR_OK;
+}
+
 template <typename T>
 int run_push(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_chunks, const void* dev_in, size_t in_stride, void* dev_out,
              size_t out_capacity, size_t out_stride, size_t* out_count, double* out_rate) {
@@ -586,6 +897,19 @@ int run_push(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_chunks,
     for (int i = 0; i < ns; ++i) {
         Stage& s = c->st[i];
         const bool last = (i == ns - 1);
+        // the Filter needs its pre-redesign state once more when a polyphase push left the decimator tail stale
+        if (s.d.kind == RR_STAGE_FILTER && !last && c->st[i + 1].d.kind == RR_STAGE_DOWNSAMPLE && c->st[i + 1].ztail_stale &&
+            cur.sh.n_chunks > 0) {
+            StageHost probe = s.h;
+            StageAct pa;
+            RR_TRY(advance_stage(s.d, probe, cur.sh, &pa));
+            StageHost dprobe = c->st[i + 1].h;
+            StageAct dpa;
+            int r = advance_stage(c->st[i + 1].d, dprobe, pa.out, &dpa);
+            const bool ds_redesign = (r == RR_OK) && dpa.redesign;
+            if (ds_redesign) c->st[i + 1].ztail_stale = false;  // the ring restarts from zero anyway
+            else if (pa.redesign || pa.first_is_history || !c->allow_poly) RR_TRY(regen_ztail<T>(c, s, c->st[i + 1]));
+        }
         StageAct a;
         RR_TRY(advance_stage(s.d, s.h, cur.sh, &a));
         if (!a.active) {
@@ -597,21 +921,23 @@ int run_push(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_chunks,
         switch (s.d.kind) {
             case RR_STAGE_FREQSHIFT: {
                 RR_TRY(nco_refresh<T>(c, s, cur.sh.rate, a.nco_recalc));
-                const bool fuse = !last && c->st[i + 1].d.kind == RR_STAGE_FILTER && cur.sh.chunk_len >= 32 &&
-                                  (cur.sh.chunk_len & (cur.sh.chunk_len - 1)) == 0 &&
-                                  rr::chain_os_supported<T>((int)cur.sh.chunk_len, 0, 0);
+                const size_t n = cur.sh.chunk_len;
+                const bool fuse = !last && c->st[i + 1].d.kind == RR_STAGE_FILTER && n >= 32 && (n & (n - 1)) == 0 &&
+                                  (rr::chain_os_supported<T>((int)n, 0, 0) || rr::big_os_supported<T>((int)n));
                 if (fuse) {
                     pending_nco = &s;
                     plan += "nco+";
                 } else {
                     Dest d;
                     RR_TRY(pick_dest<T>(c, s, last, dev_out, (long long)out_stride, (size_t)len, &d));
-                    RR_LAUNCH(2, rr::launch_freqshift<T>(cur.p, cur.stride, d.p, d.stride, len, S, (rr::NcoStream*)s.nco_d.p, st));
+                    RR_LAUNCH(1, rr::launch_freqshift<T>(cur.p, cur.stride, d.p, d.stride, len, S, (const rr::NcoStream*)s.nco_d.p, 0, st));
+                    RR_LAUNCH(1, rr::launch_nco_advance((rr::NcoStream*)s.nco_d.p, S, len, st));
                     nco_host_advance(s, len);
                     cur.p = d.p;
                     cur.stride = d.stride;
                     plan += "freqshift";
                 }
+                cur.sh = a.out;
                 break;
             }
             case RR_STAGE_GAIN: {
@@ -620,6 +946,7 @@ int run_push(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_chunks,
                 RR_LAUNCH(1, rr::launch_gain<T>(cur.p, cur.stride, d.p, d.stride, len, S, s.d.gain, st));
                 cur.p = d.p;
                 cur.stride = d.stride;
+                cur.sh = a.out;
                 plan += "gain";
                 break;
             }
@@ -633,127 +960,58 @@ int run_push(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_chunks,
                                                    a.first_is_history ? 0 : 1, factor, st));
                 cur.p = d.p;
                 cur.stride = d.stride;
+                cur.sh = a.out;
                 plan += "fmdemod";
                 break;
             }
             case RR_STAGE_FILTER: {
                 const size_t n = cur.sh.chunk_len;
-                if (a.redesign) RR_TRY(filter_redesign<T>(c, s, cur.sh.rate, n));
-                const bool small = rr::chain_os_supported<T>((int)n, 0, 0);
-                Stage* nco = pending_nco;
+                if (a.redesign) {
+                    RR_TRY(filter_redesign<T>(c, s, cur.sh.rate, n));
+                    if (!last && c->st[i + 1].d.kind == RR_STAGE_DOWNSAMPLE) {
+                        c->st[i + 1].poly_valid = false;
+                        c->st[i + 1].poly_tried = false;
+                    }
+                }
+                FilterIo io;
+                io.in = cur.p;
+                io.in_stride = cur.stride;
+                io.n = n;
+                io.n_chunks = cur.sh.n_chunks;
+                io.nco = pending_nco;
                 pending_nco = nullptr;
-                if (small) {
-                    // try to fold the following Downsampler into the epilogue
-                    bool fuse_down = false;
+                Stage* ds = (!last && c->st[i + 1].d.kind == RR_STAGE_DOWNSAMPLE) ? &c->st[i + 1] : nullptr;
+                bool took_ds = false;
+                if (ds && a.out.n_chunks > 0) {
+                    // Filter -> Downsampler handled together (fused kernels)
                     StageAct da;
-                    Stage* ds = nullptr;
-                    if (!last && c->st[i + 1].d.kind == RR_STAGE_DOWNSAMPLE && a.out.n_chunks > 0) {
-                        ds = &c->st[i + 1];
-                        StageHost probe = ds->h;
-                        StageAct pa;
-                        int r = advance_stage(ds->d, probe, a.out, &pa);
-                        if (r == RR_OK && rr::chain_os_supported<T>((int)n, 1, probe.r_L)) fuse_down = true;
+                    RR_TRY(advance_stage(ds->d, ds->h, a.out, &da));
+                    if (da.redesign) {
+                        RR_TRY(resampler_redesign<T>(c, *ds, a.out.rate));
                     }
-                    rr::ChainOsArgs<T> k{};
-                    k.in = cur.p;
-                    k.in_stride = cur.stride;
-                    k.n_chunks = (int)cur.sh.n_chunks;
-                    k.first_is_history = a.first_is_history ? 1 : 0;
-                    k.emit = 1;
-                    k.hist_in = s.hist[s.hist_cur].p;
-                    k.hist_out = s.hist[s.hist_cur ^ 1].p;
-                    k.hperm = s.hperm.p;
-                    k.twN = s.tw.p;
-                    k.nco = nco ? (const rr::NcoStream*)nco->nco_d.p : nullptr;
-                    k.nco_offset = 0;
-                    if (fuse_down) {
-                        RR_TRY(advance_stage(ds->d, ds->h, a.out, &da));
-                        if (da.redesign) RR_TRY(resampler_redesign<T>(c, *ds, a.out.rate));
-                        RR_TRY(obuf_reserve<T>(c, *ds, da.pending_before + da.n_new, da.pending_before));
-                        k.out = (char*)ds->obuf[ds->obuf_cur].p + da.pending_before * 2 * sizeof(T);
-                        k.out_stride = (long long)ds->obuf_cap;
-                        k.ir = (const T*)ds->ir.p;
-                        k.L = ds->h.r_L;
-                        k.ztail_in = ds->tail[ds->tail_cur].p;
-                        k.ztail_out = ds->tail[ds->tail_cur ^ 1].p;
-                        k.rate.P = ds->h.P;
-                        k.rate.Q = ds->h.Q;
-                        k.rate.j0 = da.j0;
-                        k.rate.m0 = da.m0;
-                        RR_TIMED_LAUNCH(c, "k_chain_os<epi=down>", 1, rr::launch_chain_os<T>((int)n, 1, S, 1, k, st));
-                        ds->tail_cur ^= 1;
-                        s.hist_cur ^= 1;
-                        plan += "fused_os[filter+down]";
-                        const bool ds_last = (i + 1 == ns - 1);
-                        RR_TRY(resampler_emit<T>(c, *ds, da, ds_last, dev_out, (long long)out_stride, &cur));
-                        ++i;  // the Downsampler stage is done
-                    } else {
-                        Dest d;
-                        RR_TRY(pick_dest<T>(c, s, last, dev_out, (long long)out_stride, a.out.len(), &d));
-                        k.out = d.p;
-                        k.out_stride = d.stride;
-                        int parts = 1;
-                        const int total = (int)a.out.n_chunks;
-                        if (total > 1) {
-                            const int want = (2 * c->ctx->sm_count + S - 1) / S;
-                            parts = want < total ? want : total;
-                            if (parts < 1) parts = 1;
-                        }
-                        RR_TIMED_LAUNCH(c, "k_chain_os<epi=none>", 1, rr::launch_chain_os<T>((int)n, 0, S, parts, k, st));
-                        s.hist_cur ^= 1;
-                        cur.p = d.p;
-                        cur.stride = d.stride;
-                        cur.sh = a.out;
-                        plan += "fused_os[filter]";
-                    }
-                    if (nco) {
-                        RR_LAUNCH(1, rr::launch_nco_advance((rr::NcoStream*)nco->nco_d.p, S, len, st));
-                        nco_host_advance(*nco, len);
-                    }
+                    RR_TRY(obuf_reserve<T>(c, *ds, da.pending_before + da.n_new, da.pending_before));
+                    RR_TRY(run_filter_down<T>(c, s, *ds, io, a, da, &plan));
+                    const bool ds_last = (i + 1 == ns - 1);
+                    RR_TRY(resampler_emit<T>(c, *ds, da, ds_last, dev_out, (long long)out_stride, &cur));
+                    took_ds = true;
                 } else {
-                    // large chunk: four-step FFT through L2-resident scratch
-                    if (nco) return fail(RR_ERR_UNSUPPORTED, "internal: NCO deferred into an unfused filter");
-                    if (!rr::big_os_supported<T>((int)n)) return fail(RR_ERR_UNSUPPORTED, "Filter: chunk length not supported");
-                    const size_t N = 2 * n;
-                    const int n_blocks = (int)a.out.n_chunks;
                     Dest d;
                     RR_TRY(pick_dest<T>(c, s, last, dev_out, (long long)out_stride, a.out.len(), &d));
-                    if (n_blocks > 0) {
-                        // bound the scratch so it stays L2 resident: process blocks in groups
-                        size_t max_blocks = ((size_t)48 << 20) / (N * 2 * sizeof(T));
-                        if (max_blocks < 1) max_blocks = 1;
-                        size_t per_launch = max_blocks / (size_t)S;
-                        if (per_launch < 1) per_launch = 1;
-                        if (per_launch > (size_t)n_blocks) per_launch = (size_t)n_blocks;
-                        RR_TRY(s.big_scratch.ensure((size_t)S * per_launch * N * 2 * sizeof(T)));
-                        const int c_first = a.first_is_history ? 1 : 0;
-                        for (size_t b0 = 0; b0 < (size_t)n_blocks; b0 += per_launch) {
-                            const size_t nb = std::min(per_launch, (size_t)n_blocks - b0);
-                            rr::BigOsArgs<T> k{};
-                            k.in = cur.p;
-                            k.in_stride = cur.stride;
-                            k.hist = s.hist[s.hist_cur].p;
-                            k.first_chunk = c_first + (int)b0;
-                            k.n_blocks = (int)nb;
-                            k.scratch = s.big_scratch.p;
-                            k.hbig = s.big_h.p;
-                            k.twN = s.tw.p;
-                            k.twA = s.big_twA.p;
-                            k.twB = s.big_twB.p;
-                            k.out = (char*)d.p + b0 * n * 2 * sizeof(T);
-                            k.out_stride = d.stride;
-                            RR_LAUNCH(3, rr::launch_big_os<T>((int)n, S, k, st));
-                        }
-                    }
-                    // new history = last pushed chunk (filters.rs:260)
-                    RR_LAUNCH(1, rr::launch_copy2d<T>((const char*)cur.p + (size_t)(len - (long long)n) * 2 * sizeof(T), cur.stride,
-                                                      s.hist[s.hist_cur ^ 1].p, (long long)n, (long long)n, S, st));
-                    s.hist_cur ^= 1;
+                    RR_TRY(run_os<T>(c, s, io, io.n_chunks, a.first_is_history, d.p, d.stride));
                     cur.p = d.p;
                     cur.stride = d.stride;
                     cur.sh = a.out;
-                    plan += "big_os";
+                    plan += rr::chain_os_supported<T>((int)n, 0, 0) ? "fused_os[filter]" : "big_os";
                 }
+                // new history: the last two mixed chunks (filters.rs:260 keeps one; the polyphase path needs two)
+                RR_LAUNCH(1, rr::launch_hist2_update<T>(io.in, io.in_stride, len, s.hist2[s.hist_cur].p, s.hist2[s.hist_cur ^ 1].p, (long long)n,
+                                                        io.nco ? (const rr::NcoStream*)io.nco->nco_d.p : nullptr, S, st));
+                s.hist_cur ^= 1;
+                if (io.nco) {
+                    RR_LAUNCH(1, rr::launch_nco_advance((rr::NcoStream*)io.nco->nco_d.p, S, len, st));
+                    nco_host_advance(*io.nco, len);
+                }
+                if (took_ds) ++i;  // the Downsampler stage is done
                 break;
             }
             case RR_STAGE_DOWNSAMPLE:
@@ -783,7 +1041,6 @@ int run_push(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_chunks,
             default:
                 return fail(RR_ERR_INVALID, "unknown stage kind");
         }
-        if (s.d.kind != RR_STAGE_FILTER && s.d.kind != RR_STAGE_DOWNSAMPLE && s.d.kind != RR_STAGE_UPSAMPLE) cur.sh = a.out;
     }
     // a chain whose last active stage did not write into the caller's buffer
     // (inactive tail stages, or an empty chain): copy the samples through
@@ -1004,6 +1261,7 @@ int rr_chain_create(rr_ctx* ctx, const rr_chain_desc* desc, rr_chain** out) {
             s.any_shift_dirty = true;
         }
     }
+    if (const char* e = std::getenv("RR_DISABLE_POLY")) c->allow_poly = !(e[0] == '1');
     RR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     *out = c.release();
     return RR_OK;
@@ -1014,7 +1272,7 @@ int rr_chain_destroy(rr_chain* c) {
     cudaSetDevice(c->ctx->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto& s : c->st) {
-        DevBuf* bufs[] = {&s.nco_d, &s.hperm, &s.tw, &s.hist[0], &s.hist[1], &s.big_h, &s.big_twA, &s.big_twB, &s.big_scratch,
+        DevBuf* bufs[] = {&s.nco_d, &s.hperm, &s.tw, &s.hist2[0], &s.hist2[1], &s.ztmp, &s.gtab, &s.twK, &s.big_h, &s.big_twA, &s.big_twB, &s.big_scratch,
                           &s.ir, &s.tail[0], &s.tail[1], &s.obuf[0], &s.obuf[1], &s.fm_prev, &s.fm_last, &s.out};
         for (DevBuf* b : bufs) b->release();
     }
@@ -1102,7 +1360,7 @@ int rr_chain_event(rr_chain* c, int is_interrupt) {
     if (!c) return fail(RR_ERR_INVALID, "null chain");
     if (!is_interrupt) return RR_OK;  // plain events are forwarded untouched by every block
     for (auto& s : c->st) {
-        if (s.d.kind == RR_STAGE_FILTER) s.h.f_has_hist = false;   // filters.rs:262-267
+        if (s.d.kind == RR_STAGE_FILTER) s.h.f_seg = 0;             // filters.rs:262-267
         if (s.d.kind == RR_STAGE_FMDEMOD) s.h.fm_has_prev = false;  // modulation.rs:133-138
     }
     return RR_OK;
@@ -1173,6 +1431,11 @@ int rr_chain_sync(rr_chain* c) {
     if (!c) return fail(RR_ERR_INVALID, "null chain");
     RR_CUDA(cudaSetDevice(c->ctx->device));
     RR_CUDA(cudaStreamSynchronize(c->stream));
+    return RR_OK;
+}
+int rr_chain_set_fast_path(rr_chain* c, int enable) {
+    if (!c) return fail(RR_ERR_INVALID, "null chain");
+    c->allow_poly = enable != 0;
     return RR_OK;
 }
 int rr_chain_set_timing(rr_chain* c, int enable) {

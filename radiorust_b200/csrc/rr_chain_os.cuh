@@ -60,7 +60,7 @@ k_chain_os(const ChainOsArgs<T> a) {
 
     const cx<T>* __restrict__ in = reinterpret_cast<const cx<T>*>(a.in) + (long long)s * a.in_stride;
     cx<T>* __restrict__ out = reinterpret_cast<cx<T>*>(a.out) + (long long)s * a.out_stride;
-    const cx<T>* __restrict__ hist_gi = reinterpret_cast<const cx<T>*>(a.hist_in) + (long long)s * n;
+    const cx<T>* __restrict__ hist_gi = reinterpret_cast<const cx<T>*>(a.hist_in) + (long long)s * a.hist_stride;
     cx<T>* __restrict__ hist_go = reinterpret_cast<cx<T>*>(a.hist_out) + (long long)s * n;
     const cx<T>* __restrict__ hperm = reinterpret_cast<const cx<T>*>(a.hperm);
 
@@ -242,7 +242,7 @@ k_chain_os(const ChainOsArgs<T> a) {
     }
 
     // ---- epilogue: persist state --------------------------------------------
-    if (last_part) {
+    if (last_part && a.hist_out != nullptr) {
 #pragma unroll
         for (int b = 0; b < B1; ++b)
 #pragma unroll

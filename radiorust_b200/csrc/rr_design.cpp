@@ -1,5 +1,6 @@
 #include "rr_design.h"
 
+#include <algorithm>
 #include <cmath>
 #include <numeric>
 
@@ -95,7 +96,7 @@ void fft_pow2(std::vector<std::complex<double>>& a, bool inverse) {
 
 // src/blocks/filters.rs:184-238
 bool design_filter_response(const FreqResp& f, const WindowFn& w, double sample_rate, size_t n, bool as_f32,
-                            std::vector<std::complex<double>>* out) {
+                            std::vector<std::complex<double>>* out, std::vector<std::complex<double>>* taps) {
     if (n < 2 || (n & (n - 1)) != 0) return false;
     const double n_flt = (double)n;
     const double scale = 2.0 * n_flt * n_flt;  // :186
@@ -122,6 +123,7 @@ bool design_filter_response(const FreqResp& f, const WindowFn& w, double sample_
         if (as_f32) (*out)[n + i] = std::complex<double>((double)(float)response[i].real(), (double)(float)response[i].imag());
         else (*out)[n + i] = response[i];
     }
+    if (taps) taps->assign(out->begin() + (long)n, out->end());
     fft_pow2(*out, false);  // :227-238 (the reference runs this one in Flt; f64 here, rounded once by the caller)
     return true;
 }
@@ -140,6 +142,37 @@ void design_resampler_taps(size_t ir_len, double ratio, double null_bin, std::ve
     }
     const double scale = 1.0 / std::sqrt(energy);
     for (auto& y : *out) y *= scale;
+}
+
+int design_poly_tables(const std::vector<std::complex<double>>& h, const std::vector<double>& ir, long long P, long long Q, int K,
+                       std::vector<std::complex<double>>* out) {
+    const long long n = (long long)h.size(), L = (long long)ir.size();
+    const long long Lg = n + L - 1;
+    // g[tau] = sum_v ir[L-1-v] * h[tau - v]
+    std::vector<std::complex<double>> g((size_t)Lg, std::complex<double>(0.0, 0.0));
+    for (long long v = 0; v < L; ++v) {
+        const double c = ir[(size_t)(L - 1 - v)];
+        if (c == 0.0) continue;
+        std::complex<double>* dst = g.data() + v;
+        for (long long m = 0; m < n; ++m) dst[m] += c * h[(size_t)m];
+    }
+    const int Lmax = (int)((Lg - 1) / P);
+    out->assign((size_t)(Q * P) * (size_t)K, std::complex<double>(0.0, 0.0));
+    std::vector<std::complex<double>> buf((size_t)K);
+    for (long long q = 0; q < Q; ++q) {
+        const long long sq = (q * P + Q - 1) / Q;
+        for (long long p = 0; p < P; ++p) {
+            std::fill(buf.begin(), buf.end(), std::complex<double>(0.0, 0.0));
+            for (long long l = -1; l <= Lmax; ++l) {
+                const long long idx = P - 1 + sq - p + l * P;
+                if (idx < 0 || idx >= Lg) continue;
+                buf[(size_t)((l + K) % K)] = g[(size_t)idx];
+            }
+            fft_pow2(buf, false);
+            std::copy(buf.begin(), buf.end(), out->begin() + (size_t)(q * P + p) * (size_t)K);
+        }
+    }
+    return Lmax;
 }
 
 }  // namespace rr

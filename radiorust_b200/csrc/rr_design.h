@@ -28,8 +28,18 @@ void fft_pow2(std::vector<std::complex<double>>& a, bool inverse);
 // extended_response (2n bins).  `as_f32`: round the zero-padded impulse
 // response to f32 before the last FFT like the reference does for Flt = f32.
 // Returns false when n is not a power of two >= 2.
+// `taps` (optional) receives the n windowed impulse-response values (already
+// rounded to Flt when as_f32): the filter is z[k] = sum_m taps[m] * x[k - m].
 bool design_filter_response(const FreqResp& f, const WindowFn& w, double sample_rate, size_t n, bool as_f32,
-                            std::vector<std::complex<double>>* out);
+                            std::vector<std::complex<double>>* out, std::vector<std::complex<double>>* taps = nullptr);
+
+// Polyphase tables of the fused Filter -> Downsampler path (rr_poly.cuh).
+// g = h * reverse(ir) (length n + L - 1); for output phase q and input branch p
+// the low-rate filter is G[q][p][l] = g[P - 1 + s_q - p + l*P], l = -1 .. Lmax,
+// s_q = ceil(q*P/Q); `out` receives FFT_K of each, natural bin order,
+// [Q][P][K].  Returns Lmax = floor((n + L - 2) / P).
+int design_poly_tables(const std::vector<std::complex<double>>& h, const std::vector<double>& ir, long long P, long long Q, int K,
+                       std::vector<std::complex<double>>* out);
 
 // unit-energy windowed-sinc taps, f64 (cast by the caller)
 void design_resampler_taps(size_t ir_len, double ratio, double null_bin, std::vector<double>* out);

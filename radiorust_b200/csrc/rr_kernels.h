@@ -32,8 +32,9 @@ template <typename T> struct ChainOsArgs {
     int first_is_history;   // 1: no stored history; chunk 0 only primes the filter
     int emit;               // 0: state-only run (no samples written, only hist/ztail state)
     int reserved;
-    const void* hist_in;    // [S][n] complex<T>, post-NCO history chunk (read when !first_is_history)
-    void* hist_out;         // [S][n] new history (never aliases hist_in: CTAs of one launch read and write)
+    const void* hist_in;    // post-NCO history chunk of stream s at hist_in + s*hist_stride (read when !first_is_history)
+    long long hist_stride;  // elements
+    void* hist_out;         // [S][n] new history or nullptr (never aliases hist_in: CTAs of one launch read and write)
     const void* hperm;      // [N] complex<T>, H(f) in FftPlan::hperm_index order
     const void* twN;        // [N] complex<T>, exp(-j*2*pi*e/N)
     const NcoStream* nco;   // [S] or nullptr (read-only; the host advances idx with launch_nco_advance)
@@ -61,7 +62,7 @@ template <typename T> int chain_os_hperm_index(int n, int k);
 // ---- standalone stages ------------------------------------------------------
 template <typename T>
 cudaError_t launch_freqshift(const void* in, long long in_stride, void* out, long long out_stride, long long len,
-                             int n_streams, NcoStream* nco, cudaStream_t st);
+                             int n_streams, const NcoStream* nco, long long nco_offset, cudaStream_t st);
 
 cudaError_t launch_nco_advance(NcoStream* nco, int n_streams, long long len, cudaStream_t st);
 
@@ -96,7 +97,8 @@ cudaError_t launch_copy2d(const void* in, long long in_stride, void* out, long l
 template <typename T> struct BigOsArgs {
     const void* in;         // [S][in_stride]: the pushed chunks
     long long in_stride;
-    const void* hist;       // [S][n]: chunk preceding `in` (read when block 0 starts at chunk 0)
+    const void* hist;       // chunk preceding `in`, stream s at hist + s*hist_stride (read when block 0 starts at chunk 0)
+    long long hist_stride;
     int first_chunk;        // block b convolves chunks (first_chunk + b - 1, first_chunk + b)
     int n_blocks;           // overlap-save blocks in this launch
     void* scratch;          // [S*n_blocks][N] complex<T>
@@ -113,5 +115,35 @@ template <typename T> void big_os_shape(int n, int* Na, int* Nb);
 template <typename T> long long big_os_hperm_index(int n, long long k);
 template <typename T>
 cudaError_t launch_big_os(int n, int n_streams, const BigOsArgs<T>& a, cudaStream_t st);
+
+// ---- polyphase fused chain: NCO -> Filter -> Downsampler without the full-rate
+// intermediate (rr_poly.cuh) ---------------------------------------------------
+template <typename T> struct PolyArgs {
+    const void* in;        // [S][in_stride] complex<T>: the pushed samples (pre-NCO)
+    long long in_stride;
+    long long len;         // pushed samples per stream
+    const void* hist2;     // [S][2n] complex<T>: the 2n post-NCO samples preceding `in`
+    long long n;           // Filter chunk length
+    const NcoStream* nco;  // [S] or nullptr
+    const void* gtab;      // [Q][P][K] complex<T>, bins in the K-point plan's hperm order
+    const void* twK;       // [K] exp(-j*2*pi*e/K)
+    long long P, Q;        // in/out = P/Q reduced
+    int Lmax, V;           // low-rate filter reach, valid outputs per block and phase
+    int n_blocks, nbpc;    // blocks per stream, blocks per CTA
+    long long J0, m0;      // filter-output samples consumed / outputs emitted before this push (reduced)
+    long long m_lo, m_hi;  // outputs m to produce (inclusive)
+    long long I_lo;        // low-rate index of block 0's first valid output
+    void* out;             // [S][out_stride]; output m goes to out[m - m0 - 1]
+    long long out_stride;
+};
+template <typename T> bool poly_supported(int K, int Q, int G);
+template <typename T> int poly_hperm_index(int K, int k);
+template <typename T> size_t poly_smem_bytes(int K, int Q, int G, int nbpc);
+template <typename T> cudaError_t launch_poly(int K, int Q, int G, int n_streams, const PolyArgs<T>& a, cudaStream_t st);
+
+// new hist2 = last 2n post-NCO samples of [hist2_in | in]
+template <typename T>
+cudaError_t launch_hist2_update(const void* in, long long in_stride, long long len, const void* hist2_in, void* hist2_out,
+                                long long n, const NcoStream* nco, int n_streams, cudaStream_t st);
 
 }  // namespace rr

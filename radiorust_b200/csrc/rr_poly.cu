@@ -1,0 +1,110 @@
+// Dispatch of the polyphase fused chain kernel + the history update kernel.
+#include "rr_poly.cuh"
+
+namespace rr {
+
+#define RR_POLY_KS(X, T, G) X(T, 256, G) X(T, 512, G) X(T, 1024, G)
+#define RR_POLY_ALL(X) RR_POLY_KS(X, float, 8) RR_POLY_KS(X, float, 10) RR_POLY_KS(X, double, 8) RR_POLY_KS(X, double, 10)
+
+#define X(T, K, G)                                                                                              \
+    extern template cudaError_t launch_poly_n<T, K, 1, G>(int, const PolyArgs<T>&, cudaStream_t);              \
+    extern template cudaError_t launch_poly_n<T, K, 2, G>(int, const PolyArgs<T>&, cudaStream_t);              \
+    extern template cudaError_t launch_poly_n<T, K, 3, G>(int, const PolyArgs<T>&, cudaStream_t);              \
+    extern template cudaError_t launch_poly_n<T, K, 4, G>(int, const PolyArgs<T>&, cudaStream_t);
+RR_POLY_ALL(X)
+#undef X
+
+template <typename T> bool poly_supported(int K, int Q, int G) {
+    return (K == 256 || K == 512 || K == 1024) && Q >= 1 && Q <= 4 && (G == 8 || G == 10);
+}
+template bool poly_supported<float>(int, int, int);
+template bool poly_supported<double>(int, int, int);
+
+template <typename T> int poly_hperm_index(int K, int k) {
+    switch (K) {
+        case 256: return PlanFor<T, 256>::type::hperm_index(k);
+        case 512: return PlanFor<T, 512>::type::hperm_index(k);
+        case 1024: return PlanFor<T, 1024>::type::hperm_index(k);
+    }
+    return -1;
+}
+template int poly_hperm_index<float>(int, int);
+template int poly_hperm_index<double>(int, int);
+
+template <typename T, int K> static size_t smem_k(int Q, int G, int nbpc) {
+    const size_t work = (G == 8) ? PlanFor<T, K, 8>::type::SMEM_ELEMS : PlanFor<T, K, 10>::type::SMEM_ELEMS;
+    return sizeof(cx<T>) * (work + (size_t)nbpc * Q * K);
+}
+template <typename T> size_t poly_smem_bytes(int K, int Q, int G, int nbpc) {
+    switch (K) {
+        case 256: return smem_k<T, 256>(Q, G, nbpc);
+        case 512: return smem_k<T, 512>(Q, G, nbpc);
+        case 1024: return smem_k<T, 1024>(Q, G, nbpc);
+    }
+    return (size_t)-1;
+}
+template size_t poly_smem_bytes<float>(int, int, int, int);
+template size_t poly_smem_bytes<double>(int, int, int, int);
+
+template <typename T, int K, int G> static cudaError_t poly_q(int Q, int S, const PolyArgs<T>& a, cudaStream_t st) {
+    switch (Q) {
+        case 1: return launch_poly_n<T, K, 1, G>(S, a, st);
+        case 2: return launch_poly_n<T, K, 2, G>(S, a, st);
+        case 3: return launch_poly_n<T, K, 3, G>(S, a, st);
+        case 4: return launch_poly_n<T, K, 4, G>(S, a, st);
+    }
+    return cudaErrorInvalidValue;
+}
+template <typename T, int G> static cudaError_t poly_k(int K, int Q, int S, const PolyArgs<T>& a, cudaStream_t st) {
+    switch (K) {
+        case 256: return poly_q<T, 256, G>(Q, S, a, st);
+        case 512: return poly_q<T, 512, G>(Q, S, a, st);
+        case 1024: return poly_q<T, 1024, G>(Q, S, a, st);
+    }
+    return cudaErrorInvalidValue;
+}
+template <typename T> cudaError_t launch_poly(int K, int Q, int G, int n_streams, const PolyArgs<T>& a, cudaStream_t st) {
+    if (G == 8) return poly_k<T, 8>(K, Q, n_streams, a, st);
+    if (G == 10) return poly_k<T, 10>(K, Q, n_streams, a, st);
+    return cudaErrorInvalidValue;
+}
+template cudaError_t launch_poly<float>(int, int, int, int, const PolyArgs<float>&, cudaStream_t);
+template cudaError_t launch_poly<double>(int, int, int, int, const PolyArgs<double>&, cudaStream_t);
+
+// ---------------------------------------------------------------------------
+// hist2_out[j] = sample (len - 2n + j) of [hist2_in (2n, already mixed) | in (len, mixed here)]
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_hist2_update(const cx<T>* __restrict__ in, long long in_stride, long long len,
+                                                      const cx<T>* __restrict__ hist2_in, cx<T>* __restrict__ hist2_out,
+                                                      long long n, const NcoStream* __restrict__ nco) {
+    const int s = blockIdx.y;
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= 2 * n) return;
+    const long long off = len - 2 * n + j;
+    cx<T> v;
+    if (off >= 0) {
+        v = ld_cx(&in[(long long)s * in_stride + off]);
+        if (nco) {
+            const NcoStream ns = nco[s];
+            v = cmul(v, nco_phasor_at<T>(off, ns.idx, ns.numer_abs, ns.denom, ns.sign, (T)ns.start_phase));
+        }
+    } else {
+        v = ld_cx(&hist2_in[(long long)s * 2 * n + off + 2 * n]);
+    }
+    st_cx(&hist2_out[(long long)s * 2 * n + j], v);
+}
+template <typename T>
+cudaError_t launch_hist2_update(const void* in, long long in_stride, long long len, const void* hist2_in, void* hist2_out,
+                                long long n, const NcoStream* nco, int n_streams, cudaStream_t st) {
+    dim3 grid((unsigned)((2 * n + 255) / 256), (unsigned)n_streams);
+    k_hist2_update<T><<<grid, 256, 0, st>>>(reinterpret_cast<const cx<T>*>(in), in_stride, len,
+                                            reinterpret_cast<const cx<T>*>(hist2_in), reinterpret_cast<cx<T>*>(hist2_out), n, nco);
+    return cudaGetLastError();
+}
+template cudaError_t launch_hist2_update<float>(const void*, long long, long long, const void*, void*, long long, const NcoStream*,
+                                                int, cudaStream_t);
+template cudaError_t launch_hist2_update<double>(const void*, long long, long long, const void*, void*, long long, const NcoStream*,
+                                                 int, cudaStream_t);
+
+}  // namespace rr

@@ -13,14 +13,14 @@ namespace rr {
 template <typename T>
 __global__ void __launch_bounds__(256) k_freqshift(const cx<T>* __restrict__ in, long long in_stride,
                                                    cx<T>* __restrict__ out, long long out_stride, long long len,
-                                                   const NcoStream* __restrict__ nco) {
+                                                   const NcoStream* __restrict__ nco, long long nco_offset) {
     const int s = blockIdx.y;
     const NcoStream ns = nco[s];
     const cx<T>* src = in + (long long)s * in_stride;
     cx<T>* dst = out + (long long)s * out_stride;
     const T start = (T)ns.start_phase;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < len; t += (long long)gridDim.x * blockDim.x) {
-        const uint32_t k = (uint32_t)(((unsigned long long)ns.idx + (unsigned long long)t) % ns.denom);
+        const uint32_t k = (uint32_t)(((unsigned long long)ns.idx + (unsigned long long)(nco_offset + t)) % ns.denom);
         const uint32_t i = mulmod_u32(ns.numer_abs, k, ns.denom);
         const cx<T> ph = nco_phasor<T>(i, ns.denom, ns.sign, start);
         st_cx(&dst[t], cmul(ld_cx(&src[t]), ph));
@@ -42,14 +42,13 @@ cudaError_t launch_nco_advance(NcoStream* nco, int n_streams, long long len, cud
 
 template <typename T>
 cudaError_t launch_freqshift(const void* in, long long in_stride, void* out, long long out_stride, long long len,
-                             int n_streams, NcoStream* nco, cudaStream_t st) {
+                             int n_streams, const NcoStream* nco, long long nco_offset, cudaStream_t st) {
     if (len <= 0) return cudaSuccess;
     long long bx = (len + 255) / 256;
     if (bx > 4096) bx = 4096;
     dim3 grid((unsigned)bx, (unsigned)n_streams);
     k_freqshift<T><<<grid, 256, 0, st>>>(reinterpret_cast<const cx<T>*>(in), in_stride, reinterpret_cast<cx<T>*>(out),
-                                         out_stride, len, nco);
-    k_nco_advance<<<(n_streams + 127) / 128, 128, 0, st>>>(nco, n_streams, len);
+                                         out_stride, len, nco, nco_offset);
     return cudaGetLastError();
 }
 
@@ -267,8 +266,8 @@ cudaError_t launch_fmdemod(const void* in, long long in_stride, void* out, long 
 }
 
 #define RR_INST(T)                                                                                                     \
-    template cudaError_t launch_freqshift<T>(const void*, long long, void*, long long, long long, int, NcoStream*,     \
-                                             cudaStream_t);                                                            \
+    template cudaError_t launch_freqshift<T>(const void*, long long, void*, long long, long long, int,                 \
+                                             const NcoStream*, long long, cudaStream_t);                                                          \
     template cudaError_t launch_gain<T>(const void*, long long, void*, long long, long long, int, double,              \
                                         cudaStream_t);                                                                 \
     template cudaError_t launch_copy2d<T>(const void*, long long, void*, long long, long long, int, cudaStream_t);     \

@@ -102,7 +102,7 @@ def test_config1_chain_f32(ctx, shift):
     x = noise(20260000 + 1 * 100000, 24 * n, "f32")
     stages = [rr.FreqShifter(shift), rr.Filter.new(orc.lowpass(3000.0)), rr.Downsampler(192, 48000.0, 6000.0)]
     got, want, plan = run_both(ctx, stages, "f32", sr, x, n, pushes=[1, 2, 5, 16])
-    assert "fused_os" in plan
+    assert "poly" in plan or "fused_os" in plan
     check(got, want, "f32")
 
 
@@ -263,3 +263,107 @@ def test_errors(ctx):
     with pytest.raises(rr.RadiorustError):  # input rate below output rate (resampling.rs:78-81)
         ch.push(8000.0, noise(1, 256, "f32"), 256)
     ch.close()
+
+
+# ---------------------------------------------------------------------------
+# polyphase fast path (rr_poly.cuh): same results as the stateful overlap-save path
+# ---------------------------------------------------------------------------
+def test_poly_path_is_used_and_matches(ctx):
+    import radiorust_b200 as rr
+
+    sr, n = 2_400_000.0, 4096
+    x = noise(20260000 + 3 * 100000 + 17, 40 * n, "f32")
+    stages = [rr.FreqShifter(-577000.0), rr.Filter.new(orc.lowpass(3000.0)), rr.Downsampler(64, 48000.0, 6000.0)]
+    got, want, plan = run_both(ctx, stages, "f32", sr, x, n, pushes=[1, 1, 1, 7, 30])
+    assert "poly" in plan, plan
+    check(got, want, "f32")
+    # and against the stateful path of the library itself
+    ch = rr.Chain(ctx, stages, "f32")
+    ch.set_fast_path(False)
+    y, _ = ch.push(sr, x, n)
+    assert "poly" not in ch.plan
+    ch.close()
+    assert orc.rel_l2(got, y) < 2e-6
+
+
+def test_poly_then_event_then_retune(ctx):
+    """The decimator tail must be rebuilt from hist2 after polyphase pushes (interrupts, redesigns, path switches)."""
+    import radiorust_b200 as rr
+
+    sr, n = 1_024_000.0, 4096
+    x = noise(424242, 40 * n, "f32")
+    stages = [rr.FreqShifter(100000.0), rr.Filter.new(orc.lowpass(3000.0)), rr.Downsampler(100, 48000.0, 6000.0)]
+    ch = rr.Chain(ctx, stages, "f32")
+    ob = oracle_blocks(stages, "f32")
+    oc = orc.Chain(ob)
+    got, want, plans = [], [], []
+
+    def feed(lo, hi):
+        y, _ = ch.push(sr, x[lo * n : hi * n], n)
+        plans.append(ch.plan)
+        got.append(y[0].copy())
+        for k in range(lo, hi):
+            for m in oc.push(orc.Samples(sr, x[k * n : (k + 1) * n])):
+                if isinstance(m, orc.Samples):
+                    want.append(m.chunk)
+
+    feed(0, 8)           # stateful (2 chunks) + poly
+    feed(8, 14)          # poly only
+    ch.event(True)       # interrupt: Filter drops history, Downsampler keeps its ring
+    oc.push(orc.DISCONNECTION)
+    feed(14, 20)
+    ch.update_filter(1, orc.lowpass(5000.0))  # redesign after poly pushes
+    ob[1].update(orc.lowpass(5000.0))
+    feed(20, 26)
+    ch.set_shift(0, -200000.0)
+    ob[0].set_shift(-200000.0)
+    feed(26, 32)
+    ch.set_fast_path(False)  # path switch: tail rebuilt, stateful continues
+    feed(32, 36)
+    ch.set_fast_path(True)
+    feed(36, 40)
+    ch.close()
+    assert any("poly" in p for p in plans)
+    g, w = np.concatenate(got), np.concatenate(want)
+    check(g[None, :], w[None, :], "f32")
+
+
+@pytest.mark.parametrize("flt,n,sr,out_rate,bw,ocl", [
+    ("f32", 4096, 1_024_000.0, 48000.0, 6000.0, 192),     # C1: P/Q = 64/3
+    ("f32", 4096, 2_400_000.0, 48000.0, 6000.0, 2048),    # C3: P = 50
+    ("f32", 2048, 960_000.0, 48000.0, 20000.0, 17),       # P = 20, odd output chunking
+    ("f32", 1024, 250_000.0, 100000.0, 30000.0, 64),      # P/Q = 5/2
+    ("f64", 2048, 1_024_000.0, 48000.0, 6000.0, 96),      # f64, 64/3
+    ("f64", 4096, 2_400_000.0, 48000.0, 6000.0, 50),      # f64, P = 50
+])
+def test_poly_rates(ctx, flt, n, sr, out_rate, bw, ocl):
+    import radiorust_b200 as rr
+
+    x = noise(77 + n, 26 * n, flt)
+    stages = [rr.FreqShifter(sr / 7.0), rr.Filter.new(orc.lowpass(bw / 2)), rr.Downsampler(ocl, out_rate, bw)]
+    got, want, plan = run_both(ctx, stages, flt, sr, x, n, pushes=[3, 10, 13])
+    assert "poly" in plan, plan
+    check(got, want, flt)
+
+
+def test_poly_filter_down_without_nco_multi_stream(ctx):
+    import radiorust_b200 as rr
+
+    sr, n, S = 2_400_000.0, 4096, 3
+    x = np.stack([noise(900 + s, 30 * n, "f32") for s in range(S)])
+    stages = [rr.Filter.new(orc.lowpass(3000.0)), rr.Downsampler(128, 48000.0, 6000.0)]
+    got, want, plan = run_both(ctx, stages, "f32", sr, x, n, pushes=[12, 18])
+    assert "poly" in plan
+    check(got, want, "f32")
+
+
+def test_config2_chain_poly(ctx):
+    """Config 2 shape: n = 65536 chunks at 20 MS/s, P/Q = 1250/3; big_os start-up then polyphase."""
+    import radiorust_b200 as rr
+
+    sr, n = 20_000_000.0, 65536
+    x = noise(20260000 + 2 * 100000 + 3, 6 * n, "f32")
+    stages = [rr.FreqShifter(1_234_567.0), rr.Filter.new(orc.lowpass(3000.0)), rr.Downsampler(128, 48000.0, 6000.0)]
+    got, want, plan = run_both(ctx, stages, "f32", sr, x, n, pushes=[2, 4])
+    assert "poly" in plan, plan
+    check(got, want, "f32")
