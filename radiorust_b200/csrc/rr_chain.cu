@@ -721,16 +721,25 @@ template <typename T> int poly_prepare(rr_chain* c, Stage& f, Stage& ds) {
     const double e8 = (double)P / (8.0 * (double)((P + 7) / 8)), e10 = (double)P / (10.0 * (double)((P + 9) / 10));
     const int G = e10 > e8 + 1e-9 ? 10 : 8;
     if (!rr::poly_supported<T>(bestK, (int)Q, G)) return RR_OK;
+    if (rr::poly_smem_bytes<T>(bestK, (int)Q, G, 1) > (size_t)220 * 1024) return RR_OK;
     std::vector<std::complex<double>> tab, perm;
     const int lm = rr::design_poly_tables(f.taps, ds.ir_host_flt, P, Q, bestK, &tab);
     if (lm != (int)Lmax) return fail(RR_ERR_INVALID, "internal: polyphase reach mismatch");
     // f.taps carry the 1/(2n) of the reference's unnormalised 2n-point inverse (filters.rs:186); the
     // kernel's K-point forward/inverse pair is unnormalised too: rescale by 2n / K
     const double scale = 2.0 * (double)n / (double)bestK;
-    perm.resize(tab.size());
-    for (long long qp = 0; qp < Q * P; ++qp)
-        for (int k = 0; k < bestK; ++k)
-            perm[(size_t)qp * bestK + (size_t)rr::poly_hperm_index<T>(bestK, k)] = tab[(size_t)qp * bestK + k] * scale;
+    // device layout [q][round][bin position][g]: the G branches of a round sit side by side (one
+    // coalesced read per bin), branches past P are zero
+    const long long NR = (P + G - 1) / G;
+    perm.assign((size_t)(Q * NR) * (size_t)bestK * (size_t)G, std::complex<double>(0.0, 0.0));
+    for (long long q = 0; q < Q; ++q)
+        for (long long p = 0; p < P; ++p) {
+            const long long r = p / G, gg = p % G;
+            for (int k = 0; k < bestK; ++k) {
+                const size_t pos = (size_t)rr::poly_hperm_index<T>(bestK, k);
+                perm[(((size_t)(q * NR + r)) * bestK + pos) * G + gg] = tab[(size_t)(q * P + p) * bestK + k] * scale;
+            }
+        }
     RR_TRY(upload_complex<T>(ds.gtab, perm, c->stream));
     std::vector<std::complex<double>> tw;
     rr::make_twiddles((size_t)bestK, &tw);
@@ -845,7 +854,7 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
             a.n_blocks = (int)((I_hi - a.I_lo) / a.V + 1);
             // blocks per CTA: one round of inverse transforms (G jobs) when the grid stays large enough
             int nbpc = std::max(1, ds.poly_G / (int)Qq);
-            while (nbpc > 1 && rr::poly_smem_bytes<T>(ds.poly_K, (int)Qq, ds.poly_G, nbpc) > (size_t)100 * 1024) --nbpc;
+            while (nbpc > 1 && rr::poly_smem_bytes<T>(ds.poly_K, (int)Qq, ds.poly_G, nbpc) > (size_t)200 * 1024) --nbpc;
             while (nbpc > 1 && (long long)S * ((a.n_blocks + nbpc - 1) / nbpc) < 2LL * c->ctx->sm_count) --nbpc;
             const int nsb = (a.n_blocks + nbpc - 1) / nbpc;
             nbpc = (a.n_blocks + nsb - 1) / nsb;  // balance

@@ -32,8 +32,8 @@ template int poly_hperm_index<float>(int, int);
 template int poly_hperm_index<double>(int, int);
 
 template <typename T, int K> static size_t smem_k(int Q, int G, int nbpc) {
-    const size_t work = (G == 8) ? PlanFor<T, K, 8>::type::SMEM_ELEMS : PlanFor<T, K, 10>::type::SMEM_ELEMS;
-    return sizeof(cx<T>) * (work + (size_t)nbpc * Q * K);
+    const size_t e = (G == 8) ? PolyCfg<T, K, 8>::smem_elems(nbpc, Q) : PolyCfg<T, K, 10>::smem_elems(nbpc, Q);
+    return sizeof(cx<T>) * e;
 }
 template <typename T> size_t poly_smem_bytes(int K, int Q, int G, int nbpc) {
     switch (K) {

@@ -14,21 +14,49 @@
 // a multiply-accumulate against FFT(G) and Q inverse FFTs of K points per
 // V*P input samples, V = K - 1 - Lmax valid outputs per block and phase.
 //
-// Launch shape: one CTA = G thread groups; group g transforms branch p0 + g of
-// the current round, so G lanes read G consecutive input samples; the groups'
-// transforms are interleaved in shared memory (FftPlan<.., G>).  Accumulators
-// live in registers across the P/G rounds, are reduced over groups through
-// shared memory and kept there per block; at the end the groups run the
-// inverse transforms of different (block, phase) jobs concurrently.
+// Launch shape: one CTA = G thread groups of NT threads; in every round group g
+// transforms branch p0 + g, so G neighbouring lanes read G consecutive input
+// samples.  The G transforms are interleaved in shared memory (element e of
+// transform g at G*sidx(e) + g: conflict-free for every pass).  Spectral
+// accumulators live in registers across the ceil(P/G) rounds, are reduced over
+// the groups through shared memory and parked there per block; at the end the
+// groups run the inverse transforms of different (block, phase) jobs at once.
+//
+// NCO: the phasor of sample (i, p) of a block factors into phb[i] (depends on
+// the row only: a K-entry shared-memory table per stream) times c_p (one scalar
+// per transform, applied to the K/NT spectrum values each thread owns before
+// the multiply-accumulate).  c_p is re-derived exactly from the integer phase
+// recurrence (transform.rs:333-338) every 16 rounds and rotated in between.
+//
+// Per round: global loads of the NEXT round are issued right after pass 1 has
+// parked the current data in shared memory, so their latency hides behind
+// passes 2 and 3; two work buffers alternate so a round needs two barriers.
 #pragma once
 #include "rr_chain_os.cuh"
 
 namespace rr {
 
 template <typename T, int K, int G> struct PolyCfg {
-    using Plan = typename PlanFor<T, K, G>::type;
-    static constexpr int THREADS = Plan::NT * G;
-    static constexpr int MIN_CTAS = (sizeof(T) == 4 && THREADS <= 512) ? 2 : 1;
+    using Plan = typename PlanFor<T, K, 1>::type;
+    static constexpr int NT = Plan::NT;
+    static constexpr int THREADS = NT * G;
+    static constexpr int R1 = Plan::R1, R2 = Plan::R2, R3 = Plan::R3;
+    static constexpr int B1 = Plan::B1, B2 = Plan::B2, B3 = Plan::B3;
+    static constexpr int S1 = Plan::S1, S2 = Plan::S2;
+    static constexpr int PAD = Plan::PAD, LOG_R3 = Plan::LOG_R3;
+    static constexpr int ROW = K + PAD * (K / R3);  // padded elements per transform
+    static constexpr int WORK = G * ROW;            // one interleaved work buffer
+    // element strides (in complex elements) inside the interleaved layout
+    static constexpr int STR1 = G * (S1 + PAD * (S1 / R3));
+    static constexpr int STR2 = G * (S2 + PAD);
+    static constexpr int STR3 = G;
+    __host__ __device__ static constexpr int sidx(int p) { return G * (p + PAD * (p >> LOG_R3)); }
+    // two alternating work buffers save one barrier per round; f64 keeps one (shared-memory budget)
+    static constexpr int NBUF = (sizeof(T) == 4) ? 2 : 1;
+    // shared memory: work buffers, 3 K-entry tables, nbpc*Q parked spectra
+    __host__ __device__ static constexpr size_t smem_elems(int nbpc, int Q) {
+        return (size_t)NBUF * WORK + 3 * (size_t)K + (size_t)nbpc * Q * K;
+    }
 };
 
 // exact NCO phasor for push-relative sample offset `off` (may be negative):
@@ -39,38 +67,50 @@ __device__ __forceinline__ cx<T> nco_phasor_at(long long off, uint32_t idx, uint
     if (k < 0) k += denom;
     return nco_phasor<T>(mulmod_u32(numer_abs, (uint32_t)k, denom), denom, sign, start);
 }
+// exp(j * sign * 2*pi * (numer*d mod denom) / denom): the phase advance over d samples (start phase excluded)
+template <typename T>
+__device__ __forceinline__ cx<T> nco_rotation(long long d, uint32_t numer_abs, uint32_t denom, int sign) {
+    long long k = d % (long long)denom;
+    if (k < 0) k += denom;
+    const uint32_t r = mulmod_u32(numer_abs, (uint32_t)k, denom);
+    double s, c;
+    sincospi(2.0 * (double)r / (double)denom, &s, &c);
+    return cx<T>((T)c, (T)(sign < 0 ? -s : s));
+}
 
 template <typename T, int K, int Q, int G>
-__global__ void __launch_bounds__(PolyCfg<T, K, G>::THREADS, PolyCfg<T, K, G>::MIN_CTAS)
+__global__ void __launch_bounds__(PolyCfg<T, K, G>::THREADS, 1)
 k_poly(const PolyArgs<T> a) {
-    using P = typename PolyCfg<T, K, G>::Plan;
-    constexpr int NT = P::NT, R1 = P::R1, B1 = P::B1, S1 = P::S1, R3 = P::R3, B3 = P::B3;
-    constexpr int THREADS = NT * G;
-    constexpr int KR = K / R3;
+    using C = PolyCfg<T, K, G>;
+    constexpr int NT = C::NT, R1 = C::R1, R2 = C::R2, R3 = C::R3, B1 = C::B1, B2 = C::B2, B3 = C::B3;
+    constexpr int S1 = C::S1, S2 = C::S2, THREADS = C::THREADS, KR = K / R3;
+    constexpr int STR1 = C::STR1, STR2 = C::STR2, STR3 = C::STR3;
     const int tid = threadIdx.x;
     const int g = tid % G, t = tid / G;
     const int s = blockIdx.y;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cx<T>* W = reinterpret_cast<cx<T>*>(smem_raw);  // interleaved work area, >= K*G elements
-    cx<T>* Ysave = W + P::SMEM_ELEMS;                // [nbpc*Q][K]
-    cx<T>* smg = W + g;
+    cx<T>* W0 = reinterpret_cast<cx<T>*>(smem_raw);
+    cx<T>* tw1s = W0 + C::NBUF * C::WORK;  // [NT*B1][R1]  W_K^(k*q)
+    cx<T>* tw2s = tw1s + K;          // [NT*B2][R2]  W_(R2*R3)^(k*n3)
+    cx<T>* phb = tw2s + K;           // [K]          NCO rotation over i*P samples
+    cx<T>* Ysave = phb + K;          // [nbpc*Q][K]
 
     const cx<T>* __restrict__ in = reinterpret_cast<const cx<T>*>(a.in) + (long long)s * a.in_stride;
     const cx<T>* __restrict__ hist = reinterpret_cast<const cx<T>*>(a.hist2) + (long long)s * 2 * a.n;
     const cx<T>* __restrict__ gtab = reinterpret_cast<const cx<T>*>(a.gtab);
+    const cx<T>* __restrict__ twK = reinterpret_cast<const cx<T>*>(a.twK);
     cx<T>* __restrict__ out = reinterpret_cast<cx<T>*>(a.out) + (long long)s * a.out_stride;
-    const long long Pd = a.P;
+    const int Pd = (int)a.P;
+    const int NR = (Pd + G - 1) / G;  // rounds per block
     const long long len = a.len, hist_len = 2 * a.n;
 
-    P plan;
-    plan.init(reinterpret_cast<const cx<T>*>(a.twK), t);
-
+    // ---- NCO constants ---------------------------------------------------------
     const bool has_nco = (a.nco != nullptr);
     uint32_t denom = 1, numer_abs = 0, idx0 = 0;
     int sign = 0;
     T start = (T)0;
-    cx<T> rotG((T)1, (T)0);  // phasor advance for +G samples
+    cx<T> rotG((T)1, (T)0);
     if (has_nco) {
         const NcoStream ns = a.nco[s];
         denom = ns.denom;
@@ -78,11 +118,41 @@ k_poly(const PolyArgs<T> a) {
         sign = ns.sign;
         start = (T)ns.start_phase;
         idx0 = ns.idx;
-        const uint32_t step = mulmod_u32(numer_abs, (uint32_t)(G % denom), denom);
-        double sj, cj;
-        sincospi(2.0 * (double)step / (double)denom, &sj, &cj);
-        rotG = cx<T>((T)cj, (T)(sign < 0 ? -sj : sj));
+        rotG = nco_rotation<T>(G, numer_abs, denom, sign);
     }
+
+    // ---- per-thread invariant shared-memory offsets (elements, before + g) -------
+    int off1[B1], off2[B2], off3[B3];
+#pragma unroll
+    for (int b = 0; b < B1; ++b) off1[b] = C::sidx(B1 * t + b) + g;
+#pragma unroll
+    for (int b = 0; b < B2; ++b) {
+        const int id = B2 * t + b;
+        off2[b] = C::sidx((id >> C::LOG_R3) * S1 + (id & (R3 - 1))) + g;
+    }
+#pragma unroll
+    for (int b = 0; b < B3; ++b) off3[b] = C::sidx((B3 * t + b) * R3) + g;
+
+    // ---- tables: twiddles of this thread's butterflies, NCO row phasors ------------
+    if (g == 0) {
+#pragma unroll
+        for (int b = 0; b < B1; ++b) {
+            cx<T> p[R1];
+            pow_chain<R1, T>(ld_cx(&twK[B1 * t + b]), p);
+#pragma unroll
+            for (int k = 0; k < R1; ++k) st_cx(&tw1s[(B1 * t + b) * R1 + k], p[k]);
+        }
+#pragma unroll
+        for (int b = 0; b < B2; ++b) {
+            cx<T> p[R2];
+            pow_chain<R2, T>(ld_cx(&twK[((B2 * t + b) & (R3 - 1)) * R1]), p);
+#pragma unroll
+            for (int k = 0; k < R2; ++k) st_cx(&tw2s[(B2 * t + b) * R2 + k], p[k]);
+        }
+    }
+    for (int i = tid; i < K; i += THREADS)
+        st_cx(&phb[i], has_nco ? nco_rotation<T>((long long)i * Pd, numer_abs, denom, sign) : cx<T>((T)1, (T)0));
+    __syncthreads();
 
     const int blk0 = blockIdx.x * a.nbpc;
     const int blk1 = min(blk0 + a.nbpc, a.n_blocks);
@@ -92,17 +162,8 @@ k_poly(const PolyArgs<T> a) {
         const long long boff = Ibase * Pd - a.J0 - Pd;  // push-relative offset of local element (i = 0, p = 0)
         // blocks whose whole input window lies inside the pushed samples skip the range checks
         const bool interior = (boff >= 0) && (boff + (long long)K * Pd <= len);
+        const cx<T>* __restrict__ bin = in + boff;  // element (i, p) at bin[i*Pd + p]
 
-        cx<T> ph[B1][R1];
-        if (has_nco) {
-#pragma unroll
-            for (int bb = 0; bb < B1; ++bb)
-#pragma unroll
-                for (int r = 0; r < R1; ++r) {
-                    const long long off = boff + (long long)(B1 * t + bb + S1 * r) * Pd + g;
-                    ph[bb][r] = nco_phasor_at<T>(off, idx0, numer_abs, denom, sign, start);
-                }
-        }
         cx<T> acc[Q][B3][R3];
 #pragma unroll
         for (int q = 0; q < Q; ++q)
@@ -111,87 +172,136 @@ k_poly(const PolyArgs<T> a) {
 #pragma unroll
                 for (int k = 0; k < R3; ++k) acc[q][b][k] = cx<T>((T)0, (T)0);
 
-        for (long long p0 = 0; p0 < Pd; p0 += G) {
-            const long long p = p0 + g;
+        // raw load of round r's data for this thread's pass-1 butterflies
+        cx<T> v[B1][R1];
+        auto load_round = [&](int r) {
+            const int p = r * G + g;
             const bool active = p < Pd;
-            cx<T> v[B1][R1];
             if (interior) {
 #pragma unroll
-                for (int bb = 0; bb < B1; ++bb)
+                for (int b = 0; b < B1; ++b)
 #pragma unroll
-                    for (int r = 0; r < R1; ++r) {
-                        const long long off = boff + (long long)(B1 * t + bb + S1 * r) * Pd + p;
-                        v[bb][r] = active ? ld_cx(&in[off]) : cx<T>((T)0, (T)0);
+                    for (int k = 0; k < R1; ++k) {
+                        const int e = (B1 * t + b + S1 * k) * Pd + p;
+                        v[b][k] = active ? ld_cx(&bin[e]) : cx<T>((T)0, (T)0);
                     }
-                if (has_nco) {
-#pragma unroll
-                    for (int bb = 0; bb < B1; ++bb)
-#pragma unroll
-                        for (int r = 0; r < R1; ++r) {
-                            v[bb][r] = cmul(v[bb][r], ph[bb][r]);
-                            ph[bb][r] = cmul(ph[bb][r], rotG);
-                        }
-                }
             } else {
 #pragma unroll
-                for (int bb = 0; bb < B1; ++bb)
+                for (int b = 0; b < B1; ++b)
 #pragma unroll
-                    for (int r = 0; r < R1; ++r) {
-                        const long long off = boff + (long long)(B1 * t + bb + S1 * r) * Pd + p;
+                    for (int k = 0; k < R1; ++k) {
+                        const long long off = boff + (long long)(B1 * t + b + S1 * k) * Pd + p;
                         cx<T> x((T)0, (T)0);
                         if (active) {
                             if (off >= 0) {
-                                if (off < len) {
-                                    x = ld_cx(&in[off]);
-                                    if (has_nco) x = cmul(x, ph[bb][r]);
-                                }
+                                if (off < len) x = ld_cx(&in[off]);
                             } else if (off >= -hist_len) {
-                                x = ld_cx(&hist[off + hist_len]);  // already mixed
+                                x = ld_cx(&hist[off + hist_len]);
                             }
                         }
-                        v[bb][r] = x;
-                        if (has_nco) ph[bb][r] = cmul(ph[bb][r], rotG);
+                        v[b][k] = x;
                     }
             }
-            plan.p1_forward(smg, t, v);
+        };
+
+        cx<T> cp((T)1, (T)0);  // NCO phasor of sample (i = 0, p) of this block
+        load_round(0);
+        for (int r = 0; r < NR; ++r) {
+            const int p = r * G + g;
+            cx<T>* W = W0 + (C::NBUF == 2 ? (r & 1) : 0) * C::WORK;
+            if (has_nco && (r & 15) == 0) cp = nco_phasor_at<T>(boff + p, idx0, numer_abs, denom, sign, start);
+
+            // ---- NCO row part + pass 1 ------------------------------------------------
+            if (has_nco) {
+                if (interior) {
+#pragma unroll
+                    for (int b = 0; b < B1; ++b)
+#pragma unroll
+                        for (int k = 0; k < R1; ++k) v[b][k] = cmul(v[b][k], ld_cx(&phb[B1 * t + b + S1 * k]));
+                } else {
+                    // history samples are already mixed: cancel the c_p that the spectrum gets later
+#pragma unroll
+                    for (int b = 0; b < B1; ++b)
+#pragma unroll
+                        for (int k = 0; k < R1; ++k) {
+                            const long long off = boff + (long long)(B1 * t + b + S1 * k) * Pd + p;
+                            v[b][k] = (off >= 0) ? cmul(v[b][k], ld_cx(&phb[B1 * t + b + S1 * k])) : cmulc(v[b][k], cp);
+                        }
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < B1; ++b) {
+                dft_regs<R1, +1, T>(v[b]);
+                st_cx(&W[off1[b]], v[b][0]);
+#pragma unroll
+                for (int k = 1; k < R1; ++k) st_cx(&W[off1[b] + k * STR1], cmul(v[b][k], ld_cx(&tw1s[(B1 * t + b) * R1 + k])));
+            }
+            // ---- prefetch: next round's samples, this round's table entries -------------
+            if (r + 1 < NR) load_round(r + 1);
+            cx<T> gt0[B3][R3];
+            {
+                const cx<T>* gp = gtab + ((long long)r * K) * G + g;
+#pragma unroll
+                for (int b = 0; b < B3; ++b)
+#pragma unroll
+                    for (int k = 0; k < R3; ++k) gt0[b][k] = ld_cx(&gp[(k * KR + B3 * t + b) * G]);
+            }
             __syncthreads();
-            plan.template p2<+1>(smg, t);
+            // ---- pass 2 -------------------------------------------------------------------
+#pragma unroll
+            for (int b = 0; b < B2; ++b) {
+                cx<T> w[R2];
+#pragma unroll
+                for (int k = 0; k < R2; ++k) w[k] = ld_cx(&W[off2[b] + k * STR2]);
+                dft_regs<R2, +1, T>(w);
+                st_cx(&W[off2[b]], w[0]);
+#pragma unroll
+                for (int k = 1; k < R2; ++k) st_cx(&W[off2[b] + k * STR2], cmul(w[k], ld_cx(&tw2s[(B2 * t + b) * R2 + k])));
+            }
             __syncthreads();
+            // ---- pass 3 + NCO transform part + multiply-accumulate ---------------------------
 #pragma unroll
             for (int b = 0; b < B3; ++b) {
-                const int u = B3 * t + b;
-                cx<T> v3[R3];
-                P::p3_load(smg, u, v3);
-                dft_regs<R3, +1, T>(v3);
-                if (active) {
+                cx<T> w[R3];
 #pragma unroll
-                    for (int q = 0; q < Q; ++q) {
-                        const cx<T>* gt = gtab + ((long long)q * Pd + p) * K + u;
+                for (int k = 0; k < R3; ++k) w[k] = ld_cx(&W[off3[b] + k * STR3]);
+                dft_regs<R3, +1, T>(w);
+                if (has_nco) {
 #pragma unroll
-                        for (int k = 0; k < R3; ++k) {
-                            const cx<T> w = ld_cx(&gt[k * KR]);
-                            acc[q][b][k].x = fma(v3[k].x, w.x, fma(-v3[k].y, w.y, acc[q][b][k].x));
-                            acc[q][b][k].y = fma(v3[k].x, w.y, fma(v3[k].y, w.x, acc[q][b][k].y));
-                        }
+                    for (int k = 0; k < R3; ++k) w[k] = cmul(w[k], cp);
+                }
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+#pragma unroll
+                    for (int k = 0; k < R3; ++k) {
+                        cx<T> h;
+                        if (q == 0) h = gt0[b][k];
+                        else h = ld_cx(&gtab[(((long long)q * NR + r) * K + k * KR + B3 * t + b) * G + g]);
+                        acc[q][b][k].x = fma(w[k].x, h.x, fma(-w[k].y, h.y, acc[q][b][k].x));
+                        acc[q][b][k].y = fma(w[k].x, h.y, fma(w[k].y, h.x, acc[q][b][k].y));
                     }
                 }
             }
-            __syncthreads();  // pass-3 reads done before the next round's pass-1 writes
+            if (has_nco) cp = cmul(cp, rotG);
+            // two buffers: the next round works in the other one, and two barriers separate this
+            // round's reads from the round after next
+            if (C::NBUF == 1) __syncthreads();
         }
+        __syncthreads();
 
-        // ---- reduce the G partial spectra of this block, keep them per (block, phase)
+        // ---- reduce the G partial spectra of this block, park them per (block, phase) ------
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
 #pragma unroll
             for (int b = 0; b < B3; ++b)
 #pragma unroll
-                for (int k = 0; k < R3; ++k) st_cx(&W[(k * KR + B3 * t + b) * G + g], acc[q][b][k]);
+                for (int k = 0; k < R3; ++k) st_cx(&W0[(k * KR + B3 * t + b) * G + g], acc[q][b][k]);
             __syncthreads();
             cx<T>* ys = Ysave + ((long long)(blk - blk0) * Q + q) * K;
             for (int j = tid; j < K; j += THREADS) {
-                cx<T> sum = ld_cx(&W[j * G]);
+                cx<T> sum = ld_cx(&W0[j * G]);
 #pragma unroll
-                for (int gg = 1; gg < G; ++gg) sum = sum + ld_cx(&W[j * G + gg]);
+                for (int gg = 1; gg < G; ++gg) sum = sum + ld_cx(&W0[j * G + gg]);
                 st_cx(&ys[j], sum);
             }
             __syncthreads();
@@ -203,34 +313,48 @@ k_poly(const PolyArgs<T> a) {
     for (int j0 = 0; j0 < njobs; j0 += G) {
         const int job = j0 + g;
         const bool activej = job < njobs;
+        cx<T>* W = W0;
 #pragma unroll
         for (int b = 0; b < B3; ++b) {
-            const int u = B3 * t + b;
-            cx<T> v3[R3];
+            cx<T> w[R3];
 #pragma unroll
-            for (int k = 0; k < R3; ++k) v3[k] = activej ? ld_cx(&Ysave[(long long)job * K + k * KR + u]) : cx<T>((T)0, (T)0);
-            dft_regs<R3, -1, T>(v3);
-            P::p3_store(smg, u, v3);
+            for (int k = 0; k < R3; ++k) w[k] = activej ? ld_cx(&Ysave[(long long)job * K + k * KR + B3 * t + b]) : cx<T>((T)0, (T)0);
+            dft_regs<R3, -1, T>(w);
+#pragma unroll
+            for (int k = 0; k < R3; ++k) st_cx(&W[off3[b] + k * STR3], w[k]);
         }
         __syncthreads();
-        plan.template p2<-1>(smg, t);
+#pragma unroll
+        for (int b = 0; b < B2; ++b) {
+            cx<T> w[R2];
+            w[0] = ld_cx(&W[off2[b]]);
+#pragma unroll
+            for (int k = 1; k < R2; ++k) w[k] = cmulc(ld_cx(&W[off2[b] + k * STR2]), ld_cx(&tw2s[(B2 * t + b) * R2 + k]));
+            dft_regs<R2, -1, T>(w);
+#pragma unroll
+            for (int k = 0; k < R2; ++k) st_cx(&W[off2[b] + k * STR2], w[k]);
+        }
         __syncthreads();
-        cx<T> v[B1][R1];
-        plan.p1_inverse(smg, t, v);
-        if (activej) {
-            const int blk = blk0 + job / Q;
-            const int q = job % Q;
-            const long long Ibase = a.I_lo + (long long)blk * a.V - a.Lmax;
+        const int blk = blk0 + job / Q;
+        const int q = job % Q;
+        const long long Ibase = a.I_lo + (long long)blk * a.V - a.Lmax;
 #pragma unroll
-            for (int bb = 0; bb < B1; ++bb)
+        for (int b = 0; b < B1; ++b) {
+            cx<T> w[R1];
+            w[0] = ld_cx(&W[off1[b]]);
 #pragma unroll
-                for (int r = 0; r < R1; ++r) {
-                    const int i = B1 * t + bb + S1 * r;
+            for (int k = 1; k < R1; ++k) w[k] = cmulc(ld_cx(&W[off1[b] + k * STR1]), ld_cx(&tw1s[(B1 * t + b) * R1 + k]));
+            dft_regs<R1, -1, T>(w);
+            if (activej) {
+#pragma unroll
+                for (int k = 0; k < R1; ++k) {
+                    const int i = B1 * t + b + S1 * k;
                     if (i >= a.Lmax && i < a.Lmax + a.V) {
                         const long long m = (Ibase + i) * a.Q + q;
-                        if (m >= a.m_lo && m <= a.m_hi) st_cx(&out[m - a.m0 - 1], v[bb][r]);
+                        if (m >= a.m_lo && m <= a.m_hi) st_cx(&out[m - a.m0 - 1], w[k]);
                     }
                 }
+            }
         }
         __syncthreads();
     }
@@ -239,8 +363,7 @@ k_poly(const PolyArgs<T> a) {
 template <typename T, int K, int Q, int G>
 cudaError_t launch_poly_n(int n_streams, const PolyArgs<T>& a, cudaStream_t st) {
     using C = PolyCfg<T, K, G>;
-    using P = typename C::Plan;
-    const size_t smem = sizeof(cx<T>) * ((size_t)P::SMEM_ELEMS + (size_t)a.nbpc * Q * K);
+    const size_t smem = sizeof(cx<T>) * C::smem_elems(a.nbpc, Q);
     auto kern = k_poly<T, K, Q, G>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
