@@ -43,7 +43,9 @@ template <typename T, int K, int G> struct PolyCfg {
     static constexpr int R1 = Plan::R1, R2 = Plan::R2, R3 = Plan::R3;
     static constexpr int B1 = Plan::B1, B2 = Plan::B2, B3 = Plan::B3;
     static constexpr int S1 = Plan::S1, S2 = Plan::S2;
-    static constexpr int PAD = Plan::PAD, LOG_R3 = Plan::LOG_R3;
+    // one pad element per R3 run keeps every pass of the interleaved layout at the minimum number of
+    // shared-memory wavefronts for G = 8 and G = 10 (checked by enumeration)
+    static constexpr int PAD = 1, LOG_R3 = Plan::LOG_R3;
     static constexpr int ROW = K + PAD * (K / R3);  // padded elements per transform
     static constexpr int WORK = G * ROW;            // one interleaved work buffer
     // element strides (in complex elements) inside the interleaved layout
@@ -78,6 +80,24 @@ __device__ __forceinline__ cx<T> nco_rotation(long long d, uint32_t numer_abs, u
     return cx<T>((T)c, (T)(sign < 0 ? -s : s));
 }
 
+// (a * b) mod m for a, b < m < 2^31 without a 64-bit division: the quotient estimate from the
+// double reciprocal is off by at most one
+__device__ __forceinline__ uint32_t mulmod_fast(uint32_t a, uint32_t b, uint32_t m, double inv_m) {
+    const unsigned long long prod = (unsigned long long)a * b;
+    const unsigned long long q = (unsigned long long)((double)prod * inv_m);
+    long long r = (long long)(prod - q * m);
+    if (r < 0) r += m;
+    else if (r >= (long long)m) r -= m;
+    return (uint32_t)r;
+}
+
+// two adjacent complex values with the widest load available
+__device__ __forceinline__ void ld_pair(const cx<float>* p, cx<float>& a, cx<float>& b) { ld_cx2(p, a, b); }
+__device__ __forceinline__ void ld_pair(const cx<double>* p, cx<double>& a, cx<double>& b) {
+    a = ld_cx(p);
+    b = ld_cx(p + 1);
+}
+
 template <typename T, int K, int Q, int G>
 __global__ void __launch_bounds__(PolyCfg<T, K, G>::THREADS, 1)
 k_poly(const PolyArgs<T> a) {
@@ -85,6 +105,7 @@ k_poly(const PolyArgs<T> a) {
     constexpr int NT = C::NT, R1 = C::R1, R2 = C::R2, R3 = C::R3, B1 = C::B1, B2 = C::B2, B3 = C::B3;
     constexpr int S1 = C::S1, S2 = C::S2, THREADS = C::THREADS, KR = K / R3;
     constexpr int STR1 = C::STR1, STR2 = C::STR2, STR3 = C::STR3;
+    static_assert(R1 % 2 == 0 && R2 % 2 == 0, "table rows are read in pairs");
     const int tid = threadIdx.x;
     const int g = tid % G, t = tid / G;
     const int s = blockIdx.y;
@@ -92,36 +113,40 @@ k_poly(const PolyArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cx<T>* W0 = reinterpret_cast<cx<T>*>(smem_raw);
     cx<T>* tw1s = W0 + C::NBUF * C::WORK;  // [NT*B1][R1]  W_K^(k*q)
-    cx<T>* tw2s = tw1s + K;          // [NT*B2][R2]  W_(R2*R3)^(k*n3)
-    cx<T>* phb = tw2s + K;           // [K]          NCO rotation over i*P samples
-    cx<T>* Ysave = phb + K;          // [nbpc*Q][K]
+    cx<T>* tw2s = tw1s + K;                // [NT*B2][R2]  W_(R2*R3)^(k*n3)
+    cx<T>* phb = tw2s + K;                 // [NT*B1][R1]  NCO rotation over i*P samples, i = q + S1*k
+    cx<T>* Ysave = phb + K;                // [nbpc*Q][K]
 
     const cx<T>* __restrict__ in = reinterpret_cast<const cx<T>*>(a.in) + (long long)s * a.in_stride;
-    const cx<T>* __restrict__ hist = reinterpret_cast<const cx<T>*>(a.hist2) + (long long)s * 2 * a.n;
+    const cx<T>* __restrict__ hist_end = reinterpret_cast<const cx<T>*>(a.hist2) + ((long long)s + 1) * 2 * a.n;
     const cx<T>* __restrict__ gtab = reinterpret_cast<const cx<T>*>(a.gtab);
     const cx<T>* __restrict__ twK = reinterpret_cast<const cx<T>*>(a.twK);
     cx<T>* __restrict__ out = reinterpret_cast<cx<T>*>(a.out) + (long long)s * a.out_stride;
     const int Pd = (int)a.P;
     const int NR = (Pd + G - 1) / G;  // rounds per block
     const long long len = a.len, hist_len = 2 * a.n;
+    const long long row_stride = (long long)S1 * Pd;  // elements between the rows of one pass-1 butterfly
 
     // ---- NCO constants ---------------------------------------------------------
     const bool has_nco = (a.nco != nullptr);
-    uint32_t denom = 1, numer_abs = 0, idx0 = 0;
+    uint32_t denom = 1, numer_abs = 0;
     int sign = 0;
     T start = (T)0;
+    double inv_denom = 1.0;
     cx<T> rotG((T)1, (T)0);
+    uint32_t kblk = 0, kstep_blk = 0;  // table index of sample (i = 0, p = g) of the current block; its advance per block
     if (has_nco) {
         const NcoStream ns = a.nco[s];
         denom = ns.denom;
         numer_abs = ns.numer_abs;
         sign = ns.sign;
         start = (T)ns.start_phase;
-        idx0 = ns.idx;
+        inv_denom = 1.0 / (double)denom;
         rotG = nco_rotation<T>(G, numer_abs, denom, sign);
+        kstep_blk = (uint32_t)(((long long)a.V * Pd) % (long long)denom);
     }
 
-    // ---- per-thread invariant shared-memory offsets (elements, before + g) -------
+    // ---- per-thread invariant shared-memory offsets (elements, g included) -------
     int off1[B1], off2[B2], off3[B3];
 #pragma unroll
     for (int b = 0; b < B1; ++b) off1[b] = C::sidx(B1 * t + b) + g;
@@ -150,20 +175,81 @@ k_poly(const PolyArgs<T> a) {
             for (int k = 0; k < R2; ++k) st_cx(&tw2s[(B2 * t + b) * R2 + k], p[k]);
         }
     }
-    for (int i = tid; i < K; i += THREADS)
-        st_cx(&phb[i], has_nco ? nco_rotation<T>((long long)i * Pd, numer_abs, denom, sign) : cx<T>((T)1, (T)0));
+    for (int j = tid; j < K; j += THREADS) {
+        const int i = (j / R1) + S1 * (j % R1);  // slot (q, k) holds row i = q + S1*k
+        st_cx(&phb[j], has_nco ? nco_rotation<T>((long long)i * Pd, numer_abs, denom, sign) : cx<T>((T)1, (T)0));
+    }
     __syncthreads();
 
     const int blk0 = blockIdx.x * a.nbpc;
     const int blk1 = min(blk0 + a.nbpc, a.n_blocks);
 
-    for (int blk = blk0; blk < blk1; ++blk) {
+    // ---- per-block window: element (i, p) of block blk sits at push offset boff + i*P + p ------
+    long long boff = 0;
+    bool interior = false;
+    int lo = 0, hi = 0, hlo = 0;  // window-relative bounds: [lo, hi) pushed samples, [hlo, lo) history
+    const cx<T>* hbase = hist_end;  // history sample of window element rel at hbase[rel]
+    auto set_block = [&](int blk) {
         const long long Ibase = a.I_lo + (long long)blk * a.V - a.Lmax;
-        const long long boff = Ibase * Pd - a.J0 - Pd;  // push-relative offset of local element (i = 0, p = 0)
-        // blocks whose whole input window lies inside the pushed samples skip the range checks
-        const bool interior = (boff >= 0) && (boff + (long long)K * Pd <= len);
-        const cx<T>* __restrict__ bin = in + boff;  // element (i, p) at bin[i*Pd + p]
+        boff = Ibase * Pd - a.J0 - Pd;
+        const long long span = (long long)K * Pd;
+        interior = (boff >= 0) && (boff + span <= len);
+        const long long l = boff < 0 ? -boff : 0;
+        const long long h = len - boff;
+        lo = (int)(l < span ? l : span);
+        hi = (int)(h < 0 ? 0 : (h < span ? h : span));
+        const long long hl = l - hist_len;
+        hlo = (int)(hl < 0 ? 0 : (hl < span ? hl : span));
+        hbase = hist_end - l;
+    };
+    // raw load of round r of the current block for this thread's pass-1 butterflies
+    cx<T> v[B1][R1];
+    auto load_round = [&](int r) {
+        const int p = r * G + g;
+        const bool active = p < Pd;
+        const cx<T>* bin = in + boff;
+        if (interior) {
+#pragma unroll
+            for (int b = 0; b < B1; ++b) {
+                const cx<T>* q = bin + (long long)(B1 * t + b) * Pd + p;
+#pragma unroll
+                for (int k = 0; k < R1; ++k) {
+                    v[b][k] = active ? ld_cx(q) : cx<T>((T)0, (T)0);
+                    q += row_stride;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int b = 0; b < B1; ++b) {
+                int rel = (B1 * t + b) * Pd + p;
+#pragma unroll
+                for (int k = 0; k < R1; ++k) {
+                    cx<T> x((T)0, (T)0);
+                    if (active) {
+                        if (rel >= lo) {
+                            if (rel < hi) x = ld_cx(&bin[rel]);
+                        } else if (rel >= hlo) {
+                            x = ld_cx(&hbase[rel]);  // history: already mixed
+                        }
+                    }
+                    v[b][k] = x;
+                    rel += (int)row_stride;
+                }
+            }
+        }
+    };
 
+    if (blk0 < blk1) {
+        set_block(blk0);
+        if (has_nco) {
+            long long k0 = ((long long)a.nco[s].idx + boff + g) % (long long)denom;
+            if (k0 < 0) k0 += denom;
+            kblk = (uint32_t)k0;
+        }
+        load_round(0);
+    }
+
+    for (int blk = blk0; blk < blk1; ++blk) {
         cx<T> acc[Q][B3][R3];
 #pragma unroll
         for (int q = 0; q < Q; ++q)
@@ -172,72 +258,60 @@ k_poly(const PolyArgs<T> a) {
 #pragma unroll
                 for (int k = 0; k < R3; ++k) acc[q][b][k] = cx<T>((T)0, (T)0);
 
-        // raw load of round r's data for this thread's pass-1 butterflies
-        cx<T> v[B1][R1];
-        auto load_round = [&](int r) {
-            const int p = r * G + g;
-            const bool active = p < Pd;
-            if (interior) {
-#pragma unroll
-                for (int b = 0; b < B1; ++b)
-#pragma unroll
-                    for (int k = 0; k < R1; ++k) {
-                        const int e = (B1 * t + b + S1 * k) * Pd + p;
-                        v[b][k] = active ? ld_cx(&bin[e]) : cx<T>((T)0, (T)0);
-                    }
-            } else {
-#pragma unroll
-                for (int b = 0; b < B1; ++b)
-#pragma unroll
-                    for (int k = 0; k < R1; ++k) {
-                        const long long off = boff + (long long)(B1 * t + b + S1 * k) * Pd + p;
-                        cx<T> x((T)0, (T)0);
-                        if (active) {
-                            if (off >= 0) {
-                                if (off < len) x = ld_cx(&in[off]);
-                            } else if (off >= -hist_len) {
-                                x = ld_cx(&hist[off + hist_len]);
-                            }
-                        }
-                        v[b][k] = x;
-                    }
-            }
-        };
-
+        const bool cur_interior = interior;
+        const int cur_lo = lo;
         cx<T> cp((T)1, (T)0);  // NCO phasor of sample (i = 0, p) of this block
-        load_round(0);
         for (int r = 0; r < NR; ++r) {
             const int p = r * G + g;
             cx<T>* W = W0 + (C::NBUF == 2 ? (r & 1) : 0) * C::WORK;
-            if (has_nco && (r & 15) == 0) cp = nco_phasor_at<T>(boff + p, idx0, numer_abs, denom, sign, start);
+            if (has_nco && (r & 15) == 0) {
+                const uint32_t k = addmod_u32(kblk, (uint32_t)(r * G) % denom, denom);
+                cp = nco_phasor<T>(mulmod_fast(numer_abs, k, denom, inv_denom), denom, sign, start);
+            }
 
             // ---- NCO row part + pass 1 ------------------------------------------------
             if (has_nco) {
-                if (interior) {
+                if (cur_interior) {
 #pragma unroll
                     for (int b = 0; b < B1; ++b)
 #pragma unroll
-                        for (int k = 0; k < R1; ++k) v[b][k] = cmul(v[b][k], ld_cx(&phb[B1 * t + b + S1 * k]));
+                        for (int k = 0; k < R1; k += 2) {
+                            cx<T> f0, f1;
+                            ld_pair(&phb[(B1 * t + b) * R1 + k], f0, f1);
+                            v[b][k] = cmul(v[b][k], f0);
+                            v[b][k + 1] = cmul(v[b][k + 1], f1);
+                        }
                 } else {
                     // history samples are already mixed: cancel the c_p that the spectrum gets later
 #pragma unroll
-                    for (int b = 0; b < B1; ++b)
+                    for (int b = 0; b < B1; ++b) {
+                        int rel = (B1 * t + b) * Pd + p;
 #pragma unroll
                         for (int k = 0; k < R1; ++k) {
-                            const long long off = boff + (long long)(B1 * t + b + S1 * k) * Pd + p;
-                            v[b][k] = (off >= 0) ? cmul(v[b][k], ld_cx(&phb[B1 * t + b + S1 * k])) : cmulc(v[b][k], cp);
+                            v[b][k] = (rel >= cur_lo) ? cmul(v[b][k], ld_cx(&phb[(B1 * t + b) * R1 + k])) : cmulc(v[b][k], cp);
+                            rel += (int)row_stride;
                         }
+                    }
                 }
             }
 #pragma unroll
             for (int b = 0; b < B1; ++b) {
                 dft_regs<R1, +1, T>(v[b]);
+                cx<T> f[R1];
+#pragma unroll
+                for (int k = 0; k < R1; k += 2) ld_pair(&tw1s[(B1 * t + b) * R1 + k], f[k], f[k + 1]);
                 st_cx(&W[off1[b]], v[b][0]);
 #pragma unroll
-                for (int k = 1; k < R1; ++k) st_cx(&W[off1[b] + k * STR1], cmul(v[b][k], ld_cx(&tw1s[(B1 * t + b) * R1 + k])));
+                for (int k = 1; k < R1; ++k) st_cx(&W[off1[b] + k * STR1], cmul(v[b][k], f[k]));
             }
-            // ---- prefetch: next round's samples, this round's table entries -------------
-            if (r + 1 < NR) load_round(r + 1);
+            // ---- prefetch: next round's samples (of the next block after the last round), this
+            //      round's table entries ---------------------------------------------------
+            if (r + 1 < NR) {
+                load_round(r + 1);
+            } else if (blk + 1 < blk1) {
+                set_block(blk + 1);
+                load_round(0);
+            }
             cx<T> gt0[B3][R3];
             {
                 const cx<T>* gp = gtab + ((long long)r * K) * G + g;
@@ -250,13 +324,15 @@ k_poly(const PolyArgs<T> a) {
             // ---- pass 2 -------------------------------------------------------------------
 #pragma unroll
             for (int b = 0; b < B2; ++b) {
-                cx<T> w[R2];
+                cx<T> w[R2], f[R2];
 #pragma unroll
                 for (int k = 0; k < R2; ++k) w[k] = ld_cx(&W[off2[b] + k * STR2]);
+#pragma unroll
+                for (int k = 0; k < R2; k += 2) ld_pair(&tw2s[(B2 * t + b) * R2 + k], f[k], f[k + 1]);
                 dft_regs<R2, +1, T>(w);
                 st_cx(&W[off2[b]], w[0]);
 #pragma unroll
-                for (int k = 1; k < R2; ++k) st_cx(&W[off2[b] + k * STR2], cmul(w[k], ld_cx(&tw2s[(B2 * t + b) * R2 + k])));
+                for (int k = 1; k < R2; ++k) st_cx(&W[off2[b] + k * STR2], cmul(w[k], f[k]));
             }
             __syncthreads();
             // ---- pass 3 + NCO transform part + multiply-accumulate ---------------------------
@@ -287,6 +363,7 @@ k_poly(const PolyArgs<T> a) {
             // round's reads from the round after next
             if (C::NBUF == 1) __syncthreads();
         }
+        if (has_nco) kblk = addmod_u32(kblk, kstep_blk, denom);
         __syncthreads();
 
         // ---- reduce the G partial spectra of this block, park them per (block, phase) ------
