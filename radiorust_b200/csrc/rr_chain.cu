@@ -719,7 +719,8 @@ template <typename T> int poly_prepare(rr_chain* c, Stage& f, Stage& ds) {
     const size_t tab_bytes = (size_t)(Q * P) * (size_t)bestK * 2 * sizeof(T);
     if (tab_bytes > ((size_t)512 << 20)) return RR_OK;
     const double e8 = (double)P / (8.0 * (double)((P + 7) / 8)), e10 = (double)P / (10.0 * (double)((P + 9) / 10));
-    const int G = e10 > e8 + 1e-9 ? 10 : 8;
+    int G = e10 > e8 + 1e-9 ? 10 : 8;
+    if (const char* e = std::getenv("RR_POLY_G")) G = std::atoi(e) == 8 ? 8 : 10;
     if (!rr::poly_supported<T>(bestK, (int)Q, G)) return RR_OK;
     if (rr::poly_smem_bytes<T>(bestK, (int)Q, G, 1) > (size_t)220 * 1024) return RR_OK;
     std::vector<std::complex<double>> tab, perm;

@@ -55,6 +55,9 @@ template <typename T, int K, int G> struct PolyCfg {
     __host__ __device__ static constexpr int sidx(int p) { return G * (p + PAD * (p >> LOG_R3)); }
     // two alternating work buffers save one barrier per round; f64 keeps one (shared-memory budget)
     static constexpr int NBUF = (sizeof(T) == 4) ? 2 : 1;
+    // one CTA per SM: two would need <= 64 registers per thread, which spills the butterflies
+    // (measured: 105 vs 185 GS/s on config 3)
+    static constexpr int MIN_CTAS = 1;
     // shared memory: work buffers, 3 K-entry tables, nbpc*Q parked spectra
     __host__ __device__ static constexpr size_t smem_elems(int nbpc, int Q) {
         return (size_t)NBUF * WORK + 3 * (size_t)K + (size_t)nbpc * Q * K;
@@ -99,7 +102,7 @@ __device__ __forceinline__ void ld_pair(const cx<double>* p, cx<double>& a, cx<d
 }
 
 template <typename T, int K, int Q, int G>
-__global__ void __launch_bounds__(PolyCfg<T, K, G>::THREADS, 1)
+__global__ void __launch_bounds__(PolyCfg<T, K, G>::THREADS, PolyCfg<T, K, G>::MIN_CTAS)
 k_poly(const PolyArgs<T> a) {
     using C = PolyCfg<T, K, G>;
     constexpr int NT = C::NT, R1 = C::R1, R2 = C::R2, R3 = C::R3, B1 = C::B1, B2 = C::B2, B3 = C::B3;
