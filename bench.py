@@ -120,38 +120,24 @@ class ClockSampler:
 # ---------------------------------------------------------------------------
 # CPU arm: the reference's algorithm (oracle restatement) on the host cores
 # ---------------------------------------------------------------------------
-def _cpu_worker(args):
-    seed, n_streams, n_chunks = args
+def cpu_chain_run(cores: int, streams_per_core: int, n_chunks: int):
+    """Times the oracle's C restatement of the reference loops (oracle/radiorust_oracle.c) on `cores`
+    threads over independent streams; returns (MS/s, seconds, sample description)."""
+    from oracle import oracle_c
     from oracle import radiorust_oracle as orc
 
-    t_total = 0.0
-    for s in range(n_streams):
-        x = orc.synth_noise(seed + s, n_chunks * CHUNK_LEN, "f32")
-        ch = orc.Chain([
-            orc.FreqShifter("f32", 1.0, stream_shift(seed + s)),
-            orc.Filter.new("f32", orc.lowpass(CUTOFF)),
-            orc.Downsampler("f32", OUT_CHUNK, OUT_RATE, BANDWIDTH),
-        ])
-        ch.run(SAMPLE_RATE, x[: 2 * CHUNK_LEN], CHUNK_LEN)  # design filters outside the timed part
-        t0 = time.perf_counter()
-        ch.run(SAMPLE_RATE, x, CHUNK_LEN)
-        t_total += time.perf_counter() - t0
-    return t_total
-
-
-def cpu_chain_run(cores: int, streams_per_core: int, n_chunks: int):
-    """Times the oracle chain on `cores` processes; returns (MS/s, seconds, sample description)."""
-    import multiprocessing as mp
-
-    ctx = mp.get_context("spawn")
-    jobs = [(20260000 + 3 * 100000 + c * streams_per_core, streams_per_core, n_chunks) for c in range(cores)]
-    with ctx.Pool(cores) as pool:
-        pool.map(_cpu_worker, [(j[0], 1, 2) for j in jobs])  # warm the workers (imports, FFT plans)
-        t0 = time.perf_counter()
-        pool.map(_cpu_worker, jobs)
-        dt = time.perf_counter() - t0
-    samples = cores * streams_per_core * n_chunks * CHUNK_LEN
-    desc = f"{cores * streams_per_core} streams x {n_chunks} chunks x {CHUNK_LEN} samples of the same chain (numpy/scipy.fft oracle port)"
+    S = cores * streams_per_core
+    base = orc.synth_noise(20260000 + 3 * 100000, n_chunks * CHUNK_LEN, "f32")
+    x = np.stack([np.roll(base, 977 * s) for s in range(S)])
+    shifts = [stream_shift(s) for s in range(S)]
+    kw = dict(shifts=shifts, freq_resp=orc.lowpass(CUTOFF), down=(OUT_RATE, BANDWIDTH, 3.0), n_threads=cores)
+    oracle_c.chain(x[:cores, : 2 * CHUNK_LEN], "f32", SAMPLE_RATE, CHUNK_LEN, **{**kw, "shifts": shifts[:cores]})  # warm up
+    t = {}
+    oracle_c.chain(x, "f32", SAMPLE_RATE, CHUNK_LEN, timing=t, **kw)
+    dt = t["seconds"]
+    samples = S * n_chunks * CHUNK_LEN
+    desc = (f"{S} streams x {n_chunks} chunks x {CHUNK_LEN} samples of the same chain; C restatement of the reference loops "
+            f"(oracle/radiorust_oracle.c, gcc -O3, radix-2 FFT standing in for rustfft), {cores} pthreads over streams")
     return samples / dt / 1e6, dt, desc
 
 
@@ -169,7 +155,7 @@ def run_reference(args):
     cores = host_cores()
     vals = []
     for i in range(args.warmup + args.steps):
-        v, dt, desc = cpu_chain_run(cores, 2, 25)
+        v, dt, desc = cpu_chain_run(cores, 4, 400)
         if i >= args.warmup:
             vals.append((v, dt))
     value = float(np.mean([v for v, _ in vals]))
@@ -339,7 +325,7 @@ def run_cuda(args):
     }
     if world == 1 and not args.no_cpu:
         cores = host_cores()
-        v, dt, desc = cpu_chain_run(cores, 2, 25)
+        v, dt, desc = cpu_chain_run(cores, 4, 400)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc, "seconds": dt}
     print(json.dumps(line), flush=True)
     if dist is not None:

@@ -1,0 +1,112 @@
+"""C-ABI checks that need no GPU: the library loads, exports every symbol the header declares,
+fails loudly without a device, and its host-side design math equals the oracle's."""
+import ctypes as C
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import radiorust_oracle as orc
+from radiorust_b200 import _ffi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(_ffi.LIB_PATH):
+        from radiorust_b200 import build
+
+        build.build()
+    return _ffi.load()
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "radiorust_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rr_[a-z0-9_]+)\s*\(", src)) - {"rr_freq_resp_fn", "rr_window_fn"})
+
+
+def test_library_exports_every_header_symbol(lib):
+    names = header_functions()
+    assert len(names) >= 35
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/radiorust_b200.h but not exported"
+        assert n in _ffi.SIGNATURES, f"{n} has no ctypes signature"
+    assert sorted(_ffi.SIGNATURES) == names
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    h = C.c_void_p()
+    rc = lib.rr_ctx_create(0, C.byref(h))
+    assert rc == _ffi.RR_ERR_CUDA and not h.value
+    assert b"no CPU fallback" in lib.rr_last_error()
+
+
+def test_design_math_known_answers(lib):
+    """src/math.rs:57-85 through the C ABI."""
+    for x, want in [(0.5, 1.06348337074132), (1.23, 1.41552757215846), (15.8, 736184.938479417), (456.0, 2.04094157812291e196)]:
+        assert math.isclose(lib.rr_bessel_i0(x), want, rel_tol=1e-10)
+    assert math.isinf(lib.rr_bessel_i0(1e6)) and math.isnan(lib.rr_bessel_i0(float("nan")))
+    for x, want in [(0.4, 0.756826728640657), (2.6, 0.11643488132933186), (5.8, -0.03225825116512552), (0.0, 1.0)]:
+        assert math.isclose(lib.rr_sinc(x), want, rel_tol=1e-10, abs_tol=1e-15)
+    assert abs(lib.rr_sinc(3.0)) < 1e-15
+    assert lib.rr_kaiser_null_at_bin_to_beta(2.0) == math.sqrt(3.0)  # no pi factor (math.rs:37-39)
+    re_, im_ = C.c_double(), C.c_double()
+    lib.rr_deemphasis_factor(50e-6, 1000.0, C.byref(re_), C.byref(im_))
+    assert complex(re_.value, im_.value) == pytest.approx(orc.deemphasis_factor(50e-6, 1000.0), rel=1e-15)
+
+
+@pytest.mark.parametrize("sr,prec,f", [(1_024_000.0, 1.0, 123457.0), (1_024_000.0, 1.0, 100000.0), (2.4e6, 1.0, -577.0),
+                                       (48000.0, 0.5, 1234.0), (48000.0, 1.0, 0.0), (20e6, 1.0, 1_234_567.0)])
+def test_freq_to_ratio(lib, sr, prec, f):
+    n, d = C.c_int64(), C.c_int64()
+    assert lib.rr_freq_to_ratio(sr, prec, f, C.byref(n), C.byref(d)) == 0
+    assert (n.value, d.value) == orc.freq_to_ratio(sr, prec, f)
+
+
+@pytest.mark.parametrize("n,flt", [(64, "f64"), (4096, "f64"), (4096, "f32"), (1024, "f32")])
+def test_filter_design_matches_oracle(lib, n, flt):
+    sr = 1_024_000.0
+    resp = orc.lowpass(3000.0)
+    cb = _ffi.FREQ_RESP_FN(lambda u, b, f, re, im: (re.__setitem__(0, resp(b, f).real), im.__setitem__(0, resp(b, f).imag)) and None)
+    out = np.zeros(4 * n, dtype=np.float64)
+    rc = lib.rr_design_filter_response(cb, None, _ffi.RR_WINDOW_KAISER, math.sqrt(3.0), _ffi.WINDOW_FN(), None, sr, n,
+                                       _ffi.RR_C32 if flt == "f32" else _ffi.RR_C64, out.ctypes.data_as(C.POINTER(C.c_double)))
+    assert rc == 0
+    got = out[0::2] + 1j * out[1::2]
+    want = orc.design_filter_response(resp, orc.Kaiser.with_null_at_bin(2.0), sr, n, flt).astype(np.complex128)
+    # f64: both are f64 designs; f32: the reference runs the last FFT in f32, the library in f64
+    assert orc.rel_l2(got, want) <= (1e-12 if flt == "f64" else 5e-7)
+
+
+@pytest.mark.parametrize("down,in_rate,out_rate,bw,q,L", [(True, 1_024_000.0, 48000.0, 6000.0, 3.0, 147), (True, 2.4e6, 48000.0, 6000.0, 3.0, 343),
+                                                        (True, 10e6, 48000.0, 40000.0, 3.0, 7500), (True, 20e6, 48000.0, 6000.0, 3.0, 2858),
+                                                        (False, 48000.0, 2.4e6, 20000.0, 3.0, 515)])
+def test_resampler_taps_match_oracle(lib, down, in_rate, out_rate, bw, q, L):
+    fn = lib.rr_design_downsampler_taps if down else lib.rr_design_upsampler_taps
+    n = C.c_size_t(0)
+    assert fn(in_rate, out_rate, bw, q, C.byref(n), None) == 0
+    assert n.value == L
+    buf = np.zeros(L, dtype=np.float64)
+    n = C.c_size_t(L)
+    assert fn(in_rate, out_rate, bw, q, C.byref(n), buf.ctypes.data_as(C.POINTER(C.c_double))) == 0
+    blk = (orc.Downsampler if down else orc.Upsampler)("f64", 1, out_rate, bw, q)
+    blk._design(in_rate)
+    assert np.allclose(buf, blk.ir, rtol=1e-12, atol=1e-18)
+    assert math.isclose(float(np.sum(buf * buf)), 1.0, rel_tol=1e-12)  # unit energy (resampling.rs:96-98)
+
+
+def test_design_argument_errors(lib):
+    n = C.c_size_t(0)
+    assert lib.rr_design_downsampler_taps(8000.0, 48000.0, 6000.0, 3.0, C.byref(n), None) == _ffi.RR_ERR_INVALID
+    assert lib.rr_design_downsampler_taps(96000.0, 48000.0, 60000.0, 3.0, C.byref(n), None) == _ffi.RR_ERR_INVALID
+    d = C.c_int64()
+    assert lib.rr_freq_to_ratio(1.0, 10.0, 0.1, C.byref(d), C.byref(d)) == _ffi.RR_ERR_INVALID  # denominator rounds to 0
+    assert lib.rr_last_error()
