@@ -49,6 +49,7 @@ def translation_units():
         ("rr_big_os.o", "rr_big_os.cu", []),
         ("rr_chain_os_dispatch.o", "rr_chain_os_dispatch.cu", []),
         ("rr_poly.o", "rr_poly.cu", []),
+        ("rr_poly2.o", "rr_poly2.cu", []),
     ]
     for t, tn in (("float", "f32"), ("double", "f64")):
         for k in (256, 512, 1024):

@@ -185,6 +185,11 @@ struct Stage {
     DevBuf gtab, twK;
     bool poly_valid = false, poly_tried = false;
     int poly_K = 0, poly_G = 0, poly_Lmax = 0, poly_V = 0;
+    // k_poly2 (f32, Q == 1): its own table layout, K = 512
+    DevBuf gtab2, twK2;
+    bool poly2_tw_own = false;
+    bool poly2_valid = false;
+    int poly2_G = 0, poly2_V = 0;
     size_t obuf_cap = 0;  // samples per stream in obuf
     std::vector<double> ir_host;
     // FMDEMOD
@@ -206,6 +211,7 @@ struct rr_chain {
     DevBuf host_in, host_out;  // device staging of rr_chain_push
     std::string plan;
     bool allow_poly = true;  // rr_chain_set_fast_path
+    bool allow_poly2 = true; // RR_DISABLE_POLY2=1: keep the generic polyphase kernel (k_poly) for f32 too
     // optional CUDA-event timing of the dominant kernel of a push (bench.py's roofline)
     bool timing = false;
     std::vector<cudaEvent_t> evs;  // pairs (start, stop), one per timed launch since rr_chain_set_timing
@@ -698,6 +704,7 @@ template <typename T> int poly_prepare(rr_chain* c, Stage& f, Stage& ds) {
     if (ds.poly_tried) return RR_OK;
     ds.poly_tried = true;
     ds.poly_valid = false;
+    ds.poly2_valid = false;
     if (!f.taps_valid) return RR_OK;
     const long long P = ds.h.P, Q = ds.h.Q;
     const long long n = (long long)f.h.f_n, L = ds.h.r_L;
@@ -750,6 +757,27 @@ template <typename T> int poly_prepare(rr_chain* c, Stage& f, Stage& ds) {
     ds.poly_Lmax = (int)Lmax;
     ds.poly_V = (int)(bestK - 1 - Lmax);
     ds.poly_valid = true;
+
+    // the packed-fp32 / TMA kernel: complex f32, integer decimation, K = 512
+    if (std::is_same<T, float>::value && c->allow_poly2 && rr::poly2_supported(512, P, Q) && 511 - Lmax >= 128) {
+        const int K2 = 512, G2 = rr::poly2_pick_G(P);
+        if (bestK != K2) rr::design_poly_tables(f.taps, ds.ir_host_flt, P, Q, K2, &tab);
+        const double scale2 = 2.0 * (double)n / (double)K2;
+        const long long NR2 = (P + G2 - 1) / G2;
+        perm.assign((size_t)NR2 * (size_t)K2 * (size_t)G2, std::complex<double>(0.0, 0.0));
+        for (long long p = 0; p < P; ++p)
+            for (int k = 0; k < K2; ++k)
+                perm[(size_t)rr::poly2_table_index(G2, (int)(p / G2), (int)(p % G2), k)] = tab[(size_t)p * K2 + k] * scale2;
+        RR_TRY(upload_complex<T>(ds.gtab2, perm, c->stream));
+        if (bestK != K2) {
+            rr::make_twiddles((size_t)K2, &tw);
+            RR_TRY(upload_complex<T>(ds.twK2, tw, c->stream));
+        }
+        ds.poly2_tw_own = bestK != K2;
+        ds.poly2_G = G2;
+        ds.poly2_V = (int)(K2 - 1 - Lmax);
+        ds.poly2_valid = true;
+    }
     return RR_OK;
 }
 
@@ -831,6 +859,7 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
         // outputs m (1-based, counted with the reduced counters) firing inside this part
         const long long m_lo = m0 + 1;
         const long long m_hi = floordiv128(j0 + zlen, Qq, Pq);
+        bool used_poly2 = false;
         if (m_hi >= m_lo) {
             rr::PolyArgs<T> a{};
             // filter output k aligns with push sample k; the part starts at push sample ca*n, and the
@@ -852,22 +881,48 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
             a.m_hi = m_hi;
             a.I_lo = m_lo / Qq;
             const long long I_hi = m_hi / Qq;
-            a.n_blocks = (int)((I_hi - a.I_lo) / a.V + 1);
-            // blocks per CTA: one round of inverse transforms (G jobs) when the grid stays large enough
-            int nbpc = std::max(1, ds.poly_G / (int)Qq);
-            while (nbpc > 1 && rr::poly_smem_bytes<T>(ds.poly_K, (int)Qq, ds.poly_G, nbpc) > (size_t)200 * 1024) --nbpc;
-            while (nbpc > 1 && (long long)S * ((a.n_blocks + nbpc - 1) / nbpc) < 2LL * c->ctx->sm_count) --nbpc;
-            const int nsb = (a.n_blocks + nbpc - 1) / nbpc;
-            nbpc = (a.n_blocks + nsb - 1) / nsb;  // balance
-            a.nbpc = nbpc;
-            a.out = obase;
-            a.out_stride = ostride;
-            a.hist2 = f.hist2[f.hist_cur].p;
-            RR_TIMED_LAUNCH(c, "k_poly", 1, rr::launch_poly<T>(ds.poly_K, (int)Qq, ds.poly_G, S, a, st));
+            bool done = false;
+            if constexpr (std::is_same<T, float>::value) {
+                const bool tma_ok = ((uintptr_t)a.in % 16 == 0) && (S == 1 || a.in_stride % 2 == 0) && a.len < (1LL << 31);
+                if (ds.poly2_valid && tma_ok) {
+                    a.gtab = ds.gtab2.p;
+                    if (ds.poly2_tw_own) a.twK = ds.twK2.p;
+                    a.V = ds.poly2_V;
+                    a.n_blocks = (int)((I_hi - a.I_lo) / a.V + 1);
+                    const int G2 = ds.poly2_G;
+                    // blocks per CTA: bounded by the columns that run the inverse transforms and by the
+                    // shared memory that lets two CTAs share an SM
+                    int nbpc = G2;
+                    while (nbpc > 1 && rr::poly2_smem_bytes(G2, nbpc) > (size_t)226 * 1024) --nbpc;
+                    while (nbpc > 1 && (long long)((S + 1) / 2) * ((a.n_blocks + nbpc - 1) / nbpc) < 2LL * c->ctx->sm_count) --nbpc;
+                    const int nsb = (a.n_blocks + nbpc - 1) / nbpc;
+                    a.nbpc = (a.n_blocks + nsb - 1) / nsb;
+                    a.out = obase;
+                    a.out_stride = ostride;
+                    a.hist2 = f.hist2[f.hist_cur].p;
+                    RR_TIMED_LAUNCH(c, "k_poly2", 1, rr::launch_poly2(G2, S, a, st));
+                    done = true;
+                    used_poly2 = true;
+                }
+            }
+            if (!done) {
+                a.n_blocks = (int)((I_hi - a.I_lo) / a.V + 1);
+                // blocks per CTA: one round of inverse transforms (G jobs) when the grid stays large enough
+                int nbpc = std::max(1, ds.poly_G / (int)Qq);
+                while (nbpc > 1 && rr::poly_smem_bytes<T>(ds.poly_K, (int)Qq, ds.poly_G, nbpc) > (size_t)200 * 1024) --nbpc;
+                while (nbpc > 1 && (long long)S * ((a.n_blocks + nbpc - 1) / nbpc) < 2LL * c->ctx->sm_count) --nbpc;
+                const int nsb = (a.n_blocks + nbpc - 1) / nbpc;
+                nbpc = (a.n_blocks + nsb - 1) / nsb;  // balance
+                a.nbpc = nbpc;
+                a.out = obase;
+                a.out_stride = ostride;
+                a.hist2 = f.hist2[f.hist_cur].p;
+                RR_TIMED_LAUNCH(c, "k_poly", 1, rr::launch_poly<T>(ds.poly_K, (int)Qq, ds.poly_G, S, a, st));
+            }
         }
         ds.ztail_stale = true;
         if (!plan->empty() && plan->back() != '+' && plan->back() != '|' && ca > 0) *plan += "|";
-        *plan += "poly[filter+down]";
+        *plan += used_poly2 ? "poly2[filter+down]" : "poly[filter+down]";
     }
     return RR_OK;
 }
@@ -1272,6 +1327,7 @@ int rr_chain_create(rr_ctx* ctx, const rr_chain_desc* desc, rr_chain** out) {
         }
     }
     if (const char* e = std::getenv("RR_DISABLE_POLY")) c->allow_poly = !(e[0] == '1');
+    if (const char* e = std::getenv("RR_DISABLE_POLY2")) c->allow_poly2 = !(e[0] == '1');
     RR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     *out = c.release();
     return RR_OK;

@@ -141,6 +141,15 @@ template <typename T> int poly_hperm_index(int K, int k);
 template <typename T> size_t poly_smem_bytes(int K, int Q, int G, int nbpc);
 template <typename T> cudaError_t launch_poly(int K, int Q, int G, int n_streams, const PolyArgs<T>& a, cudaStream_t st);
 
+// ---- k_poly2 (rr_poly2.cu): the complex-f32, Q == 1 form of the polyphase chain on packed
+// fp32 instructions with TMA-fed tiles.  Same PolyArgs; `gtab` is laid out by poly2_table_index.
+bool poly2_supported(int K, long long P, long long Q);
+int poly2_pick_G(long long P);
+size_t poly2_smem_bytes(int G, int nbpc);
+// position (complex elements) of bin k of branch p = r*G + g in the device table
+long long poly2_table_index(int G, int r, int g, int k);
+cudaError_t launch_poly2(int G, int n_streams, const PolyArgs<float>& a, cudaStream_t st);
+
 // new hist2 = last 2n post-NCO samples of [hist2_in | in]
 template <typename T>
 cudaError_t launch_hist2_update(const void* in, long long in_stride, long long len, const void* hist2_in, void* hist2_out,

@@ -1,0 +1,518 @@
+// k_poly2: the complex-f32 throughput kernel of the fused chain
+// FreqShifter -> Filter -> Downsampler (integer decimation, Q == 1, even P).
+//
+// Same algebra as k_poly (rr_poly.cuh: P branch transforms of K = 512 points, a
+// multiply-accumulate against FFT_K(G[p]) and one inverse transform per block
+// of V*P input samples), re-laid out for the issue-slot budget of an sm_100a
+// SM -- k_poly is bound by instruction issue, not by HBM:
+//
+//   * every complex operation runs on the two-wide fp32 instructions
+//     (rr_pk.cuh): half the issue slots for the same arithmetic;
+//   * two passes instead of three: a radix-32 and two radix-16 butterflies per
+//     thread, 16 threads per transform, ONE shared-memory exchange per
+//     transform (conflict-free, constant offsets);
+//   * the input tile of a round ([K rows][G branches] of the stream, rows P
+//     samples apart) is brought in by one TMA tensor copy per round into a
+//     two-stage mbarrier pipeline: no load instructions, no address arithmetic
+//     and no load latency in the compute warps; the exchange reuses the
+//     consumed tile in place;
+//   * the NCO costs one complex multiply per sample: exp(j*w*(iP + p)) with
+//     i = 16*i1 + t splits into exp(j*w*P*t), folded into the pass-1 twiddles,
+//     and E[i1] * c_p (E[i1] = exp(j*w*16*P*i1), c_p the branch phasor), a
+//     32-entry table per branch column that the column's 16 threads rebuild
+//     for the next round while they work on the current one.
+//
+// Thread (g, t), tid = t*G + g: pass 1 transforms rows t + 16*i1 of branch
+// column g, pass 2 the bins k1 in {t, t+16}; it owns the 32 accumulators of
+// bins t + 16*which + 32*k2 of its column group.  The G partial spectra of a
+// block are summed through shared memory once per block, parked, and inverted
+// at the end by the same two-pass code (conjugate trick).
+//
+// One CTA = two independent halves (own stream, shared memory, mbarriers and
+// named barrier): the register file is per SM sub-partition, so 10 warps of 168
+// registers fit where two 5-warp CTAs would be rounded up.
+//
+// Blocks that reach before the pushed samples (into hist2, already mixed) take
+// thread-local global loads instead of the TMA tile; a last block that would
+// run past the pushed samples is moved back inside them.
+//
+// Reference semantics: transform.rs:333-348 (NCO), filters.rs:240-253
+// (overlap-save filter), resampling.rs:103-121 (decimating FIR).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <mutex>
+
+#include "rr_kernels.h"
+#include "rr_poly.cuh"
+#include "rr_pk.cuh"
+
+namespace rr {
+
+namespace {
+
+constexpr int K2 = 512;   // points per branch transform
+constexpr int NT2 = 16;   // threads per transform
+constexpr int ROWS_BOX = 256;
+
+template <int G> struct P2Cfg {
+    static constexpr int THREADS = NT2 * G;  // per half
+    // exchange: element (t, k1) of column g at t*TS + k1*G + g (8-byte elements); TS = 32G + (G mod 16)
+    // makes the pass-1 stores (lanes (g, t), fixed k1) and the pass-2 loads (lanes (g, tt), fixed t)
+    // land on `tid + const`: consecutive lanes, consecutive words
+    static constexpr int TS = 32 * G + (G % 16);
+    static constexpr int TILE_BYTES = K2 * G * 8;
+    static constexpr int XCH_BYTES = 16 * TS * 8;
+    static constexpr int STAGE_BYTES = (((TILE_BYTES > XCH_BYTES ? TILE_BYTES : XCH_BYTES) + 127) / 128) * 128;
+    static constexpr int TW_UNITS = 17;              // 16-byte units per twiddle row t (16 + 1 pad)
+    static constexpr int TW_BYTES = 16 * TW_UNITS * 16;
+    static constexpr int E_BYTES = 48 * 8;           // E[32] | rowph[16]
+    static constexpr int ECP_BYTES = 16 * G * 16;    // one buffer of E[i1]*c_p: unit (m, g) = entries i1 = 2m, 2m+1 of column g
+    static constexpr int YS_STRIDE = K2 + 1;         // parked spectrum stride (elements)
+    static constexpr int OFF_STAGE = 0;
+    static constexpr int OFF_TW = 2 * STAGE_BYTES;
+    static constexpr int OFF_E = OFF_TW + TW_BYTES;
+    static constexpr int OFF_ECP = OFF_E + E_BYTES;
+    static constexpr int OFF_BAR = OFF_ECP + 2 * ECP_BYTES;
+    static constexpr int OFF_YS = OFF_BAR + 16;
+    __host__ __device__ static size_t half_bytes(int nbpc) { return (((size_t)OFF_YS + (size_t)nbpc * YS_STRIDE * 8) + 127) / 128 * 128; }
+    static size_t smem_bytes(int nbpc) { return 2 * half_bytes(nbpc); }
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+        "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+__device__ __forceinline__ pc lds_pc(uint32_t addr) {
+    pc r;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ void lds_pc2(uint32_t addr, pc& a, pc& b) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(b.x), "=f"(b.y) : "r"(addr));
+}
+__device__ __forceinline__ void sts_pc(uint32_t addr, pc a) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a.x), "f"(a.y) : "memory");
+}
+__device__ __forceinline__ void sts_pc2(uint32_t addr, pc a, pc b) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y) : "memory");
+}
+// read-only table load that stays where it is written (volatile asm is not moved across the barriers,
+// so the load is in flight while the half waits)
+__device__ __forceinline__ void ldg_pc2(const float4* p, pc& a, pc& b) {
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(b.x), "=f"(b.y) : "l"(p));
+}
+
+// pass 1 of the K-point forward transform of this thread's 32 inputs (rows t + 16*i1): radix-32
+// butterfly, twiddles from table row `tw_row`, result into the exchange area
+template <int G>
+__device__ __forceinline__ void pass1_store(pc (&v)[32], uint32_t tw_row, uint32_t xch_wr) {
+    pdft_regs<32, +1>(v);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        pc w0, w1;
+        lds_pc2(tw_row + m * 16, w0, w1);
+        sts_pc(xch_wr + (2 * m) * (G * 8), pcmul(v[2 * m], w0));
+        sts_pc(xch_wr + (2 * m + 1) * (G * 8), pcmul(v[2 * m + 1], w1));
+    }
+}
+
+}  // namespace
+
+template <int G, bool HAS_NCO>
+__global__ void __launch_bounds__(2 * NT2 * G, 1) k_poly2(const __grid_constant__ CUtensorMap tmap, const PolyArgs<float> a, const int n_streams) {
+    using C = P2Cfg<G>;
+    constexpr int THREADS = C::THREADS;
+    const int half = threadIdx.x >= THREADS ? 1 : 0;
+    const int tid = threadIdx.x - half * THREADS;
+    const int g = tid % G, t = tid / G;
+    const int s = blockIdx.y * 2 + half;
+    if (s >= n_streams) return;  // the halves never meet at a CTA-wide barrier
+    auto sync_half = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(half + 1), "n"(THREADS) : "memory"); };
+
+    extern __shared__ __align__(128) unsigned char smem_all[];
+    unsigned char* smem = smem_all + (size_t)half * C::half_bytes(a.nbpc);
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bar0 = sbase + C::OFF_BAR;
+    const uint32_t e_tab = sbase + C::OFF_E;
+    const uint32_t ecp = sbase + C::OFF_ECP;
+    const uint32_t tw_row = sbase + C::OFF_TW + t * (C::TW_UNITS * 16);
+    // exchange addresses inside a stage: store element (t, k1 = 0), load element (t' = 0, k1 = t)
+    const uint32_t xch_wr = (C::TS * t + g) * 8;
+    const uint32_t xch_rd = tid * 8;
+    float2* ysave = reinterpret_cast<float2*>(smem + C::OFF_YS);
+
+    const float2* __restrict__ in = reinterpret_cast<const float2*>(a.in) + (long long)s * a.in_stride;
+    const float2* __restrict__ hist_end = reinterpret_cast<const float2*>(a.hist2) + ((long long)s + 1) * 2 * a.n;
+    const float4* __restrict__ gtab = reinterpret_cast<const float4*>(a.gtab);
+    float2* __restrict__ out = reinterpret_cast<float2*>(a.out) + (long long)s * a.out_stride;
+    const int Pd = (int)a.P;
+    const int NR = (Pd + G - 1) / G;
+    const long long len = a.len, hist_len = 2 * a.n;
+
+    // ---- NCO constants, tables -------------------------------------------------------------
+    uint32_t denom = 1, numer_abs = 0, idx0 = 0;
+    int sign = 0;
+    float start = 0.f;
+    pc rotG(1.f, 0.f);
+    if (HAS_NCO) {
+        const NcoStream ns = a.nco[s];
+        denom = ns.denom;
+        numer_abs = ns.numer_abs;
+        sign = ns.sign;
+        idx0 = ns.idx;
+        start = (float)ns.start_phase;
+        const cx<float> r = nco_rotation<float>(G, numer_abs, denom, sign);
+        rotG = pc(r.x, r.y);
+    }
+    {
+        float2* et = reinterpret_cast<float2*>(smem + C::OFF_E);
+        if (tid < 48) {
+            cx<float> r(1.f, 0.f);
+            if (HAS_NCO) r = nco_rotation<float>(tid < 32 ? (long long)16 * Pd * tid : (long long)Pd * (tid - 32), numer_abs, denom, sign);
+            et[tid] = make_float2(r.x, r.y);
+        }
+        if (tid == 0) {
+            mbar_init(bar0, 1);
+            mbar_init(bar0 + 8, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        sync_half();
+        // pass-1 twiddles W_K^(t*k1), times the NCO's row part exp(j*w*P*t)
+        const float2* __restrict__ twK = reinterpret_cast<const float2*>(a.twK);
+        for (int e = tid; e < K2; e += THREADS) {
+            const int tr = e >> 5, k1 = e & 31;
+            const float2 w = twK[(tr * k1) & (K2 - 1)];
+            const float2 rp = et[32 + tr];
+            const int off = (tr * C::TW_UNITS + (k1 >> 1)) * 16 + (k1 & 1) * 8;
+            *reinterpret_cast<float2*>(smem + C::OFF_TW + off) = make_float2(w.x * rp.x - w.y * rp.y, w.x * rp.y + w.y * rp.x);
+        }
+        sync_half();
+    }
+    const pc rowph = lds_pc(e_tab + (32 + t) * 8);
+    // this thread's two entries of the E table (it maintains entries 2t, 2t+1 of its column's E*c_p)
+    pc e_mine0(1.f, 0.f), e_mine1(1.f, 0.f);
+    if (HAS_NCO) lds_pc2(e_tab + (2 * t) * 8, e_mine0, e_mine1);
+    const uint32_t ecp_wr = ecp + (t * G + g) * 16;
+    const uint32_t ecp_rd = ecp + g * 16;
+
+    const int blk0 = blockIdx.x * a.nbpc;
+    const int blk1 = min(blk0 + a.nbpc, a.n_blocks);
+
+    // window of block blk: element (i, p) sits at push offset boff + i*P + p.  "Interior" blocks lie
+    // completely inside the pushed samples and are fed by TMA.  A block whose window would run past
+    // the pushed samples is moved back by `d` rows so that it still lies inside them (its first d
+    // outputs repeat the previous block's and are not stored).
+    const long long need = (long long)(K2 - 1) * Pd + (long long)NR * G;  // samples a tile sweep touches
+    auto block_shift = [&](int blk) -> int {
+        const long long Ibase = a.I_lo + (long long)blk * a.V - a.Lmax;
+        const long long boff = Ibase * Pd - a.J0 - Pd;
+        if (blk == 0 || boff + need <= len) return 0;  // block 0 has no predecessor to cover the skipped outputs
+        const long long d = (boff + need - len + Pd - 1) / Pd;
+        // with Q == 1 the l = -1 slot of every branch filter is empty, so row K-1 is a valid output too:
+        // the moved block may use it to reach m_hi
+        return (d < a.V && boff - d * Pd >= 0 && a.m_hi - (Ibase - d) <= K2 - 1) ? (int)d : 0;
+    };
+    auto block_off = [&](int blk) -> long long {
+        const long long Ibase = a.I_lo + (long long)blk * a.V - a.Lmax - block_shift(blk);
+        return Ibase * Pd - a.J0 - Pd;
+    };
+    auto is_interior = [&](long long boff) -> bool { return boff >= 0 && boff + need <= len; };
+    auto issue_tile = [&](int stage, long long boff, int r) {
+        const uint32_t bar = bar0 + stage * 8;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar, C::TILE_BYTES);
+        tma_load_4d(sbase + C::OFF_STAGE + stage * C::STAGE_BYTES, &tmap, bar, (int)(boff + (long long)r * G), 0, 0, s);
+    };
+
+    int R = 0;           // rounds executed by this half
+    uint32_t phase = 0;  // bit `stage`: parity to wait for next
+    if (blk0 < blk1 && tid == 0) {
+        const long long b0 = block_off(blk0);
+        if (is_interior(b0)) issue_tile(0, b0, 0);
+    }
+
+    for (int blk = blk0; blk < blk1; ++blk) {
+        const long long boff = block_off(blk);
+        const bool interior = is_interior(boff);
+        const bool have_next = blk + 1 < blk1;
+        const long long boff_next = have_next ? block_off(blk + 1) : 0;
+        const bool next_interior = have_next && is_interior(boff_next);
+
+        pc cp(1.f, 0.f);  // NCO phasor of sample (i = 0, p = r*G + g) of this block, r = next round to prepare
+        if (HAS_NCO) {
+            long long k0 = ((long long)idx0 + boff + g) % (long long)denom;
+            if (k0 < 0) k0 += denom;
+            const cx<float> c = nco_phasor<float>(mulmod_u32(numer_abs, (uint32_t)k0, denom), denom, sign, start);
+            cp = pc(c.x, c.y);
+            // E*c_p of round 0 (read after barrier A of that round)
+            sts_pc2(ecp_wr + (R & 1) * C::ECP_BYTES, pcmul(e_mine0, cp), pcmul(e_mine1, cp));
+        }
+        pc acc[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = pc(0.f, 0.f);
+
+        for (int r = 0; r < NR; ++r, ++R) {
+            const int stage = R & 1;
+            const uint32_t stg = sbase + C::OFF_STAGE + stage * C::STAGE_BYTES;
+            pc v[32];
+            long long pos0 = 0;
+            if (interior) {
+                mbar_wait(bar0 + stage * 8, (phase >> stage) & 1);
+                phase ^= 1u << stage;
+                const uint32_t src = stg + tid * 8;
+#pragma unroll
+                for (int i1 = 0; i1 < 32; ++i1) v[i1] = lds_pc(src + i1 * (THREADS * 8));
+            } else {
+                // all loads first (independent, predicated); history samples are already mixed
+                const int p = r * G + g;
+                pos0 = boff + (long long)t * Pd + p;
+                const long long step = (long long)16 * Pd;
+#pragma unroll
+                for (int i1 = 0; i1 < 32; ++i1) {
+                    const long long pos = pos0 + i1 * step;
+                    const bool ok = p < Pd && pos < len && pos >= -hist_len;
+                    const float2* ptr = pos >= 0 ? in + pos : hist_end + pos;
+                    float2 q = make_float2(0.f, 0.f);
+                    if (ok) q = __ldg(ptr);
+                    v[i1] = pc(q.x, q.y);
+                }
+            }
+            sync_half();  // A: the tile is consumed, the other stage's exchange reads are over
+            if (tid == 0) {
+                if (r + 1 < NR) {
+                    if (interior) issue_tile(stage ^ 1, boff, r + 1);
+                } else if (next_interior) {
+                    issue_tile(stage ^ 1, boff_next, 0);
+                }
+            }
+            if (HAS_NCO) {
+                const uint32_t esrc = ecp_rd + stage * C::ECP_BYTES;
+                if (interior) {
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) {
+                        pc e0, e1;
+                        lds_pc2(esrc + m * (G * 16), e0, e1);
+                        v[2 * m] = pcmul(v[2 * m], e0);
+                        v[2 * m + 1] = pcmul(v[2 * m + 1], e1);
+                    }
+                } else {
+                    // history: cancel the row part that the twiddles will apply (no c_p, no E for them)
+                    const pc hc(rowph.x, -rowph.y);
+                    const long long step = (long long)16 * Pd;
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) {
+                        pc e0, e1;
+                        lds_pc2(esrc + m * (G * 16), e0, e1);
+                        v[2 * m] = pcmul(v[2 * m], (pos0 + (2 * m) * step) >= 0 ? e0 : hc);
+                        v[2 * m + 1] = pcmul(v[2 * m + 1], (pos0 + (2 * m + 1) * step) >= 0 ? e1 : hc);
+                    }
+                }
+                // next round's E*c_p (other buffer; its readers are past barrier A of that round)
+                cp = pcmul(cp, rotG);
+                if (r + 1 < NR) sts_pc2(ecp_wr + (stage ^ 1) * C::ECP_BYTES, pcmul(e_mine0, cp), pcmul(e_mine1, cp));
+            }
+            pass1_store<G>(v, tw_row, stg + xch_wr);
+
+            // table entries of this round: [r][which][jj][tid] (two bins each)
+            const float4* gp = gtab + ((long long)r * 16) * THREADS + tid;
+            pc h[16];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) ldg_pc2(gp + jj * THREADS, h[2 * jj], h[2 * jj + 1]);
+            sync_half();  // B
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {
+                pc x[16];
+#pragma unroll
+                for (int tr = 0; tr < 16; ++tr) x[tr] = lds_pc(stg + xch_rd + (tr * C::TS + which * 16 * G) * 8);
+                pdft_regs<16, +1>(x);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) acc[which * 16 + k] = pcfma(x[k], h[k], acc[which * 16 + k]);
+                if (which == 0) {
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) ldg_pc2(gp + (8 + jj) * THREADS, h[2 * jj], h[2 * jj + 1]);
+                }
+            }
+        }
+
+        // ---- sum the G partial spectra of this block, park the result --------------------------
+        {
+            const uint32_t stg = sbase + C::OFF_STAGE + ((R - 1) & 1) * C::STAGE_BYTES;
+            sync_half();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sts_pc(stg + (j * THREADS + tid) * 8, acc[j]);
+            sync_half();
+            float2* ys = ysave + (blk - blk0) * C::YS_STRIDE;
+            for (int o = tid; o < K2; o += THREADS) {
+                const int j = o >> 4, tt = o & 15;
+                const uint32_t src = stg + (j * THREADS + tt * G) * 8;
+                pc sum(0.f, 0.f);
+                if (G % 2 == 0) {
+#pragma unroll
+                    for (int gg = 0; gg < G; gg += 2) {
+                        pc u0, u1;
+                        lds_pc2(src + gg * 8, u0, u1);
+                        sum = sum + u0;
+                        sum = sum + u1;
+                    }
+                } else {
+#pragma unroll
+                    for (int gg = 0; gg < G; ++gg) sum = sum + lds_pc(src + gg * 8);
+                }
+                const int bin = tt + 16 * (j >> 4) + 32 * (j & 15);
+                ys[bin] = make_float2(sum.x, sum.y);
+            }
+        }
+    }
+    sync_half();
+
+    // ---- inverse transforms: column g takes job g (one parked block spectrum) ------------------
+    const int njobs = blk1 - blk0;
+    for (int j0 = 0; j0 < njobs; j0 += G) {
+        const int job = j0 + g;
+        const bool active = job < njobs;
+        const uint32_t stg = sbase + C::OFF_STAGE;
+        pc v[32];
+        const float2* ys = ysave + (active ? job : 0) * C::YS_STRIDE;
+        // conj in, conj out = inverse transform; the table's NCO row part is cancelled on the way in
+        const pc hc(rowph.x, -rowph.y);
+#pragma unroll
+        for (int i1 = 0; i1 < 32; ++i1) {
+            const float2 q = ys[t + 16 * i1];
+            v[i1] = active ? pcmul(pc(q.x, -q.y), hc) : pc(0.f, 0.f);
+        }
+        pass1_store<G>(v, tw_row, stg + xch_wr);
+        sync_half();
+        const int blk = blk0 + (active ? job : 0);
+        const int d = block_shift(blk);
+        const long long Ibase = a.I_lo + (long long)blk * a.V - a.Lmax - d;
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+            pc x[16];
+#pragma unroll
+            for (int tr = 0; tr < 16; ++tr) x[tr] = lds_pc(stg + xch_rd + (tr * C::TS + which * 16 * G) * 8);
+            pdft_regs<16, +1>(x);
+            if (active) {
+#pragma unroll
+                for (int k2 = 0; k2 < 16; ++k2) {
+                    const int i = t + 16 * which + 32 * k2;
+                    if (i >= a.Lmax + d && i < a.Lmax + a.V + (d > 0 ? 1 : 0)) {
+                        const long long m = Ibase + i;  // Q == 1
+                        if (m >= a.m_lo && m <= a.m_hi) out[m - a.m0 - 1] = make_float2(x[k2].x, -x[k2].y);
+                    }
+                }
+            }
+        }
+        sync_half();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+namespace {
+
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                              const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn encode_fn() {
+    static EncodeFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeFn>(p);
+    });
+    return fn;
+}
+
+template <int G> cudaError_t launch_g(int n_streams, const PolyArgs<float>& a, const CUtensorMap& tm, cudaStream_t st) {
+    using C = P2Cfg<G>;
+    const size_t smem = C::smem_bytes(a.nbpc);
+    const dim3 grid((unsigned)((a.n_blocks + a.nbpc - 1) / a.nbpc), (unsigned)((n_streams + 1) / 2));
+    cudaError_t e;
+    if (a.nco) {
+        auto kern = k_poly2<G, true>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, 2 * C::THREADS, smem, st>>>(tm, a, n_streams);
+    } else {
+        auto kern = k_poly2<G, false>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, 2 * C::THREADS, smem, st>>>(tm, a, n_streams);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+int poly2_pick_G(long long P) {
+    // branches per round: even (TMA rows are 16-byte multiples) and as few idle columns as possible
+    int best = 0;
+    double best_eff = 0.0;
+    for (int G : {10, 8}) {
+        const double eff = (double)P / (double)(G * ((P + G - 1) / G));
+        if (eff > best_eff + 1e-9) {
+            best = G;
+            best_eff = eff;
+        }
+    }
+    return best;
+}
+
+bool poly2_supported(int K, long long P, long long Q) { return K == K2 && Q == 1 && P >= 2 && (P % 2) == 0 && encode_fn() != nullptr; }
+
+size_t poly2_smem_bytes(int G, int nbpc) { return G == 8 ? P2Cfg<8>::smem_bytes(nbpc) : P2Cfg<10>::smem_bytes(nbpc); }
+
+long long poly2_table_index(int G, int r, int g, int k) {
+    const int threads = NT2 * G;
+    const int k1 = k & 31, k2 = k >> 5;
+    const int tt = k1 & 15, which = k1 >> 4;
+    const int tid = tt * G + g;
+    return ((((long long)r * 2 + which) * 8 + (k2 >> 1)) * threads + tid) * 2 + (k2 & 1);
+}
+
+cudaError_t launch_poly2(int G, int n_streams, const PolyArgs<float>& a, cudaStream_t st) {
+    EncodeFn enc = encode_fn();
+    if (!enc) return cudaErrorNotSupported;
+    // the stream as overlapping rows: element (c0, i_lo, i_hi, s) = in[s*in_stride + c0 + (i_lo + 256*i_hi)*P]
+    CUtensorMap tm;
+    const cuuint64_t dims[4] = {(cuuint64_t)a.len, (cuuint64_t)ROWS_BOX, (cuuint64_t)(K2 / ROWS_BOX), (cuuint64_t)n_streams};
+    const cuuint64_t sstride = n_streams > 1 ? (cuuint64_t)a.in_stride * 8 : (((cuuint64_t)a.len * 8 + 15) / 16) * 16;
+    const cuuint64_t strides[3] = {(cuuint64_t)a.P * 8, (cuuint64_t)a.P * 8 * ROWS_BOX, sstride};
+    const cuuint32_t box[4] = {(cuuint32_t)G, (cuuint32_t)ROWS_BOX, (cuuint32_t)(K2 / ROWS_BOX), 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(a.in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    if (G == 8) return launch_g<8>(n_streams, a, tm, st);
+    if (G == 10) return launch_g<10>(n_streams, a, tm, st);
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace rr
