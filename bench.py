@@ -250,6 +250,7 @@ def run_cuda(args):
     launches = rr.kernel_launch_count() - launches0
     elapsed_ms = e0.elapsed_time(e1)
     k_ms, k_n, k_name = chain.kernel_time()
+    k_all = chain.kernel_breakdown()
     chain.set_timing(False)
     plan = chain.plan
     if dist is not None:
@@ -320,6 +321,8 @@ def run_cuda(args):
             "traffic": args.traffic, "peak_kind": peak_kind, "kernel": k_name, "kernel_ms": k_avg_ms, "kernel_launches": k_n,
             "algorithmic_bytes_per_launch": samples_step * BYTES_PER_SAMPLE,
             "kernel_share_of_step": (k_ms / elapsed_ms) if elapsed_ms else None,
+            "kernels": {nm: {"ms_per_launch": ms / max(n, 1), "launches": n, "share_of_step": ms / elapsed_ms}
+                        for nm, (ms, n) in k_all.items()},
         },
         "output_samples_per_step": out_total // max(args.steps, 1),
     }

@@ -191,11 +191,14 @@ int rr_chain_sync(rr_chain* chain);
 int rr_chain_set_fast_path(rr_chain* chain, int enable);
 /* Measurement aid: while enabled, CUDA events on the chain's stream bracket the
  * dominant kernel of every push (no synchronisation is added).
- * rr_chain_kernel_time waits for the recorded pairs and returns their summed
- * duration, their count and the kernel's name; rr_chain_set_timing(.., 1)
- * restarts the record. */
+ * rr_chain_kernel_time waits for the recorded pairs and returns, for the kernel
+ * with the largest summed duration, that duration, its launch count and its
+ * name; rr_chain_set_timing(.., 1) restarts the record. */
 int rr_chain_set_timing(rr_chain* chain, int enable);
 int rr_chain_kernel_time(rr_chain* chain, double* total_ms, int* n_launches, const char** kernel_name);
+/* every timed kernel of the record as "name:total_ms:launches;..." (valid after rr_chain_kernel_time,
+ * which reports the one with the largest total) */
+const char* rr_chain_kernel_breakdown(rr_chain* chain);
 /* raw cudaStream_t of the chain (for event timing by the caller) */
 void* rr_chain_cuda_stream(rr_chain* chain);
 /* name of the execution plan chosen at the last push (diagnostics), e.g.

@@ -101,6 +101,7 @@ SIGNATURES = {
     "rr_chain_set_fast_path": (_I, [_P, _I]),
     "rr_chain_set_timing": (_I, [_P, _I]),
     "rr_chain_kernel_time": (_I, [_P, C.POINTER(_D), C.POINTER(_I), C.POINTER(C.c_char_p)]),
+    "rr_chain_kernel_breakdown": (C.c_char_p, [_P]),
     "rr_chain_cuda_stream": (_P, [_P]),
     "rr_chain_plan": (C.c_char_p, [_P]),
 }

@@ -50,6 +50,7 @@ def translation_units():
         ("rr_chain_os_dispatch.o", "rr_chain_os_dispatch.cu", []),
         ("rr_poly.o", "rr_poly.cu", []),
         ("rr_poly2.o", "rr_poly2.cu", []),
+        ("rr_front.o", "rr_front.cu", []),
     ]
     for t, tn in (("float", "f32"), ("double", "f64")):
         for k in (256, 512, 1024):

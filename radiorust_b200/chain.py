@@ -319,6 +319,15 @@ class Chain:
         check(self._lib.rr_chain_kernel_time(self._h, C.byref(ms), C.byref(cnt), C.byref(name)))
         return ms.value, cnt.value, (name.value or b"").decode()
 
+    def kernel_breakdown(self):
+        """{kernel name: (total ms, launches)} of every timed kernel (call after ``kernel_time``)."""
+        out = {}
+        for item in self._lib.rr_chain_kernel_breakdown(self._h).decode().split(";"):
+            if item:
+                name, ms, cnt = item.rsplit(":", 2)
+                out[name] = (float(ms), int(cnt))
+        return out
+
     @property
     def cuda_stream(self) -> int:
         return int(self._lib.rr_chain_cuda_stream(self._h) or 0)

@@ -188,6 +188,11 @@ struct Stage {
     // k_poly2 (f32, Q == 1): its own table layout, K = 512
     DevBuf gtab2, twK2;
     bool poly2_tw_own = false;
+    // rank-reduced front end (k_front) + k_poly2 on its output: coefficient table, low-rate table, scratch
+    DevBuf acoef, gtab3, ubuf;
+    bool front_valid = false;
+    int front_rank = 0;
+    double front_discarded = 0.0;
     bool poly2_valid = false;
     int poly2_G = 0, poly2_V = 0;
     size_t obuf_cap = 0;  // samples per stream in obuf
@@ -212,11 +217,13 @@ struct rr_chain {
     std::string plan;
     bool allow_poly = true;  // rr_chain_set_fast_path
     bool allow_poly2 = true; // RR_DISABLE_POLY2=1: keep the generic polyphase kernel (k_poly) for f32 too
+    bool allow_front = true; // RR_DISABLE_FRONT=1: k_poly2 on all P branches instead of the rank-reduced front end
     // optional CUDA-event timing of the dominant kernel of a push (bench.py's roofline)
     bool timing = false;
     std::vector<cudaEvent_t> evs;  // pairs (start, stop), one per timed launch since rr_chain_set_timing
     size_t ev_used = 0;
-    std::string timed_kernel;
+    std::vector<std::string> ev_names;  // kernel name per pair
+    std::string timed_kernel, breakdown;
     int timing_begin() {
         if (!timing) return 0;
         if (ev_used + 2 > evs.size()) {
@@ -231,7 +238,8 @@ struct rr_chain {
     void timing_end(const char* name) {
         cudaEventRecord(evs[ev_used + 1], stream);
         ev_used += 2;
-        timed_kernel = name;
+        if (ev_names.size() < ev_used / 2) ev_names.resize(ev_used / 2);
+        ev_names[ev_used / 2 - 1] = name;
     }
 };
 
@@ -705,6 +713,7 @@ template <typename T> int poly_prepare(rr_chain* c, Stage& f, Stage& ds) {
     ds.poly_tried = true;
     ds.poly_valid = false;
     ds.poly2_valid = false;
+    ds.front_valid = false;
     if (!f.taps_valid) return RR_OK;
     const long long P = ds.h.P, Q = ds.h.Q;
     const long long n = (long long)f.h.f_n, L = ds.h.r_L;
@@ -777,6 +786,31 @@ template <typename T> int poly_prepare(rr_chain* c, Stage& f, Stage& ds) {
         ds.poly2_G = G2;
         ds.poly2_V = (int)(K2 - 1 - Lmax);
         ds.poly2_valid = true;
+
+        // rank-reduced form: the P x (Lmax+1) matrix of the fused filter to below f32 rounding
+        constexpr int RK = 10;
+        if (c->allow_front && rr::front_supported(RK, P) && rr::poly2_supported(K2, RK, 1)) {
+            std::vector<double> acf;
+            std::vector<std::complex<double>> bfft;
+            int rank = 0;
+            double disc = 0.0;
+            const int lm2 = rr::design_rank_tables(f.taps, ds.ir_host_flt, P, K2, 2.0e-8, RK, &rank, &acf, &bfft, &disc);
+            if (rank > 0 && lm2 == (int)Lmax) {
+                std::vector<float> ac((size_t)P * RK);
+                for (long long p = 0; p < P; ++p)
+                    for (int cc = 0; cc < RK; ++cc) ac[(size_t)(((p / 2) * 2 + (p & 1)) * RK + cc)] = (float)acf[(size_t)p * RK + cc];
+                RR_TRY(ds.acoef.ensure(ac.size() * sizeof(float)));
+                RR_CUDA(cudaMemcpyAsync(ds.acoef.p, ac.data(), ac.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+                RR_CUDA(cudaStreamSynchronize(c->stream));
+                perm.assign((size_t)K2 * (size_t)RK, std::complex<double>(0.0, 0.0));
+                for (int cc = 0; cc < RK; ++cc)
+                    for (int k = 0; k < K2; ++k) perm[(size_t)rr::poly2_table_index(RK, 0, cc, k)] = bfft[(size_t)cc * K2 + k] * scale2;
+                RR_TRY(upload_complex<T>(ds.gtab3, perm, c->stream));
+                ds.front_rank = rank;
+                ds.front_discarded = disc;
+                ds.front_valid = true;
+            }
+        }
     }
     return RR_OK;
 }
@@ -859,7 +893,7 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
         // outputs m (1-based, counted with the reduced counters) firing inside this part
         const long long m_lo = m0 + 1;
         const long long m_hi = floordiv128(j0 + zlen, Qq, Pq);
-        bool used_poly2 = false;
+        bool used_poly2 = false, used_front = false;
         if (m_hi >= m_lo) {
             rr::PolyArgs<T> a{};
             // filter output k aligns with push sample k; the part starts at push sample ca*n, and the
@@ -884,7 +918,68 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
             bool done = false;
             if constexpr (std::is_same<T, float>::value) {
                 const bool tma_ok = ((uintptr_t)a.in % 16 == 0) && (S == 1 || a.in_stride % 2 == 0) && a.len < (1LL << 31);
-                if (ds.poly2_valid && tma_ok) {
+                if (ds.poly2_valid && ds.front_valid && tma_ok) {
+                    // u rows [m_lo-1-Lmax, m_hi-1] of every stream, then the low-rate part on u as a stream of
+                    // RK branches whose first output (virtual index Lmax+1) is output m_lo
+                    constexpr int RK = 10;
+                    const int G2 = RK;
+                    const long long n_out = m_hi - m_lo + 1;
+                    const long long n_rows = n_out + ds.poly_Lmax;
+                    const long long u_stride = (n_rows * RK + 1) / 2 * 2;
+                    if (n_rows < (1LL << 27)) {
+                        RR_TRY(ds.ubuf.ensure((size_t)S * (size_t)u_stride * 2 * sizeof(float)));
+                        rr::FrontArgs fa{};
+                        fa.in = a.in;
+                        fa.in_stride = a.in_stride;
+                        fa.len = a.len;
+                        fa.hist2 = f.hist2[f.hist_cur].p;
+                        fa.n = a.n;
+                        fa.nco = a.nco;
+                        fa.acoef = (const float*)ds.acoef.p;
+                        fa.P = (int)Pq;
+                        fa.J0 = a.J0;
+                        fa.row_first = m_lo - 1 - ds.poly_Lmax;
+                        fa.n_rows = (int)n_rows;
+                        fa.u = ds.ubuf.p;
+                        fa.u_stride = u_stride;
+                        RR_TIMED_LAUNCH(c, "k_front", 1, rr::launch_front(RK, S, fa, st));
+                        rr::PolyArgs<float> b{};
+                        b.in = ds.ubuf.p;
+                        b.in_stride = u_stride;
+                        b.len = n_rows * RK;
+                        b.hist2 = ds.ubuf.p;
+                        b.n = 0;
+                        b.nco = nullptr;
+                        b.gtab = ds.gtab3.p;
+                        b.twK = ds.poly2_tw_own ? ds.twK2.p : ds.twK.p;
+                        b.P = RK;
+                        b.Q = 1;
+                        b.Lmax = ds.poly_Lmax;
+                        b.V = ds.poly2_V;
+                        b.J0 = 0;
+                        b.m0 = ds.poly_Lmax;
+                        b.m_lo = ds.poly_Lmax + 1;
+                        b.m_hi = ds.poly_Lmax + n_out;
+                        b.I_lo = b.m_lo;
+                        b.n_blocks = (int)((b.m_hi - b.I_lo) / b.V + 1);
+                        int nbpc = std::min(G2, b.n_blocks);
+                        while (nbpc > 1 && rr::poly2_smem_bytes(G2, nbpc) > (size_t)226 * 1024) --nbpc;
+                        const long long ctas_y = (S + 1) / 2;
+                        while (nbpc > 1 && ctas_y * ((b.n_blocks + nbpc - 1) / nbpc) < 2LL * c->ctx->sm_count) --nbpc;
+                        const int ngroups = (b.n_blocks + nbpc - 1) / nbpc;
+                        nbpc = (b.n_blocks + ngroups - 1) / ngroups;
+                        int ngrp = ngroups;
+                        while (ngrp > 1 && ctas_y * ((ngroups + ngrp - 1) / ngrp) < 2LL * c->ctx->sm_count) --ngrp;
+                        b.nbpc = nbpc;
+                        b.ngrp = ngrp;
+                        b.out = obase;
+                        b.out_stride = ostride;
+                        RR_TIMED_LAUNCH(c, "k_poly2", 1, rr::launch_poly2(G2, S, b, st));
+                        done = true;
+                        used_front = true;
+                    }
+                }
+                if (!done && ds.poly2_valid && tma_ok) {
                     a.gtab = ds.gtab2.p;
                     if (ds.poly2_tw_own) a.twK = ds.twK2.p;
                     a.V = ds.poly2_V;
@@ -892,11 +987,18 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
                     const int G2 = ds.poly2_G;
                     // blocks per CTA: bounded by the columns that run the inverse transforms and by the
                     // shared memory that lets two CTAs share an SM
-                    int nbpc = G2;
+                    // blocks per group (one round of inverse transforms; bounded by shared memory), groups per
+                    // CTA half: as many as keep the grid at two CTAs per SM or more
+                    int nbpc = std::min(G2, a.n_blocks);
                     while (nbpc > 1 && rr::poly2_smem_bytes(G2, nbpc) > (size_t)226 * 1024) --nbpc;
-                    while (nbpc > 1 && (long long)((S + 1) / 2) * ((a.n_blocks + nbpc - 1) / nbpc) < 2LL * c->ctx->sm_count) --nbpc;
-                    const int nsb = (a.n_blocks + nbpc - 1) / nbpc;
-                    a.nbpc = (a.n_blocks + nsb - 1) / nsb;
+                    const long long ctas_y = (S + 1) / 2;
+                    while (nbpc > 1 && ctas_y * ((a.n_blocks + nbpc - 1) / nbpc) < 2LL * c->ctx->sm_count) --nbpc;
+                    const int ngroups = (a.n_blocks + nbpc - 1) / nbpc;
+                    nbpc = (a.n_blocks + ngroups - 1) / ngroups;  // balance
+                    int ngrp = ngroups;
+                    while (ngrp > 1 && ctas_y * ((ngroups + ngrp - 1) / ngrp) < 2LL * c->ctx->sm_count) --ngrp;
+                    a.nbpc = nbpc;
+                    a.ngrp = ngrp;
                     a.out = obase;
                     a.out_stride = ostride;
                     a.hist2 = f.hist2[f.hist_cur].p;
@@ -922,7 +1024,7 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
         }
         ds.ztail_stale = true;
         if (!plan->empty() && plan->back() != '+' && plan->back() != '|' && ca > 0) *plan += "|";
-        *plan += used_poly2 ? "poly2[filter+down]" : "poly[filter+down]";
+        *plan += used_front ? "front+poly2[filter+down]" : (used_poly2 ? "poly2[filter+down]" : "poly[filter+down]");
     }
     return RR_OK;
 }
@@ -1328,6 +1430,7 @@ int rr_chain_create(rr_ctx* ctx, const rr_chain_desc* desc, rr_chain** out) {
     }
     if (const char* e = std::getenv("RR_DISABLE_POLY")) c->allow_poly = !(e[0] == '1');
     if (const char* e = std::getenv("RR_DISABLE_POLY2")) c->allow_poly2 = !(e[0] == '1');
+    if (const char* e = std::getenv("RR_DISABLE_FRONT")) c->allow_front = !(e[0] == '1');
     RR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     *out = c.release();
     return RR_OK;
@@ -1514,18 +1617,41 @@ int rr_chain_set_timing(rr_chain* c, int enable) {
 int rr_chain_kernel_time(rr_chain* c, double* total_ms, int* n_launches, const char** kernel_name) {
     if (!c || !total_ms) return fail(RR_ERR_INVALID, "null argument");
     RR_CUDA(cudaSetDevice(c->ctx->device));
-    double sum = 0.0;
+    // per kernel name: total and count; the dominant kernel (largest total) is reported here, the whole
+    // list by rr_chain_kernel_breakdown
+    std::vector<std::string> names;
+    std::vector<double> tot;
+    std::vector<int> cnt;
     for (size_t i = 0; i + 1 < c->ev_used; i += 2) {
         float ms = 0.f;
         RR_CUDA(cudaEventSynchronize(c->evs[i + 1]));
         RR_CUDA(cudaEventElapsedTime(&ms, c->evs[i], c->evs[i + 1]));
-        sum += ms;
+        const std::string& nm = c->ev_names[i / 2];
+        size_t k = 0;
+        while (k < names.size() && names[k] != nm) ++k;
+        if (k == names.size()) {
+            names.push_back(nm);
+            tot.push_back(0.0);
+            cnt.push_back(0);
+        }
+        tot[k] += ms;
+        cnt[k] += 1;
     }
-    *total_ms = sum;
-    if (n_launches) *n_launches = (int)(c->ev_used / 2);
+    size_t best = 0;
+    c->breakdown.clear();
+    for (size_t k = 0; k < names.size(); ++k) {
+        if (tot[k] > tot[best]) best = k;
+        char buf[160];
+        std::snprintf(buf, sizeof buf, "%s%s:%.6f:%d", k ? ";" : "", names[k].c_str(), tot[k], cnt[k]);
+        c->breakdown += buf;
+    }
+    *total_ms = names.empty() ? 0.0 : tot[best];
+    if (n_launches) *n_launches = names.empty() ? 0 : cnt[best];
+    c->timed_kernel = names.empty() ? "" : names[best];
     if (kernel_name) *kernel_name = c->timed_kernel.c_str();
     return RR_OK;
 }
+const char* rr_chain_kernel_breakdown(rr_chain* c) { return c ? c->breakdown.c_str() : ""; }
 void* rr_chain_cuda_stream(rr_chain* c) { return c ? (void*)c->stream : nullptr; }
 const char* rr_chain_plan(rr_chain* c) { return c ? c->plan.c_str() : ""; }
 

@@ -41,6 +41,19 @@ bool design_filter_response(const FreqResp& f, const WindowFn& w, double sample_
 int design_poly_tables(const std::vector<std::complex<double>>& h, const std::vector<double>& ir, long long P, long long Q, int K,
                        std::vector<std::complex<double>>* out);
 
+// Rank factorisation of the same fused filter for integer decimation (Q == 1):
+//   y_m = sum_l sum_p M[p][l] * x'[(m-1-l)*P + p],   M[p][l] = g[P-1-p + l*P],  l = 0 .. Lmax.
+// g is a narrow low-pass, heavily oversampled at the input rate, so the P x (Lmax+1) matrix M is
+// numerically of low rank: M = sum_c a_c b_c^T with real orthonormal a_c (one-sided Jacobi SVD of
+// [Re M | Im M]).  The front end u_c[i] = sum_p a_c[p] * x'[i*P + p] then needs `rank` real
+// multiply-adds per input sample and the low-rate part y = sum_c (b_c * u_c) runs on rank (not P)
+// branches.  `rank` = the smallest count whose discarded part is below `tol` relative to |M|_F
+// (2e-8 for f32: under the rounding of any f32 evaluation of the same sums), 0 if that needs more
+// than max_rank.  `a`: [P][rank_pad] real (zero padded to rank_pad columns), `bfft`: [rank_pad][K]
+// = FFT_K of b_c (natural bin order).  Returns Lmax.
+int design_rank_tables(const std::vector<std::complex<double>>& h, const std::vector<double>& ir, long long P, int K, double tol,
+                       int max_rank, int* rank, std::vector<double>* a, std::vector<std::complex<double>>* b, double* discarded);
+
 // unit-energy windowed-sinc taps, f64 (cast by the caller)
 void design_resampler_taps(size_t ir_len, double ratio, double null_bin, std::vector<double>* out);
 

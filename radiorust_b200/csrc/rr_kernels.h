@@ -129,7 +129,8 @@ template <typename T> struct PolyArgs {
     const void* twK;       // [K] exp(-j*2*pi*e/K)
     long long P, Q;        // in/out = P/Q reduced
     int Lmax, V;           // low-rate filter reach, valid outputs per block and phase
-    int n_blocks, nbpc;    // blocks per stream, blocks per CTA
+    int n_blocks, nbpc;    // blocks per stream, blocks per CTA (k_poly2: per group)
+    int ngrp;              // k_poly2: groups of nbpc blocks that one CTA half works through
     long long J0, m0;      // filter-output samples consumed / outputs emitted before this push (reduced)
     long long m_lo, m_hi;  // outputs m to produce (inclusive)
     long long I_lo;        // low-rate index of block 0's first valid output
@@ -149,6 +150,27 @@ size_t poly2_smem_bytes(int G, int nbpc);
 // position (complex elements) of bin k of branch p = r*G + g in the device table
 long long poly2_table_index(int G, int r, int g, int k);
 cudaError_t launch_poly2(int G, int n_streams, const PolyArgs<float>& a, cudaStream_t st);
+
+// ---- k_front (rr_front.cu): rank-reduced front end u_c[i] = sum_p a_c[p] * x'[i*P + p] (f32, Q == 1).
+// k_poly2 then runs on u as a stream of `rank_pad` branches.
+struct FrontArgs {
+    const void* in;        // [S][in_stride] complex<float>: the pushed samples (pre-NCO)
+    long long in_stride;
+    long long len;         // pushed samples per stream
+    const void* hist2;     // [S][2n]: the 2n post-NCO samples preceding `in`
+    long long n;
+    const NcoStream* nco;  // [S] or nullptr
+    const float* acoef;    // [P/2][2][rank_pad]: a_c[p] at ((p/2)*2 + (p&1))*rank_pad + c
+    int P;
+    long long J0;          // as PolyArgs::J0: row r, branch p is push sample r*P + p - J0
+    long long row_first;   // row index of u row 0
+    int n_rows;            // rows to produce per stream
+    void* u;               // [S][u_stride] complex<float>, row-major [row][rank_pad]
+    long long u_stride;    // complex elements, even
+    int tiles_per_warp;    // set by the launcher
+};
+bool front_supported(int rank_pad, long long P);
+cudaError_t launch_front(int rank_pad, int n_streams, const FrontArgs& a, cudaStream_t st);
 
 // new hist2 = last 2n post-NCO samples of [hist2_in | in]
 template <typename T>

@@ -28,6 +28,10 @@
 // block are summed through shared memory once per block, parked, and inverted
 // at the end by the same two-pass code (conjugate trick).
 //
+// A warp owns two branch columns end to end (both passes of both transforms),
+// so a round needs no CTA-wide barrier: warps drift apart and one warp's
+// shared-memory phases overlap another's arithmetic.  The warp that is last to
+// hand a tile stage back starts the TMA copy of the round after next into it.
 // One CTA = two independent halves (own stream, shared memory, mbarriers and
 // named barrier): the register file is per SM sub-partition, so 10 warps of 168
 // registers fit where two 5-warp CTAs would be rounded up.
@@ -56,25 +60,29 @@ constexpr int NT2 = 16;   // threads per transform
 constexpr int ROWS_BOX = 256;
 
 template <int G> struct P2Cfg {
-    static constexpr int THREADS = NT2 * G;  // per half
-    // exchange: element (t, k1) of column g at t*TS + k1*G + g (8-byte elements); TS = 32G + (G mod 16)
-    // makes the pass-1 stores (lanes (g, t), fixed k1) and the pass-2 loads (lanes (g, tt), fixed t)
-    // land on `tid + const`: consecutive lanes, consecutive words
-    static constexpr int TS = 32 * G + (G % 16);
-    static constexpr int TILE_BYTES = K2 * G * 8;
-    static constexpr int XCH_BYTES = 16 * TS * 8;
-    static constexpr int STAGE_BYTES = (((TILE_BYTES > XCH_BYTES ? TILE_BYTES : XCH_BYTES) + 127) / 128) * 128;
+    static_assert(G % 4 == 2, "a warp's two columns are conflict-free only when the tile pitch is an odd number of 16-byte units");
+    static constexpr int NCW = G / 2;                // warps per half (two branch columns each)
+    static constexpr int THREADS = 32 * NCW;         // threads per half
+    static constexpr int PITCH = G * 8;              // bytes per tile row
+    // A warp owns the 16-byte strip of its two columns in every row.  The exchange lives in the same
+    // strip: element (t, k1) at row 33*t + k1 (rows 512..527 are spare), so that the pass-1 stores (lanes
+    // t, fixed k1) and the pass-2 loads (lanes k1, fixed t) both walk 8 consecutive rows per quarter warp:
+    // with an odd pitch/16 that is 8 distinct 16-byte bank groups, and every offset is an immediate.
+    static constexpr int ROWS = 528;
+    static constexpr int TILE_BYTES = K2 * PITCH;
+    static constexpr int STAGE_BYTES = ROWS * PITCH;
+    static_assert(STAGE_BYTES % 128 == 0, "TMA destination alignment");
     static constexpr int TW_UNITS = 17;              // 16-byte units per twiddle row t (16 + 1 pad)
     static constexpr int TW_BYTES = 16 * TW_UNITS * 16;
-    static constexpr int E_BYTES = 48 * 8;           // E[32] | rowph[16]
+    static constexpr int E_BYTES = 400;              // E[32] | rowph[16] | rotG (+ pad to 16 bytes)
     static constexpr int ECP_BYTES = 16 * G * 16;    // one buffer of E[i1]*c_p: unit (m, g) = entries i1 = 2m, 2m+1 of column g
     static constexpr int YS_STRIDE = K2 + 1;         // parked spectrum stride (elements)
     static constexpr int OFF_STAGE = 0;
     static constexpr int OFF_TW = 2 * STAGE_BYTES;
     static constexpr int OFF_E = OFF_TW + TW_BYTES;
     static constexpr int OFF_ECP = OFF_E + E_BYTES;
-    static constexpr int OFF_BAR = OFF_ECP + 2 * ECP_BYTES;
-    static constexpr int OFF_YS = OFF_BAR + 16;
+    static constexpr int OFF_BAR = OFF_ECP + 2 * ECP_BYTES;  // full[2] (mbarriers), released[2] (counters)
+    static constexpr int OFF_YS = OFF_BAR + 32;
     __host__ __device__ static size_t half_bytes(int nbpc) { return (((size_t)OFF_YS + (size_t)nbpc * YS_STRIDE * 8) + 127) / 128 * 128; }
     static size_t smem_bytes(int nbpc) { return 2 * half_bytes(nbpc); }
 };
@@ -105,6 +113,11 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm,
         "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+__device__ __forceinline__ uint32_t atom_add_acqrel_shared(uint32_t addr, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+    return old;
+}
 
 __device__ __forceinline__ pc lds_pc(uint32_t addr) {
     pc r;
@@ -120,35 +133,41 @@ __device__ __forceinline__ void sts_pc(uint32_t addr, pc a) {
 __device__ __forceinline__ void sts_pc2(uint32_t addr, pc a, pc b) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y) : "memory");
 }
-// read-only table load that stays where it is written (volatile asm is not moved across the barriers,
-// so the load is in flight while the half waits)
+// read-only table load that stays where it is written (volatile asm keeps its place, so the load is
+// in flight while the warp works on something else)
 __device__ __forceinline__ void ldg_pc2(const float4* p, pc& a, pc& b) {
     asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(b.x), "=f"(b.y) : "l"(p));
 }
 
 // pass 1 of the K-point forward transform of this thread's 32 inputs (rows t + 16*i1): radix-32
-// butterfly, twiddles from table row `tw_row`, result into the exchange area
-template <int G>
+// butterfly, twiddles from table row `tw_row` (loaded two steps ahead of their use), element (t, k1)
+// to row 33*t + k1 of the warp's strip
+template <int PITCH>
 __device__ __forceinline__ void pass1_store(pc (&v)[32], uint32_t tw_row, uint32_t xch_wr) {
     pdft_regs<32, +1>(v);
+    pc w[3][2];
+    lds_pc2(tw_row, w[0][0], w[0][1]);
+    lds_pc2(tw_row + 16, w[1][0], w[1][1]);
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
-        pc w0, w1;
-        lds_pc2(tw_row + m * 16, w0, w1);
-        sts_pc(xch_wr + (2 * m) * (G * 8), pcmul(v[2 * m], w0));
-        sts_pc(xch_wr + (2 * m + 1) * (G * 8), pcmul(v[2 * m + 1], w1));
+        if (m + 2 < 16) lds_pc2(tw_row + (m + 2) * 16, w[(m + 2) % 3][0], w[(m + 2) % 3][1]);
+        sts_pc(xch_wr + (2 * m) * PITCH, pcmul(v[2 * m], w[m % 3][0]));
+        sts_pc(xch_wr + (2 * m + 1) * PITCH, pcmul(v[2 * m + 1], w[m % 3][1]));
     }
 }
 
 }  // namespace
 
+// One CTA = two independent halves (own stream, shared memory, mbarriers, named barrier).
 template <int G, bool HAS_NCO>
-__global__ void __launch_bounds__(2 * NT2 * G, 1) k_poly2(const __grid_constant__ CUtensorMap tmap, const PolyArgs<float> a, const int n_streams) {
+__global__ void __launch_bounds__(2 * P2Cfg<G>::THREADS, 1) k_poly2(const __grid_constant__ CUtensorMap tmap, const PolyArgs<float> a, const int n_streams) {
     using C = P2Cfg<G>;
-    constexpr int THREADS = C::THREADS;
+    constexpr int THREADS = C::THREADS, PITCH = C::PITCH;
     const int half = threadIdx.x >= THREADS ? 1 : 0;
     const int tid = threadIdx.x - half * THREADS;
-    const int g = tid % G, t = tid / G;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int t = lane >> 1, gg = lane & 1;
+    const int g = 2 * warp + gg;  // branch column of this lane
     const int s = blockIdx.y * 2 + half;
     if (s >= n_streams) return;  // the halves never meet at a CTA-wide barrier
     auto sync_half = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(half + 1), "n"(THREADS) : "memory"); };
@@ -156,71 +175,11 @@ __global__ void __launch_bounds__(2 * NT2 * G, 1) k_poly2(const __grid_constant_
     extern __shared__ __align__(128) unsigned char smem_all[];
     unsigned char* smem = smem_all + (size_t)half * C::half_bytes(a.nbpc);
     const uint32_t sbase = smem_u32(smem);
-    const uint32_t bar0 = sbase + C::OFF_BAR;
-    const uint32_t e_tab = sbase + C::OFF_E;
-    const uint32_t ecp = sbase + C::OFF_ECP;
-    const uint32_t tw_row = sbase + C::OFF_TW + t * (C::TW_UNITS * 16);
-    // exchange addresses inside a stage: store element (t, k1 = 0), load element (t' = 0, k1 = t)
-    const uint32_t xch_wr = (C::TS * t + g) * 8;
-    const uint32_t xch_rd = tid * 8;
-    float2* ysave = reinterpret_cast<float2*>(smem + C::OFF_YS);
+    const uint32_t bar_full = sbase + C::OFF_BAR, cnt_rel = bar_full + 16;
 
-    const float2* __restrict__ in = reinterpret_cast<const float2*>(a.in) + (long long)s * a.in_stride;
-    const float2* __restrict__ hist_end = reinterpret_cast<const float2*>(a.hist2) + ((long long)s + 1) * 2 * a.n;
-    const float4* __restrict__ gtab = reinterpret_cast<const float4*>(a.gtab);
-    float2* __restrict__ out = reinterpret_cast<float2*>(a.out) + (long long)s * a.out_stride;
     const int Pd = (int)a.P;
     const int NR = (Pd + G - 1) / G;
-    const long long len = a.len, hist_len = 2 * a.n;
-
-    // ---- NCO constants, tables -------------------------------------------------------------
-    uint32_t denom = 1, numer_abs = 0, idx0 = 0;
-    int sign = 0;
-    float start = 0.f;
-    pc rotG(1.f, 0.f);
-    if (HAS_NCO) {
-        const NcoStream ns = a.nco[s];
-        denom = ns.denom;
-        numer_abs = ns.numer_abs;
-        sign = ns.sign;
-        idx0 = ns.idx;
-        start = (float)ns.start_phase;
-        const cx<float> r = nco_rotation<float>(G, numer_abs, denom, sign);
-        rotG = pc(r.x, r.y);
-    }
-    {
-        float2* et = reinterpret_cast<float2*>(smem + C::OFF_E);
-        if (tid < 48) {
-            cx<float> r(1.f, 0.f);
-            if (HAS_NCO) r = nco_rotation<float>(tid < 32 ? (long long)16 * Pd * tid : (long long)Pd * (tid - 32), numer_abs, denom, sign);
-            et[tid] = make_float2(r.x, r.y);
-        }
-        if (tid == 0) {
-            mbar_init(bar0, 1);
-            mbar_init(bar0 + 8, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        sync_half();
-        // pass-1 twiddles W_K^(t*k1), times the NCO's row part exp(j*w*P*t)
-        const float2* __restrict__ twK = reinterpret_cast<const float2*>(a.twK);
-        for (int e = tid; e < K2; e += THREADS) {
-            const int tr = e >> 5, k1 = e & 31;
-            const float2 w = twK[(tr * k1) & (K2 - 1)];
-            const float2 rp = et[32 + tr];
-            const int off = (tr * C::TW_UNITS + (k1 >> 1)) * 16 + (k1 & 1) * 8;
-            *reinterpret_cast<float2*>(smem + C::OFF_TW + off) = make_float2(w.x * rp.x - w.y * rp.y, w.x * rp.y + w.y * rp.x);
-        }
-        sync_half();
-    }
-    const pc rowph = lds_pc(e_tab + (32 + t) * 8);
-    // this thread's two entries of the E table (it maintains entries 2t, 2t+1 of its column's E*c_p)
-    pc e_mine0(1.f, 0.f), e_mine1(1.f, 0.f);
-    if (HAS_NCO) lds_pc2(e_tab + (2 * t) * 8, e_mine0, e_mine1);
-    const uint32_t ecp_wr = ecp + (t * G + g) * 16;
-    const uint32_t ecp_rd = ecp + g * 16;
-
-    const int blk0 = blockIdx.x * a.nbpc;
-    const int blk1 = min(blk0 + a.nbpc, a.n_blocks);
+    const int len = (int)a.len, hist_len = (int)(2 * a.n);
 
     // window of block blk: element (i, p) sits at push offset boff + i*P + p.  "Interior" blocks lie
     // completely inside the pushed samples and are fed by TMA.  A block whose window would run past
@@ -241,191 +200,279 @@ __global__ void __launch_bounds__(2 * NT2 * G, 1) k_poly2(const __grid_constant_
         return Ibase * Pd - a.J0 - Pd;
     };
     auto is_interior = [&](long long boff) -> bool { return boff >= 0 && boff + need <= len; };
-    auto issue_tile = [&](int stage, long long boff, int r) {
-        const uint32_t bar = bar0 + stage * 8;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    // the tile of round Rg of the group that starts at block blk_first (nothing for edge blocks)
+    auto issue_tile = [&](int blk_first, int blk_end, int Rg) {
+        const int blk = blk_first + Rg / NR;
+        if (blk >= blk_end) return;
+        const long long boff = block_off(blk);
+        if (!is_interior(boff)) return;
+        const int stage = Rg & 1;
+        const uint32_t bar = bar_full + stage * 8;
         mbar_expect_tx(bar, C::TILE_BYTES);
-        tma_load_4d(sbase + C::OFF_STAGE + stage * C::STAGE_BYTES, &tmap, bar, (int)(boff + (long long)r * G), 0, 0, s);
+        tma_load_4d(sbase + C::OFF_STAGE + stage * C::STAGE_BYTES, &tmap, bar, (int)(boff + (long long)(Rg % NR) * G), 0, 0, s);
     };
 
-    int R = 0;           // rounds executed by this half
-    uint32_t phase = 0;  // bit `stage`: parity to wait for next
-    if (blk0 < blk1 && tid == 0) {
-        const long long b0 = block_off(blk0);
-        if (is_interior(b0)) issue_tile(0, b0, 0);
+    const uint32_t e_tab = sbase + C::OFF_E;
+    const uint32_t ecp = sbase + C::OFF_ECP;
+    const uint32_t tw_row = sbase + C::OFF_TW + t * (C::TW_UNITS * 16);
+    // strip offsets inside a stage: tile row t, exchange row 33*t (stores), exchange row t (loads)
+    const uint32_t tile_rd = t * PITCH + g * 8;
+    const uint32_t xch_wr = 33 * t * PITCH + g * 8;
+    const uint32_t xch_rd = t * PITCH + g * 8;
+    float2* ysave = reinterpret_cast<float2*>(smem + C::OFF_YS);
+
+    const float2* __restrict__ in = reinterpret_cast<const float2*>(a.in) + (long long)s * a.in_stride;
+    const float2* __restrict__ hist_end = reinterpret_cast<const float2*>(a.hist2) + ((long long)s + 1) * 2 * a.n;
+    const float4* __restrict__ gtab = reinterpret_cast<const float4*>(a.gtab);
+    float2* __restrict__ out = reinterpret_cast<float2*>(a.out) + (long long)s * a.out_stride;
+
+    // ---- NCO constants, tables -------------------------------------------------------------
+    uint32_t denom = 1, numer_abs = 0, idx0 = 0;
+    int sign = 0;
+    float start = 0.f;
+    pc rotG(1.f, 0.f);
+    if (HAS_NCO) {
+        const NcoStream ns = a.nco[s];
+        denom = ns.denom;
+        numer_abs = ns.numer_abs;
+        sign = ns.sign;
+        idx0 = ns.idx;
+        start = (float)ns.start_phase;
     }
-
-    for (int blk = blk0; blk < blk1; ++blk) {
-        const long long boff = block_off(blk);
-        const bool interior = is_interior(boff);
-        const bool have_next = blk + 1 < blk1;
-        const long long boff_next = have_next ? block_off(blk + 1) : 0;
-        const bool next_interior = have_next && is_interior(boff_next);
-
-        pc cp(1.f, 0.f);  // NCO phasor of sample (i = 0, p = r*G + g) of this block, r = next round to prepare
-        if (HAS_NCO) {
-            long long k0 = ((long long)idx0 + boff + g) % (long long)denom;
-            if (k0 < 0) k0 += denom;
-            const cx<float> c = nco_phasor<float>(mulmod_u32(numer_abs, (uint32_t)k0, denom), denom, sign, start);
-            cp = pc(c.x, c.y);
-            // E*c_p of round 0 (read after barrier A of that round)
-            sts_pc2(ecp_wr + (R & 1) * C::ECP_BYTES, pcmul(e_mine0, cp), pcmul(e_mine1, cp));
+    {
+        float2* et = reinterpret_cast<float2*>(smem + C::OFF_E);  // E[32] | rowph[16] | rotG
+        if (tid < 49) {
+            cx<float> r(1.f, 0.f);
+            const long long d = tid < 32 ? (long long)16 * Pd * tid : (tid < 48 ? (long long)Pd * (tid - 32) : (long long)G);
+            if (HAS_NCO) r = nco_rotation<float>(d, numer_abs, denom, sign);
+            et[tid] = make_float2(r.x, r.y);
         }
-        pc acc[32];
+        if (tid == 64) {
+            mbar_init(bar_full, 1);
+            mbar_init(bar_full + 8, 1);
+            *reinterpret_cast<uint2*>(smem + C::OFF_BAR + 16) = make_uint2(0u, 0u);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        // pass-1 twiddles W_K^(t*k1) (the NCO's row part exp(j*w*P*t) is multiplied in below)
+        const float2* __restrict__ twK = reinterpret_cast<const float2*>(a.twK);
+        float2 w[(K2 + THREADS - 1) / THREADS];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = pc(0.f, 0.f);
+        for (int i = 0; i < (K2 + THREADS - 1) / THREADS; ++i) {
+            const int e = tid + i * THREADS;
+            if (e < K2) w[i] = twK[((e >> 5) * (e & 31)) & (K2 - 1)];
+        }
+        sync_half();
+#pragma unroll
+        for (int i = 0; i < (K2 + THREADS - 1) / THREADS; ++i) {
+            const int e = tid + i * THREADS;
+            if (e < K2) {
+                const int tr = e >> 5, k1 = e & 31;
+                const float2 rp = et[32 + tr];
+                const int off = (tr * C::TW_UNITS + (k1 >> 1)) * 16 + (k1 & 1) * 8;
+                *reinterpret_cast<float2*>(smem + C::OFF_TW + off) = make_float2(w[i].x * rp.x - w[i].y * rp.y, w[i].x * rp.y + w[i].y * rp.x);
+            }
+        }
+        sync_half();
+        rotG = lds_pc(e_tab + 48 * 8);
+    }
+    const pc rowph = lds_pc(e_tab + (32 + t) * 8);
+    // this lane's two entries of the E table (it maintains entries 2t, 2t+1 of its column's E*c_p)
+    pc e_mine0(1.f, 0.f), e_mine1(1.f, 0.f);
+    if (HAS_NCO) lds_pc2(e_tab + (2 * t) * 8, e_mine0, e_mine1);
+    const uint32_t ecp_wr = ecp + (t * G + g) * 16;
+    const uint32_t ecp_rd = ecp + g * 16;
 
-        for (int r = 0; r < NR; ++r, ++R) {
-            const int stage = R & 1;
-            const uint32_t stg = sbase + C::OFF_STAGE + stage * C::STAGE_BYTES;
-            pc v[32];
-            long long pos0 = 0;
-            if (interior) {
-                mbar_wait(bar0 + stage * 8, (phase >> stage) & 1);
-                phase ^= 1u << stage;
-                const uint32_t src = stg + tid * 8;
-#pragma unroll
-                for (int i1 = 0; i1 < 32; ++i1) v[i1] = lds_pc(src + i1 * (THREADS * 8));
-            } else {
-                // all loads first (independent, predicated); history samples are already mixed
-                const int p = r * G + g;
-                pos0 = boff + (long long)t * Pd + p;
-                const long long step = (long long)16 * Pd;
-#pragma unroll
-                for (int i1 = 0; i1 < 32; ++i1) {
-                    const long long pos = pos0 + i1 * step;
-                    const bool ok = p < Pd && pos < len && pos >= -hist_len;
-                    const float2* ptr = pos >= 0 ? in + pos : hist_end + pos;
-                    float2 q = make_float2(0.f, 0.f);
-                    if (ok) q = __ldg(ptr);
-                    v[i1] = pc(q.x, q.y);
-                }
-            }
-            sync_half();  // A: the tile is consumed, the other stage's exchange reads are over
-            if (tid == 0) {
-                if (r + 1 < NR) {
-                    if (interior) issue_tile(stage ^ 1, boff, r + 1);
-                } else if (next_interior) {
-                    issue_tile(stage ^ 1, boff_next, 0);
-                }
-            }
+    uint32_t phase = 0;  // bit `stage`: parity of the next TMA completion to wait for
+
+    // hand stage (R & 1) back after round R of the group: the warp that completes the count starts the
+    // TMA copy of round R + 2 into it
+    auto release_stage = [&](int gb0, int gb1, int R) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            const uint32_t old = atom_add_acqrel_shared(cnt_rel + (R & 1) * 4, 1u);
+            if (old % C::NCW == C::NCW - 1) issue_tile(gb0, gb1, R + 2);
+        }
+    };
+
+    for (int grp = 0; grp < a.ngrp; ++grp) {
+        const int blk0 = (blockIdx.x * a.ngrp + grp) * a.nbpc;
+        const int blk1 = min(blk0 + a.nbpc, a.n_blocks);
+        if (blk0 >= blk1) break;
+        if (tid == 0) {
+            issue_tile(blk0, blk1, 0);
+            issue_tile(blk0, blk1, 1);
+        }
+        int R = 0;  // rounds of this group
+
+        for (int blk = blk0; blk < blk1; ++blk) {
+            const long long boff = block_off(blk);
+            const bool interior = is_interior(boff);
+
+            pc cp(1.f, 0.f);  // NCO phasor of sample (i = 0, p = r*G + g) of this block, r = next round to prepare
             if (HAS_NCO) {
+                if (lane < 2) {  // one evaluation per column
+                    long long k0 = ((long long)idx0 + boff + g) % (long long)denom;
+                    if (k0 < 0) k0 += denom;
+                    const cx<float> c = nco_phasor<float>(mulmod_u32(numer_abs, (uint32_t)k0, denom), denom, sign, start);
+                    cp = pc(c.x, c.y);
+                }
+                cp.x = __shfl_sync(0xffffffffu, cp.x, gg);
+                cp.y = __shfl_sync(0xffffffffu, cp.y, gg);
+                // E*c_p of round 0 (the buffer's last readers were this warp's own lanes, two rounds ago)
+                sts_pc2(ecp_wr + (R & 1) * C::ECP_BYTES, pcmul(e_mine0, cp), pcmul(e_mine1, cp));
+                __syncwarp();
+            }
+            pc acc[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = pc(0.f, 0.f);
+
+            for (int r = 0; r < NR; ++r, ++R) {
+                const int stage = R & 1;
+                const uint32_t stg = sbase + C::OFF_STAGE + stage * C::STAGE_BYTES;
                 const uint32_t esrc = ecp_rd + stage * C::ECP_BYTES;
+                pc v[32];
                 if (interior) {
+                    mbar_wait(bar_full + stage * 8, (phase >> stage) & 1);
+                    phase ^= 1u << stage;
+                    const uint32_t src = stg + tile_rd;
 #pragma unroll
                     for (int m = 0; m < 16; ++m) {
                         pc e0, e1;
-                        lds_pc2(esrc + m * (G * 16), e0, e1);
-                        v[2 * m] = pcmul(v[2 * m], e0);
-                        v[2 * m + 1] = pcmul(v[2 * m + 1], e1);
+                        if (HAS_NCO) lds_pc2(esrc + m * (G * 16), e0, e1);
+                        v[2 * m] = lds_pc(src + (2 * m) * (16 * PITCH));
+                        v[2 * m + 1] = lds_pc(src + (2 * m + 1) * (16 * PITCH));
+                        if (HAS_NCO) {
+                            v[2 * m] = pcmul(v[2 * m], e0);
+                            v[2 * m + 1] = pcmul(v[2 * m + 1], e1);
+                        }
                     }
                 } else {
-                    // history: cancel the row part that the twiddles will apply (no c_p, no E for them)
-                    const pc hc(rowph.x, -rowph.y);
-                    const long long step = (long long)16 * Pd;
+                    // thread-local loads (all issued first, predicated); history samples are already mixed:
+                    // for them only the row part that the twiddles will apply is cancelled
+                    const int p = r * G + g;
+                    const int pos0 = (int)boff + t * Pd + p;
+                    const int step = 16 * Pd;
+                    const unsigned span = (unsigned)(len + hist_len);
 #pragma unroll
-                    for (int m = 0; m < 16; ++m) {
-                        pc e0, e1;
-                        lds_pc2(esrc + m * (G * 16), e0, e1);
-                        v[2 * m] = pcmul(v[2 * m], (pos0 + (2 * m) * step) >= 0 ? e0 : hc);
-                        v[2 * m + 1] = pcmul(v[2 * m + 1], (pos0 + (2 * m + 1) * step) >= 0 ? e1 : hc);
+                    for (int i1 = 0; i1 < 32; ++i1) {
+                        const int pos = pos0 + i1 * step;
+                        const bool ok = p < Pd && (unsigned)(pos + hist_len) < span;
+                        const float2* ptr = (pos >= 0 ? in : hist_end) + pos;
+                        float2 q = make_float2(0.f, 0.f);
+                        if (ok) q = __ldg(ptr);
+                        v[i1] = pc(q.x, q.y);
+                    }
+                    if (HAS_NCO) {
+                        const pc hc(rowph.x, -rowph.y);
+#pragma unroll
+                        for (int m = 0; m < 16; ++m) {
+                            pc e0, e1;
+                            lds_pc2(esrc + m * (G * 16), e0, e1);
+                            v[2 * m] = pcmul(v[2 * m], (pos0 + (2 * m) * step) >= 0 ? e0 : hc);
+                            v[2 * m + 1] = pcmul(v[2 * m + 1], (pos0 + (2 * m + 1) * step) >= 0 ? e1 : hc);
+                        }
                     }
                 }
-                // next round's E*c_p (other buffer; its readers are past barrier A of that round)
-                cp = pcmul(cp, rotG);
-                if (r + 1 < NR) sts_pc2(ecp_wr + (stage ^ 1) * C::ECP_BYTES, pcmul(e_mine0, cp), pcmul(e_mine1, cp));
-            }
-            pass1_store<G>(v, tw_row, stg + xch_wr);
+                if (HAS_NCO) {
+                    // next round's E*c_p (other buffer: its readers were this warp's lanes, a round ago)
+                    cp = pcmul(cp, rotG);
+                    if (r + 1 < NR) sts_pc2(ecp_wr + (stage ^ 1) * C::ECP_BYTES, pcmul(e_mine0, cp), pcmul(e_mine1, cp));
+                }
+                __syncwarp();  // the strip's tile rows are consumed by every lane before any lane overwrites them
+                pass1_store<PITCH>(v, tw_row, stg + xch_wr);
 
-            // table entries of this round: [r][which][jj][tid] (two bins each)
-            const float4* gp = gtab + ((long long)r * 16) * THREADS + tid;
-            pc h[16];
+                // table entries of this round: [r][which][jj][tid] (two bins each)
+                const float4* gp = gtab + ((long long)r * 16) * THREADS + tid;
+                pc h[16];
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) ldg_pc2(gp + jj * THREADS, h[2 * jj], h[2 * jj + 1]);
-            sync_half();  // B
+                for (int jj = 0; jj < 8; ++jj) ldg_pc2(gp + jj * THREADS, h[2 * jj], h[2 * jj + 1]);
+                __syncwarp();
+#pragma unroll
+                for (int which = 0; which < 2; ++which) {
+                    pc x[16];
+#pragma unroll
+                    for (int tr = 0; tr < 16; ++tr) x[tr] = lds_pc(stg + xch_rd + (33 * tr + 16 * which) * PITCH);
+                    pdft_regs<16, +1>(x);
+                    if (which == 1 && r + 1 < NR) release_stage(blk0, blk1, R);  // the exchange is read: stage free
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) acc[which * 16 + k] = pcfma(x[k], h[k], acc[which * 16 + k]);
+                    if (which == 0) {
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) ldg_pc2(gp + (8 + jj) * THREADS, h[2 * jj], h[2 * jj + 1]);
+                    }
+                }
+            }
+
+            // ---- sum the G partial spectra of this block, park the result; the block's last stage is
+            //      the scratch area and is released afterwards ------------------------------------------
+            {
+                const uint32_t stg = sbase + C::OFF_STAGE + ((R - 1) & 1) * C::STAGE_BYTES;
+                sync_half();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sts_pc(stg + (j * THREADS + tid) * 8, acc[j]);
+                sync_half();
+                float2* ys = ysave + (blk - blk0) * C::YS_STRIDE;
+                for (int o = tid; o < K2; o += THREADS) {
+                    const int j = o >> 4, tt = o & 15;
+                    const uint32_t src = stg + (j * THREADS + 2 * tt) * 8;
+                    pc sum(0.f, 0.f);
+#pragma unroll
+                    for (int w = 0; w < C::NCW; ++w) {
+                        pc u0, u1;
+                        lds_pc2(src + w * 256, u0, u1);
+                        sum = sum + u0;
+                        sum = sum + u1;
+                    }
+                    const int bin = tt + 16 * (j >> 4) + 32 * (j & 15);
+                    ys[bin] = make_float2(sum.x, sum.y);
+                }
+                release_stage(blk0, blk1, R - 1);
+            }
+        }
+        sync_half();
+
+        // ---- inverse transforms: branch column g takes job g (one parked block spectrum) -------------
+        const int njobs = blk1 - blk0;
+        for (int j0 = 0; j0 < njobs; j0 += G) {
+            const int job = j0 + g;
+            const bool active = job < njobs;
+            const uint32_t stg = sbase + C::OFF_STAGE;
+            pc v[32];
+            const float2* ys = ysave + (active ? job : 0) * C::YS_STRIDE;
+            // conj in, conj out = inverse transform; the table's NCO row part is cancelled on the way in
+            const pc hc(rowph.x, -rowph.y);
+#pragma unroll
+            for (int i1 = 0; i1 < 32; ++i1) {
+                const float2 q = ys[t + 16 * i1];
+                v[i1] = active ? pcmul(pc(q.x, -q.y), hc) : pc(0.f, 0.f);
+            }
+            pass1_store<PITCH>(v, tw_row, stg + xch_wr);
+            __syncwarp();
+            const int blk = blk0 + (active ? job : 0);
+            const int d = block_shift(blk);
+            const long long Ibase = a.I_lo + (long long)blk * a.V - a.Lmax - d;
 #pragma unroll
             for (int which = 0; which < 2; ++which) {
                 pc x[16];
 #pragma unroll
-                for (int tr = 0; tr < 16; ++tr) x[tr] = lds_pc(stg + xch_rd + (tr * C::TS + which * 16 * G) * 8);
+                for (int tr = 0; tr < 16; ++tr) x[tr] = lds_pc(stg + xch_rd + (33 * tr + 16 * which) * PITCH);
                 pdft_regs<16, +1>(x);
+                if (active) {
 #pragma unroll
-                for (int k = 0; k < 16; ++k) acc[which * 16 + k] = pcfma(x[k], h[k], acc[which * 16 + k]);
-                if (which == 0) {
-#pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) ldg_pc2(gp + (8 + jj) * THREADS, h[2 * jj], h[2 * jj + 1]);
-                }
-            }
-        }
-
-        // ---- sum the G partial spectra of this block, park the result --------------------------
-        {
-            const uint32_t stg = sbase + C::OFF_STAGE + ((R - 1) & 1) * C::STAGE_BYTES;
-            sync_half();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) sts_pc(stg + (j * THREADS + tid) * 8, acc[j]);
-            sync_half();
-            float2* ys = ysave + (blk - blk0) * C::YS_STRIDE;
-            for (int o = tid; o < K2; o += THREADS) {
-                const int j = o >> 4, tt = o & 15;
-                const uint32_t src = stg + (j * THREADS + tt * G) * 8;
-                pc sum(0.f, 0.f);
-                if (G % 2 == 0) {
-#pragma unroll
-                    for (int gg = 0; gg < G; gg += 2) {
-                        pc u0, u1;
-                        lds_pc2(src + gg * 8, u0, u1);
-                        sum = sum + u0;
-                        sum = sum + u1;
-                    }
-                } else {
-#pragma unroll
-                    for (int gg = 0; gg < G; ++gg) sum = sum + lds_pc(src + gg * 8);
-                }
-                const int bin = tt + 16 * (j >> 4) + 32 * (j & 15);
-                ys[bin] = make_float2(sum.x, sum.y);
-            }
-        }
-    }
-    sync_half();
-
-    // ---- inverse transforms: column g takes job g (one parked block spectrum) ------------------
-    const int njobs = blk1 - blk0;
-    for (int j0 = 0; j0 < njobs; j0 += G) {
-        const int job = j0 + g;
-        const bool active = job < njobs;
-        const uint32_t stg = sbase + C::OFF_STAGE;
-        pc v[32];
-        const float2* ys = ysave + (active ? job : 0) * C::YS_STRIDE;
-        // conj in, conj out = inverse transform; the table's NCO row part is cancelled on the way in
-        const pc hc(rowph.x, -rowph.y);
-#pragma unroll
-        for (int i1 = 0; i1 < 32; ++i1) {
-            const float2 q = ys[t + 16 * i1];
-            v[i1] = active ? pcmul(pc(q.x, -q.y), hc) : pc(0.f, 0.f);
-        }
-        pass1_store<G>(v, tw_row, stg + xch_wr);
-        sync_half();
-        const int blk = blk0 + (active ? job : 0);
-        const int d = block_shift(blk);
-        const long long Ibase = a.I_lo + (long long)blk * a.V - a.Lmax - d;
-#pragma unroll
-        for (int which = 0; which < 2; ++which) {
-            pc x[16];
-#pragma unroll
-            for (int tr = 0; tr < 16; ++tr) x[tr] = lds_pc(stg + xch_rd + (tr * C::TS + which * 16 * G) * 8);
-            pdft_regs<16, +1>(x);
-            if (active) {
-#pragma unroll
-                for (int k2 = 0; k2 < 16; ++k2) {
-                    const int i = t + 16 * which + 32 * k2;
-                    if (i >= a.Lmax + d && i < a.Lmax + a.V + (d > 0 ? 1 : 0)) {
-                        const long long m = Ibase + i;  // Q == 1
-                        if (m >= a.m_lo && m <= a.m_hi) out[m - a.m0 - 1] = make_float2(x[k2].x, -x[k2].y);
+                    for (int k2 = 0; k2 < 16; ++k2) {
+                        const int i = t + 16 * which + 32 * k2;
+                        if (i >= a.Lmax + d && i < a.Lmax + a.V + (d > 0 ? 1 : 0)) {
+                            const long long m = Ibase + i;  // Q == 1
+                            if (m >= a.m_lo && m <= a.m_hi) out[m - a.m0 - 1] = make_float2(x[k2].x, -x[k2].y);
+                        }
                     }
                 }
             }
+            __syncwarp();
         }
+        // the next group's first tiles go into the stages the inverse just used
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         sync_half();
     }
 }
@@ -453,7 +500,8 @@ EncodeFn encode_fn() {
 template <int G> cudaError_t launch_g(int n_streams, const PolyArgs<float>& a, const CUtensorMap& tm, cudaStream_t st) {
     using C = P2Cfg<G>;
     const size_t smem = C::smem_bytes(a.nbpc);
-    const dim3 grid((unsigned)((a.n_blocks + a.nbpc - 1) / a.nbpc), (unsigned)((n_streams + 1) / 2));
+    const int per_cta = a.nbpc * (a.ngrp > 0 ? a.ngrp : 1);
+    const dim3 grid((unsigned)((a.n_blocks + per_cta - 1) / per_cta), (unsigned)((n_streams + 1) / 2));
     cudaError_t e;
     if (a.nco) {
         auto kern = k_poly2<G, true>;
@@ -475,25 +523,27 @@ int poly2_pick_G(long long P) {
     // branches per round: even (TMA rows are 16-byte multiples) and as few idle columns as possible
     int best = 0;
     double best_eff = 0.0;
-    for (int G : {10, 8}) {
+    for (int G : {10}) {
         const double eff = (double)P / (double)(G * ((P + G - 1) / G));
         if (eff > best_eff + 1e-9) {
             best = G;
             best_eff = eff;
         }
     }
-    return best;
+    return best_eff >= 0.5 ? best : 0;
 }
 
-bool poly2_supported(int K, long long P, long long Q) { return K == K2 && Q == 1 && P >= 2 && (P % 2) == 0 && encode_fn() != nullptr; }
+bool poly2_supported(int K, long long P, long long Q) {
+    return K == K2 && Q == 1 && P >= 2 && (P % 2) == 0 && poly2_pick_G(P) != 0 && encode_fn() != nullptr;
+}
 
-size_t poly2_smem_bytes(int G, int nbpc) { return G == 8 ? P2Cfg<8>::smem_bytes(nbpc) : P2Cfg<10>::smem_bytes(nbpc); }
+size_t poly2_smem_bytes(int G, int nbpc) { return P2Cfg<10>::smem_bytes(nbpc); }
 
 long long poly2_table_index(int G, int r, int g, int k) {
-    const int threads = NT2 * G;
+    const int threads = NT2 * G;  // compute threads per half
     const int k1 = k & 31, k2 = k >> 5;
     const int tt = k1 & 15, which = k1 >> 4;
-    const int tid = tt * G + g;
+    const int tid = (g >> 1) * 32 + 2 * tt + (g & 1);  // warp g/2, lane (t, column parity)
     return ((((long long)r * 2 + which) * 8 + (k2 >> 1)) * threads + tid) * 2 + (k2 & 1);
 }
 
@@ -510,7 +560,6 @@ cudaError_t launch_poly2(int G, int n_streams, const PolyArgs<float>& a, cudaStr
     const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(a.in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
-    if (G == 8) return launch_g<8>(n_streams, a, tm, st);
     if (G == 10) return launch_g<10>(n_streams, a, tm, st);
     return cudaErrorInvalidValue;
 }
