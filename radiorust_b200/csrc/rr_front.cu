@@ -12,9 +12,12 @@
 // transformed.  This is the HBM-bound half of the path: 8 B read and 8*RK/P B
 // written per input sample.
 //
-// A warp takes 32 consecutive rows (= 32*P consecutive samples of one stream,
-// one TMA box) into its own shared-memory tile; lane = row.  With P/2 odd the
-// 16-byte loads of 32 lanes that sit P*8 bytes apart are conflict free.  The
+// A warp takes 16 consecutive rows (= 16*P consecutive samples of one stream,
+// one TMA box) into its own two-slot ring of shared-memory tiles; a lane pair
+// per row, each lane half of the row's columns, the two partial results meet in
+// one shuffle per result.  With P/2 odd the 16-byte loads of lanes that sit P*8
+// bytes apart are conflict free.  16 warps per SM, each with a tile in flight
+// while it works on the other.  The
 // NCO phasor of sample (i, p) factors into the row phasor (exact per row from
 // the integer phase recurrence, transform.rs:333-338, applied to the RK results
 // of the row) and exp(j*w*p) (a P-entry table, applied to the sample).
@@ -37,25 +40,30 @@ namespace rr {
 namespace {
 
 constexpr int FR_WARPS = 4;
-constexpr int FR_ROWS = 32;  // rows per tile = lanes
+constexpr int FR_ROWS = 16;  // rows per tile: a lane pair per row, each lane half of the columns
+constexpr int FR_STAGES = 2;  // tiles per warp in shared memory (one being filled while the other is used)
 
 __device__ __forceinline__ uint32_t f_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <int RK, bool HAS_NCO>
 __global__ void __launch_bounds__(FR_WARPS * 32) k_front(const __grid_constant__ CUtensorMap tmap, const FrontArgs a) {
+    static_assert(RK == 10, "the store split below (6 + 4 results per lane pair) is written for ten columns");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = lane >> 1, hh = lane & 1;  // row of the tile, half of its columns
     const int s = blockIdx.y;
     const int P = a.P;
     const int steps = P / 2;
+    // column pairs of this lane: [st0, st1)
+    const int st0 = hh ? steps / 2 : 0, st1 = hh ? steps : steps / 2;
 
     extern __shared__ __align__(128) unsigned char smem[];
     const int tile_bytes = FR_ROWS * P * 8;
     const int tile_stride = (tile_bytes + 127) / 128 * 128;
-    unsigned char* tile = smem + warp * tile_stride;
-    float* coef = reinterpret_cast<float*>(smem + FR_WARPS * tile_stride);  // [steps][2][RK]
+    unsigned char* tiles = smem + warp * (FR_STAGES * tile_stride);          // this warp's ring of tiles
+    float* coef = reinterpret_cast<float*>(smem + FR_WARPS * FR_STAGES * tile_stride);  // [steps][2][RK]
     float2* colph = reinterpret_cast<float2*>(coef + steps * 2 * RK);        // [P]
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(colph + P);
-    const uint32_t bar = f_smem_u32(&bars[warp]);
+    const uint32_t bar0 = f_smem_u32(&bars[warp * FR_STAGES]);
 
     uint32_t denom = 1, numer_abs = 0, idx0 = 0;
     int sign = 0;
@@ -75,7 +83,8 @@ __global__ void __launch_bounds__(FR_WARPS * 32) k_front(const __grid_constant__
         colph[p] = make_float2(r.x, r.y);
     }
     if (lane == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+#pragma unroll
+        for (int q = 0; q < FR_STAGES; ++q) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + q * 8) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -84,10 +93,10 @@ __global__ void __launch_bounds__(FR_WARPS * 32) k_front(const __grid_constant__
     const float2* __restrict__ hist_end = reinterpret_cast<const float2*>(a.hist2) + ((long long)s + 1) * 2 * a.n;
     float4* __restrict__ u = reinterpret_cast<float4*>(reinterpret_cast<float2*>(a.u) + (long long)s * a.u_stride);
     const long long len = a.len, hist_len = 2 * a.n;
-    const uint32_t tile_s = f_smem_u32(tile);
+    const uint32_t tiles_s = f_smem_u32(tiles);
     const uint32_t coef_s = f_smem_u32(coef), col_s = f_smem_u32(colph);
 
-    // rotation of the row phasor from one tile to the next (32 rows)
+    // rotation of the row phasor from one tile to the next
     pc rot_tile(1.f, 0.f);
     if (HAS_NCO) {
         const cx<float> r = nco_rotation<float>((long long)FR_ROWS * P, numer_abs, denom, sign);
@@ -95,24 +104,40 @@ __global__ void __launch_bounds__(FR_WARPS * 32) k_front(const __grid_constant__
     }
 
     const int tile0 = (blockIdx.x * FR_WARPS + warp) * a.tiles_per_warp;
-    uint32_t phase = 0;
+    const int n_tiles = min(a.tiles_per_warp, (a.n_rows - tile0 * FR_ROWS + FR_ROWS - 1) / FR_ROWS);  // may be <= 0
+    auto tile_pos0 = [&](int k) -> long long { return ((long long)a.row_first + (long long)(tile0 + k) * FR_ROWS) * P - a.J0; };
+    auto tile_interior = [&](long long pos0) -> bool { return pos0 >= 0 && pos0 + (long long)FR_ROWS * P <= len; };
+    // start the TMA copy of tile k into ring slot k % FR_STAGES (interior tiles only)
+    auto issue = [&](int k) {
+        if (k >= n_tiles) return;
+        const long long pos0 = tile_pos0(k);
+        if (!tile_interior(pos0)) return;
+        const uint32_t bar = bar0 + (k % FR_STAGES) * 8;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tile_bytes) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                         tiles_s + (k % FR_STAGES) * tile_stride),
+                     "l"(&tmap), "r"(bar), "r"((int)pos0), "r"(0), "r"(s)
+                     : "memory");
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < FR_STAGES - 1; ++q) issue(q);
+    }
+
+    uint32_t phase = 0;  // bit q: parity of ring slot q's next completion
     pc rowph(1.f, 0.f);
-    for (int k = 0; k < a.tiles_per_warp; ++k) {
+    for (int k = 0; k < n_tiles; ++k) {
+        const int slot = k % FR_STAGES;
         const int v0 = (tile0 + k) * FR_ROWS;  // first row (of this push's u rows) of the tile
-        if (v0 >= a.n_rows) break;
-        const long long pos0 = ((long long)a.row_first + v0) * P - a.J0;  // push offset of the tile's first sample
-        const bool interior = pos0 >= 0 && pos0 + (long long)FR_ROWS * P <= len;
-        if (interior && lane == 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tile_bytes) : "memory");
-            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(tile_s),
-                         "l"(&tmap), "r"(bar), "r"((int)pos0), "r"(0), "r"(s)
-                         : "memory");
-        }
-        // row phasor: exact at the warp's first tile and every 8th one, rotated in between
+        const long long pos0 = tile_pos0(k);
+        const bool interior = tile_interior(pos0);
+        const uint32_t tile_s = tiles_s + slot * tile_stride;
+        // the slot of tile k + FR_STAGES - 1 was released at the end of the previous iteration
+        if (lane == 0) issue(k + FR_STAGES - 1);
+        // row phasor: exact at the warp's first tile and every 16th one, rotated in between
         if (HAS_NCO) {
-            if ((k & 7) == 0) {
-                long long kk = ((long long)idx0 + pos0 + (long long)lane * P) % (long long)denom;
+            if ((k & 15) == 0) {
+                long long kk = ((long long)idx0 + pos0 + (long long)row * P) % (long long)denom;
                 if (kk < 0) kk += denom;
                 const cx<float> c = nco_phasor<float>(mulmod_u32(numer_abs, (uint32_t)kk, denom), denom, sign, start);
                 rowph = pc(c.x, c.y);
@@ -120,12 +145,7 @@ __global__ void __launch_bounds__(FR_WARPS * 32) k_front(const __grid_constant__
                 rowph = pcmul(rowph, rot_tile);
             }
         }
-        pc acc[RK];
-#pragma unroll
-        for (int c = 0; c < RK; ++c) acc[c] = pc(0.f, 0.f);
-
         if (interior) {
-            // wait for the tile
             asm volatile(
                 "{\n"
                 ".reg .pred p;\n"
@@ -134,75 +154,104 @@ __global__ void __launch_bounds__(FR_WARPS * 32) k_front(const __grid_constant__
                 "@p bra FD_%=;\n"
                 "bra FW_%=;\n"
                 "FD_%=:\n"
-                "}\n" ::"r"(bar),
-                "r"(phase)
+                "}\n" ::"r"(bar0 + slot * 8),
+                "r"((phase >> slot) & 1)
                 : "memory");
-            phase ^= 1;
-            const uint32_t row_s = tile_s + lane * (P * 8);
-#pragma unroll 5
-            for (int st = 0; st < steps; ++st) {
-                pc x0, x1;
-                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x0.x), "=f"(x0.y), "=f"(x1.x), "=f"(x1.y) : "r"(row_s + st * 16));
-                if (HAS_NCO) {
-                    pc c0, c1;
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c0.x), "=f"(c0.y), "=f"(c1.x), "=f"(c1.y) : "r"(col_s + st * 16));
-                    x0 = pcmul(x0, c0);
-                    x1 = pcmul(x1, c1);
+            phase ^= 1u << slot;
+        } else {
+            // edge tile (reaches before the pushed samples or past them): the warp fills its slot itself,
+            // coalesced.  History samples are already mixed: they get the conjugate of the phasors that the
+            // loop below and the row's results apply.
+            int rr_ = 0, p = lane;
+            while (p >= P) {
+                p -= P;
+                ++rr_;
+            }
+            float2* dst = reinterpret_cast<float2*>(tiles + slot * tile_stride);
+            for (int e = lane; e < FR_ROWS * P; e += 32) {
+                const long long pos = pos0 + e;
+                float2 q = make_float2(0.f, 0.f);
+                if (pos >= 0) {
+                    if (pos < len) q = in[pos];
+                } else if (pos >= -hist_len) {
+                    q = hist_end[pos];
                 }
-                float cf[2 * RK];
-                static_assert((2 * RK) % 4 == 2 || (2 * RK) % 4 == 0, "");
-#pragma unroll
-                for (int q = 0; q < (2 * RK) / 4; ++q)
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                 : "=f"(cf[4 * q]), "=f"(cf[4 * q + 1]), "=f"(cf[4 * q + 2]), "=f"(cf[4 * q + 3])
-                                 : "r"(coef_s + st * (2 * RK * 4) + q * 16));
-                if ((2 * RK) % 4 == 2)
-                    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(cf[2 * RK - 2]), "=f"(cf[2 * RK - 1]) : "r"(coef_s + st * (2 * RK * 4) + (2 * RK - 2) * 4));
-#pragma unroll
-                for (int c = 0; c < RK; ++c) {
-                    acc[c] = pfma_s(x0, cf[c], acc[c]);
-                    acc[c] = pfma_s(x1, cf[RK + c], acc[c]);
+                if (HAS_NCO) {
+                    const float rx = __shfl_sync(0xffffffffu, rowph.x, 2 * rr_), ry = __shfl_sync(0xffffffffu, rowph.y, 2 * rr_);
+                    if (pos < 0) {
+                        const float2 c = colph[p];
+                        const pc f = pcmul(pc(rx, ry), pc(c.x, c.y));
+                        const pc y = pcmulc(pc(q.x, q.y), f);
+                        q = make_float2(y.x, y.y);
+                    }
+                }
+                dst[e] = q;
+                p += 32;
+                while (p >= P) {
+                    p -= P;
+                    ++rr_;
                 }
             }
-            __syncwarp();  // every lane is done with the tile before the next copy lands in it
-        } else {
-            // edge rows: straight from global memory; history samples are already mixed, so they only get
-            // the conjugate of the row phasor that the row's results receive below
-            const long long prow = pos0 + (long long)lane * P;
-            const pc hc(rowph.x, -rowph.y);
-            for (int p = 0; p < P; ++p) {
-                const long long pos = prow + p;
-                pc x(0.f, 0.f);
-                if (pos >= 0) {
-                    if (pos < len) {
-                        const float2 q = in[pos];
-                        x = pc(q.x, q.y);
-                        if (HAS_NCO) {
-                            const float2 c = colph[p];
-                            x = pcmul(x, pc(c.x, c.y));
-                        }
-                    }
-                } else if (pos >= -hist_len) {
-                    const float2 q = hist_end[pos];
-                    x = pc(q.x, q.y);
-                    if (HAS_NCO) x = pcmul(x, hc);
-                }
-                const float* cf = coef + (p >> 1) * (2 * RK) + (p & 1) * RK;
+            __syncwarp();
+        }
+        pc acc[RK];
 #pragma unroll
-                for (int c = 0; c < RK; ++c) acc[c] = pfma_s(x, cf[c], acc[c]);
+        for (int c = 0; c < RK; ++c) acc[c] = pc(0.f, 0.f);
+        const uint32_t row_s = tile_s + row * (P * 8);
+#pragma unroll 4
+        for (int st = st0; st < st1; ++st) {
+            pc x0, x1;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x0.x), "=f"(x0.y), "=f"(x1.x), "=f"(x1.y) : "r"(row_s + st * 16));
+            if (HAS_NCO) {
+                pc c0, c1;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c0.x), "=f"(c0.y), "=f"(c1.x), "=f"(c1.y) : "r"(col_s + st * 16));
+                x0 = pcmul(x0, c0);
+                x1 = pcmul(x1, c1);
+            }
+            float cf[2 * RK];
+#pragma unroll
+            for (int q = 0; q < (2 * RK) / 4; ++q)
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(cf[4 * q]), "=f"(cf[4 * q + 1]), "=f"(cf[4 * q + 2]), "=f"(cf[4 * q + 3])
+                             : "r"(coef_s + st * (2 * RK * 4) + q * 16));
+#pragma unroll
+            for (int c = 0; c < RK; ++c) {
+                acc[c] = pfma_s(x0, cf[c], acc[c]);
+                acc[c] = pfma_s(x1, cf[RK + c], acc[c]);
             }
         }
-        const int v = v0 + lane;
+        // every lane is done with the slot: it may be refilled (generic-proxy accesses ordered before the copy)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        // the two column halves of a row meet; lane hh = 0 stores results 0..5, lane hh = 1 results 6..9
+#pragma unroll
+        for (int c = 0; c < RK; ++c) {
+            acc[c].x += __shfl_xor_sync(0xffffffffu, acc[c].x, 1);
+            acc[c].y += __shfl_xor_sync(0xffffffffu, acc[c].y, 1);
+        }
+        const int v = v0 + row;
         if (v < a.n_rows) {
             float4* dst = u + ((long long)v * RK) / 2;
+            if (hh == 0) {
 #pragma unroll
-            for (int c = 0; c < RK; c += 2) {
-                pc y0 = acc[c], y1 = acc[c + 1];
-                if (HAS_NCO) {
-                    y0 = pcmul(y0, rowph);
-                    y1 = pcmul(y1, rowph);
+                for (int c = 0; c < 6; c += 2) {
+                    pc y0 = acc[c], y1 = acc[c + 1];
+                    if (HAS_NCO) {
+                        y0 = pcmul(y0, rowph);
+                        y1 = pcmul(y1, rowph);
+                    }
+                    dst[c / 2] = make_float4(y0.x, y0.y, y1.x, y1.y);
                 }
-                dst[c / 2] = make_float4(y0.x, y0.y, y1.x, y1.y);
+            } else {
+#pragma unroll
+                for (int c = 6; c < RK; c += 2) {
+                    pc y0 = acc[c], y1 = acc[c + 1];
+                    if (HAS_NCO) {
+                        y0 = pcmul(y0, rowph);
+                        y1 = pcmul(y1, rowph);
+                    }
+                    dst[c / 2] = make_float4(y0.x, y0.y, y1.x, y1.y);
+                }
             }
         }
     }
@@ -234,8 +283,11 @@ cudaError_t launch_front(int rank_pad, int n_streams, const FrontArgs& a0, cudaS
     if (!enc || rank_pad != 10) return cudaErrorNotSupported;
     FrontArgs a = a0;
     const int tiles = (a.n_rows + FR_ROWS - 1) / FR_ROWS;
-    a.tiles_per_warp = 8;
-    while (a.tiles_per_warp > 1 && (long long)n_streams * ((tiles + FR_WARPS * a.tiles_per_warp - 1) / (FR_WARPS * a.tiles_per_warp)) < 1184) a.tiles_per_warp /= 2;
+    // long-lived warps amortise the per-CTA tables: as few CTAs per stream as keep ~4 CTAs per SM in the
+    // grid, the tiles spread evenly over their warps
+    int ctas = (tiles + FR_WARPS * 64 - 1) / (FR_WARPS * 64);
+    while ((long long)n_streams * ctas < 592 && ctas * FR_WARPS < tiles) ++ctas;
+    a.tiles_per_warp = (tiles + ctas * FR_WARPS - 1) / (ctas * FR_WARPS);
     // the stream as overlapping rows of P samples: element (c0, i, s) = in[s*in_stride + c0 + i*P]
     CUtensorMap tm;
     const cuuint64_t dims[3] = {(cuuint64_t)a.len, (cuuint64_t)FR_ROWS, (cuuint64_t)n_streams};
@@ -247,7 +299,7 @@ cudaError_t launch_front(int rank_pad, int n_streams, const FrontArgs& a0, cudaS
                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
     const int tile_stride = (FR_ROWS * a.P * 8 + 127) / 128 * 128;
-    const size_t smem = (size_t)FR_WARPS * tile_stride + (size_t)(a.P / 2) * 2 * 10 * 4 + (size_t)a.P * 8 + FR_WARPS * 8 + 16;
+    const size_t smem = (size_t)FR_WARPS * FR_STAGES * tile_stride + (size_t)(a.P / 2) * 2 * 10 * 4 + (size_t)a.P * 8 + FR_WARPS * FR_STAGES * 8 + 16;
     const dim3 grid((unsigned)((tiles + FR_WARPS * a.tiles_per_warp - 1) / (FR_WARPS * a.tiles_per_warp)), (unsigned)n_streams);
     cudaError_t e;
     if (a.nco) {

@@ -159,7 +159,9 @@ __device__ __forceinline__ void pass1_store(pc (&v)[32], uint32_t tw_row, uint32
 }  // namespace
 
 // One CTA = two independent halves (own stream, shared memory, mbarriers, named barrier).
-template <int G, bool HAS_NCO>
+// SINGLE: P <= G, one round per block (the low-rate part behind k_front): nothing is accumulated over
+// rounds, the products go straight to the warp's strip and the block needs one barrier.
+template <int G, bool HAS_NCO, bool SINGLE>
 __global__ void __launch_bounds__(2 * P2Cfg<G>::THREADS, 1) k_poly2(const __grid_constant__ CUtensorMap tmap, const PolyArgs<float> a, const int n_streams) {
     using C = P2Cfg<G>;
     constexpr int THREADS = C::THREADS, PITCH = C::PITCH;
@@ -324,8 +326,10 @@ __global__ void __launch_bounds__(2 * P2Cfg<G>::THREADS, 1) k_poly2(const __grid
                 __syncwarp();
             }
             pc acc[32];
+            if (!SINGLE) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] = pc(0.f, 0.f);
+                for (int j = 0; j < 32; ++j) acc[j] = pc(0.f, 0.f);
+            }
 
             for (int r = 0; r < NR; ++r, ++R) {
                 const int stage = R & 1;
@@ -396,7 +400,7 @@ __global__ void __launch_bounds__(2 * P2Cfg<G>::THREADS, 1) k_poly2(const __grid
                     pdft_regs<16, +1>(x);
                     if (which == 1 && r + 1 < NR) release_stage(blk0, blk1, R);  // the exchange is read: stage free
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) acc[which * 16 + k] = pcfma(x[k], h[k], acc[which * 16 + k]);
+                    for (int k = 0; k < 16; ++k) acc[which * 16 + k] = SINGLE ? pcmul(x[k], h[k]) : pcfma(x[k], h[k], acc[which * 16 + k]);
                     if (which == 0) {
 #pragma unroll
                         for (int jj = 0; jj < 8; ++jj) ldg_pc2(gp + (8 + jj) * THREADS, h[2 * jj], h[2 * jj + 1]);
@@ -406,7 +410,29 @@ __global__ void __launch_bounds__(2 * P2Cfg<G>::THREADS, 1) k_poly2(const __grid
 
             // ---- sum the G partial spectra of this block, park the result; the block's last stage is
             //      the scratch area and is released afterwards ------------------------------------------
-            {
+            if (SINGLE) {
+                // the exchange of this warp's strip is consumed: park bin (j, t) of its two columns at row 16*j + t
+                const uint32_t stg = sbase + C::OFF_STAGE + ((R - 1) & 1) * C::STAGE_BYTES;
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sts_pc(stg + xch_rd + (16 * j) * PITCH, acc[j]);
+                sync_half();
+                float2* ys = ysave + (blk - blk0) * C::YS_STRIDE;
+                for (int o = tid; o < K2; o += THREADS) {
+                    const uint32_t src = stg + o * PITCH;  // row o: the G columns side by side
+                    pc sum(0.f, 0.f);
+#pragma unroll
+                    for (int w = 0; w < C::NCW; ++w) {
+                        pc u0, u1;
+                        lds_pc2(src + w * 16, u0, u1);
+                        sum = sum + u0;
+                        sum = sum + u1;
+                    }
+                    const int j = o >> 4, tt = o & 15;
+                    ys[tt + 16 * (j >> 4) + 32 * (j & 15)] = make_float2(sum.x, sum.y);
+                }
+                release_stage(blk0, blk1, R - 1);
+            } else {
                 const uint32_t stg = sbase + C::OFF_STAGE + ((R - 1) & 1) * C::STAGE_BYTES;
                 sync_half();
 #pragma unroll
@@ -502,18 +528,13 @@ template <int G> cudaError_t launch_g(int n_streams, const PolyArgs<float>& a, c
     const size_t smem = C::smem_bytes(a.nbpc);
     const int per_cta = a.nbpc * (a.ngrp > 0 ? a.ngrp : 1);
     const dim3 grid((unsigned)((a.n_blocks + per_cta - 1) / per_cta), (unsigned)((n_streams + 1) / 2));
-    cudaError_t e;
-    if (a.nco) {
-        auto kern = k_poly2<G, true>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        kern<<<grid, 2 * C::THREADS, smem, st>>>(tm, a, n_streams);
-    } else {
-        auto kern = k_poly2<G, false>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        kern<<<grid, 2 * C::THREADS, smem, st>>>(tm, a, n_streams);
-    }
+    void (*kern)(const CUtensorMap, const PolyArgs<float>, const int);
+    const bool single = a.P <= G;
+    if (a.nco) kern = single ? k_poly2<G, true, true> : k_poly2<G, true, false>;
+    else kern = single ? k_poly2<G, false, true> : k_poly2<G, false, false>;
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, 2 * C::THREADS, smem, st>>>(tm, a, n_streams);
     return cudaGetLastError();
 }
 
