@@ -162,34 +162,38 @@ __global__ void __launch_bounds__(FR_WARPS * 32) k_front(const __grid_constant__
             // edge tile (reaches before the pushed samples or past them): the warp fills its slot itself,
             // coalesced.  History samples are already mixed: they get the conjugate of the phasors that the
             // loop below and the row's results apply.
-            int rr_ = 0, p = lane;
-            while (p >= P) {
-                p -= P;
-                ++rr_;
-            }
             float2* dst = reinterpret_cast<float2*>(tiles + slot * tile_stride);
-            for (int e = lane; e < FR_ROWS * P; e += 32) {
-                const long long pos = pos0 + e;
-                float2 q = make_float2(0.f, 0.f);
-                if (pos >= 0) {
-                    if (pos < len) q = in[pos];
-                } else if (pos >= -hist_len) {
-                    q = hist_end[pos];
-                }
-                if (HAS_NCO) {
-                    const float rx = __shfl_sync(0xffffffffu, rowph.x, 2 * rr_), ry = __shfl_sync(0xffffffffu, rowph.y, 2 * rr_);
-                    if (pos < 0) {
-                        const float2 c = colph[p];
-                        const pc f = pcmul(pc(rx, ry), pc(c.x, c.y));
-                        const pc y = pcmulc(pc(q.x, q.y), f);
-                        q = make_float2(y.x, y.y);
+            constexpr int UNR = 5;  // loads in flight per lane
+            for (int e0 = lane; e0 < FR_ROWS * P; e0 += 32 * UNR) {
+                float2 q[UNR];
+#pragma unroll
+                for (int j = 0; j < UNR; ++j) {
+                    const int e = e0 + 32 * j;
+                    const long long pos = pos0 + e;
+                    q[j] = make_float2(0.f, 0.f);
+                    if (e < FR_ROWS * P) {
+                        if (pos >= 0) {
+                            if (pos < len) q[j] = __ldg(in + pos);
+                        } else if (pos >= -hist_len) {
+                            q[j] = __ldg(hist_end + pos);
+                        }
                     }
                 }
-                dst[e] = q;
-                p += 32;
-                while (p >= P) {
-                    p -= P;
-                    ++rr_;
+#pragma unroll
+                for (int j = 0; j < UNR; ++j) {
+                    const int e = e0 + 32 * j;
+                    const int er = e < FR_ROWS * P ? e : 0;
+                    const int rr_ = er / P, p = er - rr_ * P;
+                    if (HAS_NCO) {
+                        const float rx = __shfl_sync(0xffffffffu, rowph.x, 2 * rr_), ry = __shfl_sync(0xffffffffu, rowph.y, 2 * rr_);
+                        if (pos0 + e < 0) {
+                            const float2 c = colph[p];
+                            const pc f = pcmul(pc(rx, ry), pc(c.x, c.y));
+                            const pc y = pcmulc(pc(q[j].x, q[j].y), f);
+                            q[j] = make_float2(y.x, y.y);
+                        }
+                    }
+                    if (e < FR_ROWS * P) dst[e] = q[j];
                 }
             }
             __syncwarp();

@@ -461,6 +461,7 @@ __global__ void __launch_bounds__(2 * P2Cfg<G>::THREADS, 1) k_poly2(const __grid
         // ---- inverse transforms: branch column g takes job g (one parked block spectrum) -------------
         const int njobs = blk1 - blk0;
         for (int j0 = 0; j0 < njobs; j0 += G) {
+            if (j0 + 2 * warp >= njobs) continue;  // neither column of this warp has a job (warp-uniform)
             const int job = j0 + g;
             const bool active = job < njobs;
             const uint32_t stg = sbase + C::OFF_STAGE;
