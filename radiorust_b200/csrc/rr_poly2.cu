@@ -45,6 +45,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <mutex>
 
 #include "rr_kernels.h"
@@ -170,8 +171,10 @@ __global__ void __launch_bounds__(2 * P2Cfg<G>::THREADS, 1) k_poly2(const __grid
     const int warp = tid >> 5, lane = tid & 31;
     const int t = lane >> 1, gg = lane & 1;
     const int g = 2 * warp + gg;  // branch column of this lane
-    const int s = blockIdx.y * 2 + half;
-    if (s >= n_streams) return;  // the halves never meet at a CTA-wide barrier
+    // this half works through streams s_first, s_first + s_step, ...
+    const int s_first = blockIdx.y * 2 + half, s_step = gridDim.y * 2;
+    if (s_first >= n_streams) return;  // the halves never meet at a CTA-wide barrier
+    int s = s_first;
     auto sync_half = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(half + 1), "n"(THREADS) : "memory"); };
 
     extern __shared__ __align__(128) unsigned char smem_all[];
@@ -187,31 +190,34 @@ __global__ void __launch_bounds__(2 * P2Cfg<G>::THREADS, 1) k_poly2(const __grid
     // completely inside the pushed samples and are fed by TMA.  A block whose window would run past
     // the pushed samples is moved back by `d` rows so that it still lies inside them (its first d
     // outputs repeat the previous block's and are not stored).
-    const long long need = (long long)(K2 - 1) * Pd + (long long)NR * G;  // samples a tile sweep touches
-    auto block_shift = [&](int blk) -> int {
-        const long long Ibase = a.I_lo + (long long)blk * a.V - a.Lmax;
-        const long long boff = Ibase * Pd - a.J0 - Pd;
-        if (blk == 0 || boff + need <= len) return 0;  // block 0 has no predecessor to cover the skipped outputs
-        const long long d = (boff + need - len + Pd - 1) / Pd;
-        // with Q == 1 the l = -1 slot of every branch filter is empty, so row K-1 is a valid output too:
-        // the moved block may use it to reach m_hi
-        return (d < a.V && boff - d * Pd >= 0 && a.m_hi - (Ibase - d) <= K2 - 1) ? (int)d : 0;
-    };
-    auto block_off = [&](int blk) -> long long {
-        const long long Ibase = a.I_lo + (long long)blk * a.V - a.Lmax - block_shift(blk);
-        return Ibase * Pd - a.J0 - Pd;
-    };
-    auto is_interior = [&](long long boff) -> bool { return boff >= 0 && boff + need <= len; };
+    const int need = (K2 - 1) * Pd + NR * G;  // samples a tile sweep touches
+    const int boff0 = (int)((a.I_lo - a.Lmax) * Pd - a.J0 - Pd), bstep = a.V * Pd;  // window start of block 0, per block
+    // only the last block can run past the end; block 0 has no predecessor to cover skipped outputs
+    int last_shift = 0;
+    {
+        const int blk = a.n_blocks - 1;
+        const int boff = boff0 + blk * bstep;
+        if (blk > 0 && boff + need > len) {
+            const int d = (boff + need - len + Pd - 1) / Pd;
+            const long long Ibase = a.I_lo + (long long)blk * a.V - a.Lmax;
+            // with Q == 1 the l = -1 slot of every branch filter is empty, so row K-1 is a valid output too:
+            // the moved block may use it to reach m_hi
+            if (d < a.V && boff - d * Pd >= 0 && a.m_hi - (Ibase - d) <= K2 - 1) last_shift = d;
+        }
+    }
+    auto block_shift = [&](int blk) -> int { return blk == a.n_blocks - 1 ? last_shift : 0; };
+    auto block_off = [&](int blk) -> int { return boff0 + blk * bstep - block_shift(blk) * Pd; };
+    auto is_interior = [&](int boff) -> bool { return boff >= 0 && boff + need <= len; };
     // the tile of round Rg of the group that starts at block blk_first (nothing for edge blocks)
     auto issue_tile = [&](int blk_first, int blk_end, int Rg) {
         const int blk = blk_first + Rg / NR;
         if (blk >= blk_end) return;
-        const long long boff = block_off(blk);
+        const int boff = block_off(blk);
         if (!is_interior(boff)) return;
         const int stage = Rg & 1;
         const uint32_t bar = bar_full + stage * 8;
         mbar_expect_tx(bar, C::TILE_BYTES);
-        tma_load_4d(sbase + C::OFF_STAGE + stage * C::STAGE_BYTES, &tmap, bar, (int)(boff + (long long)(Rg % NR) * G), 0, 0, s);
+        tma_load_4d(sbase + C::OFF_STAGE + stage * C::STAGE_BYTES, &tmap, bar, boff + (Rg % NR) * G, 0, 0, s);
     };
 
     const uint32_t e_tab = sbase + C::OFF_E;
@@ -223,9 +229,12 @@ __global__ void __launch_bounds__(2 * P2Cfg<G>::THREADS, 1) k_poly2(const __grid
     const uint32_t xch_rd = t * PITCH + g * 8;
     float2* ysave = reinterpret_cast<float2*>(smem + C::OFF_YS);
 
+    const float4* __restrict__ gtab = reinterpret_cast<const float4*>(a.gtab);
+    uint32_t phase = 0;  // bit `stage`: parity of the next TMA completion to wait for
+
+    for (; s < n_streams; s += s_step) {
     const float2* __restrict__ in = reinterpret_cast<const float2*>(a.in) + (long long)s * a.in_stride;
     const float2* __restrict__ hist_end = reinterpret_cast<const float2*>(a.hist2) + ((long long)s + 1) * 2 * a.n;
-    const float4* __restrict__ gtab = reinterpret_cast<const float4*>(a.gtab);
     float2* __restrict__ out = reinterpret_cast<float2*>(a.out) + (long long)s * a.out_stride;
 
     // ---- NCO constants, tables -------------------------------------------------------------
@@ -241,7 +250,7 @@ __global__ void __launch_bounds__(2 * P2Cfg<G>::THREADS, 1) k_poly2(const __grid
         idx0 = ns.idx;
         start = (float)ns.start_phase;
     }
-    {
+    if (HAS_NCO || s == s_first) {  // the tables depend on the stream only through its NCO
         float2* et = reinterpret_cast<float2*>(smem + C::OFF_E);  // E[32] | rowph[16] | rotG
         if (tid < 49) {
             cx<float> r(1.f, 0.f);
@@ -249,7 +258,7 @@ __global__ void __launch_bounds__(2 * P2Cfg<G>::THREADS, 1) k_poly2(const __grid
             if (HAS_NCO) r = nco_rotation<float>(d, numer_abs, denom, sign);
             et[tid] = make_float2(r.x, r.y);
         }
-        if (tid == 64) {
+        if (tid == 64 && s == s_first) {
             mbar_init(bar_full, 1);
             mbar_init(bar_full + 8, 1);
             *reinterpret_cast<uint2*>(smem + C::OFF_BAR + 16) = make_uint2(0u, 0u);
@@ -284,8 +293,6 @@ __global__ void __launch_bounds__(2 * P2Cfg<G>::THREADS, 1) k_poly2(const __grid
     const uint32_t ecp_wr = ecp + (t * G + g) * 16;
     const uint32_t ecp_rd = ecp + g * 16;
 
-    uint32_t phase = 0;  // bit `stage`: parity of the next TMA completion to wait for
-
     // hand stage (R & 1) back after round R of the group: the warp that completes the count starts the
     // TMA copy of round R + 2 into it
     auto release_stage = [&](int gb0, int gb1, int R) {
@@ -308,7 +315,7 @@ __global__ void __launch_bounds__(2 * P2Cfg<G>::THREADS, 1) k_poly2(const __grid
         int R = 0;  // rounds of this group
 
         for (int blk = blk0; blk < blk1; ++blk) {
-            const long long boff = block_off(blk);
+            const int boff = block_off(blk);
             const bool interior = is_interior(boff);
 
             pc cp(1.f, 0.f);  // NCO phasor of sample (i = 0, p = r*G + g) of this block, r = next round to prepare
@@ -355,7 +362,7 @@ __global__ void __launch_bounds__(2 * P2Cfg<G>::THREADS, 1) k_poly2(const __grid
                     // thread-local loads (all issued first, predicated); history samples are already mixed:
                     // for them only the row part that the twiddles will apply is cancelled
                     const int p = r * G + g;
-                    const int pos0 = (int)boff + t * Pd + p;
+                    const int pos0 = boff + t * Pd + p;
                     const int step = 16 * Pd;
                     const unsigned span = (unsigned)(len + hist_len);
 #pragma unroll
@@ -502,6 +509,7 @@ __global__ void __launch_bounds__(2 * P2Cfg<G>::THREADS, 1) k_poly2(const __grid
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         sync_half();
     }
+    }  // streams
 }
 
 // ---------------------------------------------------------------------------
@@ -528,7 +536,18 @@ template <int G> cudaError_t launch_g(int n_streams, const PolyArgs<float>& a, c
     using C = P2Cfg<G>;
     const size_t smem = C::smem_bytes(a.nbpc);
     const int per_cta = a.nbpc * (a.ngrp > 0 ? a.ngrp : 1);
-    const dim3 grid((unsigned)((a.n_blocks + per_cta - 1) / per_cta), (unsigned)((n_streams + 1) / 2));
+    // one CTA per SM; a half walks through several streams when there are more stream pairs than SMs
+    static int sm_count = 0;
+    if (sm_count == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (sm_count <= 0) sm_count = 1;
+    }
+    const unsigned gx = (unsigned)((a.n_blocks + per_cta - 1) / per_cta);
+    unsigned gy = (unsigned)((n_streams + 1) / 2);
+    if ((long long)gx * gy > sm_count) gy = (unsigned)std::max(1, std::min((int)gy, (sm_count + (int)gx - 1) / (int)gx));
+    const dim3 grid(gx, gy);
     void (*kern)(const CUtensorMap, const PolyArgs<float>, const int);
     const bool single = a.P <= G;
     if (a.nco) kern = single ? k_poly2<G, true, true> : k_poly2<G, true, false>;
