@@ -171,6 +171,7 @@ struct Stage {
     DevBuf hperm, tw;
     DevBuf hist2[2];  // [S][2n] post-NCO samples preceding the next push (older chunk | newer chunk), ping-pong
     int hist_cur = 0;
+    long long hist_fused_jlo = -1;  // >= 0: this push's k_front already wrote entries [0, jlo) of the new hist2
     DevBuf ztmp;      // filter-output scratch of the unfused stateful path
     std::vector<std::complex<double>> taps;  // windowed impulse response (Flt-rounded), for the polyphase tables
     bool taps_valid = false;
@@ -942,6 +943,16 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
                         fa.n_rows = (int)n_rows;
                         fa.u = ds.ubuf.p;
                         fa.u_stride = u_stride;
+                        // the rows cover push offsets [row_first*P - J0, m_hi*P - J0): when that reaches back to
+                        // len - 2n the kernel also writes the Filter's next history up to its last row
+                        const long long cover_lo = fa.row_first * Pq - a.J0, cover_hi = m_hi * Pq - a.J0;
+                        f.hist_fused_jlo = -1;
+                        if (a.len >= 2 * a.n && cover_lo <= a.len - 2 * a.n && cover_hi > a.len - 2 * a.n) {
+                            fa.hist_out = f.hist2[f.hist_cur ^ 1].p;
+                            fa.hist_from = a.len - 2 * a.n;
+                            fa.hist_stride = 2 * a.n;
+                            f.hist_fused_jlo = cover_hi - fa.hist_from;
+                        }
                         RR_TIMED_LAUNCH(c, "k_front", 1, rr::launch_front(RK, S, fa, st));
                         rr::PolyArgs<float> b{};
                         b.in = ds.ubuf.p;
@@ -1172,7 +1183,9 @@ int run_push(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_chunks,
                 }
                 // new history: the last two mixed chunks (filters.rs:260 keeps one; the polyphase path needs two)
                 RR_LAUNCH(1, rr::launch_hist2_update<T>(io.in, io.in_stride, len, s.hist2[s.hist_cur].p, s.hist2[s.hist_cur ^ 1].p, (long long)n,
-                                                        io.nco ? (const rr::NcoStream*)io.nco->nco_d.p : nullptr, S, st));
+                                                        io.nco ? (const rr::NcoStream*)io.nco->nco_d.p : nullptr, S, st,
+                                                        s.hist_fused_jlo > 0 ? s.hist_fused_jlo : 0));
+                s.hist_fused_jlo = -1;
                 s.hist_cur ^= 1;
                 if (io.nco) {
                     RR_LAUNCH(1, rr::launch_nco_advance((rr::NcoStream*)io.nco->nco_d.p, S, len, st));

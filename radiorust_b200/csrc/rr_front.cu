@@ -30,6 +30,7 @@
 #include <cuda_runtime.h>
 
 #include <mutex>
+#include <type_traits>
 
 #include "rr_kernels.h"
 #include "rr_poly.cuh"
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(FR_WARPS * 32) k_front(const __grid_constant__
     const float2* __restrict__ hist_end = reinterpret_cast<const float2*>(a.hist2) + ((long long)s + 1) * 2 * a.n;
     float4* __restrict__ u = reinterpret_cast<float4*>(reinterpret_cast<float2*>(a.u) + (long long)s * a.u_stride);
     const long long len = a.len, hist_len = 2 * a.n;
+    float2* __restrict__ hist_o = a.hist_out ? reinterpret_cast<float2*>(a.hist_out) + (long long)s * a.hist_stride : nullptr;
     const uint32_t tiles_s = f_smem_u32(tiles);
     const uint32_t coef_s = f_smem_u32(coef), col_s = f_smem_u32(colph);
 
@@ -202,28 +204,43 @@ __global__ void __launch_bounds__(FR_WARPS * 32) k_front(const __grid_constant__
 #pragma unroll
         for (int c = 0; c < RK; ++c) acc[c] = pc(0.f, 0.f);
         const uint32_t row_s = tile_s + row * (P * 8);
+        const long long prow = pos0 + (long long)row * P;  // push offset of this lane's row
+        const bool row_ok = v0 + row < a.n_rows;
+        auto run_row = [&](auto write_hist) {
 #pragma unroll 4
-        for (int st = st0; st < st1; ++st) {
-            pc x0, x1;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x0.x), "=f"(x0.y), "=f"(x1.x), "=f"(x1.y) : "r"(row_s + st * 16));
-            if (HAS_NCO) {
-                pc c0, c1;
-                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c0.x), "=f"(c0.y), "=f"(c1.x), "=f"(c1.y) : "r"(col_s + st * 16));
-                x0 = pcmul(x0, c0);
-                x1 = pcmul(x1, c1);
-            }
-            float cf[2 * RK];
+            for (int st = st0; st < st1; ++st) {
+                pc x0, x1;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x0.x), "=f"(x0.y), "=f"(x1.x), "=f"(x1.y) : "r"(row_s + st * 16));
+                if (HAS_NCO) {
+                    pc c0, c1;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c0.x), "=f"(c0.y), "=f"(c1.x), "=f"(c1.y) : "r"(col_s + st * 16));
+                    x0 = pcmul(x0, c0);
+                    x1 = pcmul(x1, c1);
+                }
+                if (decltype(write_hist)::value) {
+                    // the Filter's next history: the fully mixed samples near the end of the push
+                    const long long j = prow + 2 * st - a.hist_from;
+                    if (row_ok && j >= -1) {
+                        const pc y0 = HAS_NCO ? pcmul(x0, rowph) : x0, y1 = HAS_NCO ? pcmul(x1, rowph) : x1;
+                        if (j >= 0) hist_o[j] = make_float2(y0.x, y0.y);
+                        hist_o[j + 1] = make_float2(y1.x, y1.y);
+                    }
+                }
+                float cf[2 * RK];
 #pragma unroll
-            for (int q = 0; q < (2 * RK) / 4; ++q)
-                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                             : "=f"(cf[4 * q]), "=f"(cf[4 * q + 1]), "=f"(cf[4 * q + 2]), "=f"(cf[4 * q + 3])
-                             : "r"(coef_s + st * (2 * RK * 4) + q * 16));
+                for (int q = 0; q < (2 * RK) / 4; ++q)
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(cf[4 * q]), "=f"(cf[4 * q + 1]), "=f"(cf[4 * q + 2]), "=f"(cf[4 * q + 3])
+                                 : "r"(coef_s + st * (2 * RK * 4) + q * 16));
 #pragma unroll
-            for (int c = 0; c < RK; ++c) {
-                acc[c] = pfma_s(x0, cf[c], acc[c]);
-                acc[c] = pfma_s(x1, cf[RK + c], acc[c]);
+                for (int c = 0; c < RK; ++c) {
+                    acc[c] = pfma_s(x0, cf[c], acc[c]);
+                    acc[c] = pfma_s(x1, cf[RK + c], acc[c]);
+                }
             }
-        }
+        };
+        if (hist_o != nullptr && pos0 + (long long)FR_ROWS * P > a.hist_from) run_row(std::true_type{});
+        else run_row(std::false_type{});
         // every lane is done with the slot: it may be refilled (generic-proxy accesses ordered before the copy)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();

@@ -168,13 +168,18 @@ struct FrontArgs {
     void* u;               // [S][u_stride] complex<float>, row-major [row][rank_pad]
     long long u_stride;    // complex elements, even
     int tiles_per_warp;    // set by the launcher
+    // optional: the mixed samples at push offsets >= hist_from also go to hist_out[s][offset - hist_from]
+    // (the Filter's next history, [S][hist_stride]), for every offset inside the rows this launch covers
+    void* hist_out;
+    long long hist_from, hist_stride;
 };
 bool front_supported(int rank_pad, long long P);
 cudaError_t launch_front(int rank_pad, int n_streams, const FrontArgs& a, cudaStream_t st);
 
-// new hist2 = last 2n post-NCO samples of [hist2_in | in]
+// new hist2 = last 2n post-NCO samples of [hist2_in | in]; j_lo > 0: only entries [j_lo, 2n) (the rest was
+// written by k_front)
 template <typename T>
 cudaError_t launch_hist2_update(const void* in, long long in_stride, long long len, const void* hist2_in, void* hist2_out,
-                                long long n, const NcoStream* nco, int n_streams, cudaStream_t st);
+                                long long n, const NcoStream* nco, int n_streams, cudaStream_t st, long long j_lo = 0);
 
 }  // namespace rr
