@@ -361,8 +361,12 @@ __global__ void __launch_bounds__(2 * P2Cfg<G>::THREADS, 1) k_poly2(const __grid
                 } else {
                     // thread-local loads (all issued first, predicated); history samples are already mixed:
                     // for them only the row part that the twiddles will apply is cancelled
-                    const int p = r * G + g;
-                    const int pos0 = boff + t * Pd + p;
+                    // (the offsets are made opaque so that the compiler does not carry 32 induction variables of
+                    // this rarely taken branch through the round loop)
+                    int r_o = r, boff_o = boff;
+                    asm volatile("" : "+r"(r_o), "+r"(boff_o));
+                    const int p = r_o * G + g;
+                    const int pos0 = boff_o + t * Pd + p;
                     const int step = 16 * Pd;
                     const unsigned span = (unsigned)(len + hist_len);
 #pragma unroll
