@@ -137,6 +137,15 @@ int rr_design_downsampler_taps(double input_rate, double output_rate, double ban
 int rr_design_upsampler_taps(double input_rate, double output_rate, double bandwidth, double quality,
                              size_t* ir_len, double* ir);   /* resampling.rs:205-233 */
 
+/* Diagnostic of the rank-reduced form of Filter -> Downsampler (integer decimation): the P x (Lmax+1)
+ * matrix of the fused filter g = taps(filters.rs:184-238) * reversed taps(resampling.rs:82-101) is
+ * factored as sum_c a_c b_c^T; *rank = smallest count whose discarded part is <= tol * |M|_F (0 if that
+ * needs more than max_rank), *discarded = that part, *table_error = relative L2 distance between the
+ * factorisation and the full polyphase tables (K = 512). */
+int rr_design_fused_rank(rr_freq_resp_fn f, void* f_user, int32_t window_kind, double window_beta, rr_window_fn w, void* w_user,
+                         double sample_rate, size_t n, double output_rate, double bandwidth, double quality, double tol,
+                         int max_rank, int* rank, double* discarded, double* table_error);
+
 /* ---- chain ----------------------------------------------------------------- */
 int rr_chain_create(rr_ctx* ctx, const rr_chain_desc* desc, rr_chain** out);
 int rr_chain_destroy(rr_chain* chain);
@@ -184,10 +193,12 @@ int rr_chain_push_device(rr_chain* chain, double sample_rate, size_t chunk_len, 
                          size_t in_stride, void* dev_out, size_t out_capacity, size_t out_stride, size_t* out_count,
                          double* out_sample_rate);
 int rr_chain_sync(rr_chain* chain);
-/* The polyphase fused Filter -> Downsampler kernel is used whenever the chain
- * allows it; enable = 0 forces the stateful overlap-save path (same results
- * within rounding; for tests and comparisons).  Env RR_DISABLE_POLY=1 sets the
- * default to off. */
+/* The fused Filter -> Downsampler kernels (rank-reduced front end + low-rate
+ * polyphase part, or the polyphase kernels on all P branches) are used whenever
+ * the chain allows it; enable = 0 forces the stateful overlap-save path (same
+ * results within rounding; for tests and comparisons).  Env RR_DISABLE_POLY=1
+ * sets the default to off; RR_DISABLE_FRONT=1 / RR_DISABLE_POLY2=1 step back to
+ * k_poly2 on all branches / to k_poly. */
 int rr_chain_set_fast_path(rr_chain* chain, int enable);
 /* Measurement aid: while enabled, CUDA events on the chain's stream bracket the
  * dominant kernel of every push (no synchronisation is added).

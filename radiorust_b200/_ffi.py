@@ -85,6 +85,8 @@ SIGNATURES = {
     "rr_design_filter_response": (_I, [FREQ_RESP_FN, _P, C.c_int32, _D, WINDOW_FN, _P, _D, _SZ, C.c_int32, C.POINTER(_D)]),
     "rr_design_downsampler_taps": (_I, [_D, _D, _D, _D, C.POINTER(_SZ), C.POINTER(_D)]),
     "rr_design_upsampler_taps": (_I, [_D, _D, _D, _D, C.POINTER(_SZ), C.POINTER(_D)]),
+    "rr_design_fused_rank": (_I, [FREQ_RESP_FN, _P, C.c_int32, _D, WINDOW_FN, _P, _D, _SZ, _D, _D, _D, _D, _I,
+                                  C.POINTER(_I), C.POINTER(_D), C.POINTER(_D)]),
     "rr_chain_create": (_I, [_P, C.POINTER(ChainDesc), C.POINTER(_P)]),
     "rr_chain_destroy": (_I, [_P]),
     "rr_chain_set_shift": (_I, [_P, _I, _I, _D]),

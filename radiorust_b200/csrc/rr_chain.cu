@@ -1391,6 +1391,56 @@ int rr_design_upsampler_taps(double input_rate, double output_rate, double bandw
     return design_taps(false, input_rate, output_rate, bandwidth, quality, ir_len, ir);
 }
 
+// Rank of the fused Filter -> Downsampler filter for integer decimation (rr_design.h: design_rank_tables),
+// the part it discards, and how far sum_c a_c b_c^T is from the full polyphase tables (relative L2 over
+// all P*K table entries) -- the last one is the check that the factorisation is exact to rounding.
+int rr_design_fused_rank(rr_freq_resp_fn f, void* f_user, int32_t window_kind, double window_beta, rr_window_fn w, void* w_user,
+                         double sample_rate, size_t n, double output_rate, double bandwidth, double quality, double tol, int max_rank,
+                         int* rank, double* discarded, double* table_error) {
+    if (!f || !rank) return fail(RR_ERR_INVALID, "rr_design_fused_rank: null argument");
+    if (max_rank < 1 || max_rank > 64) return fail(RR_ERR_INVALID, "rr_design_fused_rank: max_rank out of range");
+    rr::FreqResp fr = [f, f_user](int64_t bin, double freq) {
+        double re = 0.0, im = 0.0;
+        f(f_user, bin, freq, &re, &im);
+        return std::complex<double>(re, im);
+    };
+    std::vector<std::complex<double>> resp, taps;
+    if (!rr::design_filter_response(fr, make_window(window_kind, window_beta, w, w_user), sample_rate, n, true, &resp, &taps))
+        return fail(RR_ERR_INVALID, "rr_design_fused_rank: chunk length must be a power of two >= 2");
+    if (!integer_valued(sample_rate) || !integer_valued(output_rate) || output_rate <= 0.0 || sample_rate < output_rate)
+        return fail(RR_ERR_INVALID, "rr_design_fused_rank: rates must be integer valued, input >= output > 0");
+    const long long g = std::gcd((long long)sample_rate, (long long)output_rate);
+    const long long P = (long long)sample_rate / g, Q = (long long)output_rate / g;
+    if (Q != 1) return fail(RR_ERR_UNSUPPORTED, "rr_design_fused_rank: integer decimation only");
+    size_t L = 0;
+    RR_TRY(design_taps(true, sample_rate, output_rate, bandwidth, quality, &L, nullptr));
+    std::vector<double> ir(L);
+    RR_TRY(design_taps(true, sample_rate, output_rate, bandwidth, quality, &L, ir.data()));
+    for (auto& v : ir) v = (double)(float)v;
+    const int K = 512;
+    std::vector<double> a;
+    std::vector<std::complex<double>> b, full;
+    double disc = 0.0;
+    const int lmax = rr::design_rank_tables(taps, ir, P, K, tol, max_rank, rank, &a, &b, &disc);
+    if (discarded) *discarded = disc;
+    if (table_error) {
+        *table_error = -1.0;
+        if (*rank > 0 && lmax + 1 < K) {
+            rr::design_poly_tables(taps, ir, P, 1, K, &full);
+            double num = 0.0, den = 0.0;
+            for (long long p = 0; p < P; ++p)
+                for (int k = 0; k < K; ++k) {
+                    std::complex<double> sum(0.0, 0.0);
+                    for (int c = 0; c < *rank; ++c) sum += a[(size_t)p * max_rank + c] * b[(size_t)c * K + k];
+                    num += std::norm(sum - full[(size_t)p * K + k]);
+                    den += std::norm(full[(size_t)p * K + k]);
+                }
+            *table_error = den > 0.0 ? std::sqrt(num / den) : 0.0;
+        }
+    }
+    return RR_OK;
+}
+
 // ---- chain ---------------------------------------------------------------------
 int rr_chain_create(rr_ctx* ctx, const rr_chain_desc* desc, rr_chain** out) {
     if (!ctx || !desc || !out) return fail(RR_ERR_INVALID, "rr_chain_create: null argument");

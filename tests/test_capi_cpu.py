@@ -110,3 +110,64 @@ def test_design_argument_errors(lib):
     d = C.c_int64()
     assert lib.rr_freq_to_ratio(1.0, 10.0, 0.1, C.byref(d), C.byref(d)) == _ffi.RR_ERR_INVALID  # denominator rounds to 0
     assert lib.rr_last_error()
+
+
+# ---------------------------------------------------------------------------
+# rank-reduced form of Filter -> Downsampler (k_front + k_poly2): the factorisation of the fused filter
+# must reproduce the full polyphase tables to below f32 rounding, with the rank the kernels are built for
+# ---------------------------------------------------------------------------
+def _fused_rank(lib, resp, sr, n, out_rate, bw, tol, max_rank, window=("kaiser", math.sqrt(3.0))):
+    cb = _ffi.FREQ_RESP_FN(lambda u, b, f, re, im: (re.__setitem__(0, complex(resp(b, f)).real), im.__setitem__(0, complex(resp(b, f)).imag)) and None)
+    rank, disc, err = C.c_int(0), C.c_double(0.0), C.c_double(0.0)
+    kind = _ffi.RR_WINDOW_KAISER if window[0] == "kaiser" else _ffi.RR_WINDOW_RECTANGULAR
+    rc = lib.rr_design_fused_rank(cb, None, kind, window[1], _ffi.WINDOW_FN(), None, sr, n, out_rate, bw, 3.0, tol, max_rank,
+                                  C.byref(rank), C.byref(disc), C.byref(err))
+    return rc, rank.value, disc.value, err.value
+
+
+@pytest.mark.parametrize("sr,n,cut,out_rate,bw", [
+    (2_400_000.0, 4096, 3000.0, 48000.0, 6000.0),     # C3 (the benchmarked configuration): P = 50
+    (1_440_000.0, 4096, 3000.0, 48000.0, 6000.0),     # P = 30
+    (480_000.0, 2048, 8000.0, 48000.0, 20000.0),      # P = 10
+    (960_000.0, 2048, 10000.0, 48000.0, 20000.0),     # P = 20 (k_poly2 on all branches; the rank is still low)
+])
+def test_fused_filter_rank_is_low_and_exact(lib, sr, n, cut, out_rate, bw):
+    rc, rank, disc, err = _fused_rank(lib, orc.lowpass(cut), sr, n, out_rate, bw, 2.0e-8, 10)
+    assert rc == 0
+    assert 1 <= rank <= 10, rank
+    assert disc <= 2.0e-8
+    assert 0.0 <= err <= 2.5e-8, err  # sum_c a_c b_c^T == the full [P][K] tables to below f32 rounding
+
+
+def test_fused_filter_rank_numpy_cross_check(lib):
+    """The same rank out of numpy's SVD of M[p][l] = g[P-1-p+l*P] built from the oracle's designs."""
+    sr, n, P = 2_400_000.0, 4096, 50
+    H = orc.design_filter_response(orc.lowpass(3000.0), orc.Kaiser.with_null_at_bin(2.0), sr, n, "f32").astype(np.complex128)
+    h = np.fft.ifft(H)[n:]
+    ds = orc.Downsampler("f32", 1, 48000.0, 6000.0, 3.0)
+    ds._design(sr)
+    g = np.convolve(h, np.asarray(ds.ir, dtype=np.float64)[::-1])
+    lmax = (len(g) - 1) // P
+    M = np.zeros((P, lmax + 1), dtype=np.complex128)
+    for p in range(P):
+        idx = P - 1 - p + P * np.arange(lmax + 1)
+        ok = idx < len(g)
+        M[p, ok] = g[idx[ok]]
+    sv = np.linalg.svd(M, compute_uv=False)
+    tail = np.sqrt(np.cumsum((sv ** 2)[::-1])[::-1] / np.sum(sv ** 2))
+    want = int(np.argmax(tail <= 2.0e-8))
+    rc, rank, disc, err = _fused_rank(lib, orc.lowpass(3000.0), sr, n, 48000.0, 6000.0, 2.0e-8, 16)
+    assert rc == 0 and rank == want, (rank, want)
+    assert disc == pytest.approx(float(tail[want]), rel=0.05)
+
+
+def test_fused_filter_rank_gives_up_on_wideband_filters(lib):
+    """An all-pass Filter leaves only the Downsampler's taps: more branches stay independent and the front
+    end must not be chosen with too small a rank (rank = 0 -> the chain falls back to k_poly2 / k_poly)."""
+    rc, rank, disc, err = _fused_rank(lib, lambda b, f: 1.0, 2_400_000.0, 4096, 48000.0, 6000.0, 2.0e-8, 4)
+    assert rc == 0 and rank == 0
+    rc, rank, disc, err = _fused_rank(lib, lambda b, f: 1.0, 2_400_000.0, 4096, 240000.0, 100000.0, 2.0e-8, 64)
+    assert rc == 0 and (rank == 0 or err <= 2.5e-8)
+    # contract violations
+    assert _fused_rank(lib, orc.lowpass(3000.0), 1_024_000.0, 4096, 48000.0, 6000.0, 2.0e-8, 10)[0] == _ffi.RR_ERR_UNSUPPORTED  # 64/3
+    assert _fused_rank(lib, orc.lowpass(3000.0), 2_400_000.0, 4000, 48000.0, 6000.0, 2.0e-8, 10)[0] == _ffi.RR_ERR_INVALID
