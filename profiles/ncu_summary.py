@@ -19,9 +19,18 @@ def main():
     rep = sys.argv[1]
     samples = float(sys.argv[2]) if len(sys.argv) > 2 else None
     rows = page(rep, "raw")
-    hdr, units, r = rows[0], rows[1], rows[2]
-    d = dict(zip(hdr, r))
-    u = dict(zip(hdr, units))
+    hdr, units = rows[0], rows[1]
+    src = page(rep, "source")
+    starts = [i for i, r in enumerate(src) if r and r[0] == "Kernel Name"]
+    for ki, r in enumerate(rows[2:]):
+        if ki:
+            print()
+        lo = starts[ki] if ki < len(starts) else None
+        hi = starts[ki + 1] if lo is not None and ki + 1 < len(starts) else len(src)
+        one(dict(zip(hdr, r)), dict(zip(hdr, units)), src[lo:hi] if lo is not None else None, samples)
+
+
+def one(d, u, src, samples):
     keys = [
         "Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
         "launch__shared_mem_per_block", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
@@ -31,7 +40,8 @@ def main():
         "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
         "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
-        "dram__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum.per_second", "lts__t_bytes.sum",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "smsp__thread_inst_executed_per_inst_executed.ratio",
     ]
     for k in keys:
@@ -41,7 +51,8 @@ def main():
     st = [(float(v), h) for h, v in d.items() if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio") and v not in ("", "n/a")]
     for v, h in sorted(st, reverse=True)[:10]:
         print(f"   {h[len('smsp__average_warps_issue_stalled_'):-len('_per_issue_active.ratio')]:28s} {v:6.2f}")
-    src = page(rep, "source")
+    if not src:
+        return
     sh = src[1]
     iS, iE = sh.index("Source"), sh.index("Instructions Executed")
     ops = collections.Counter()
