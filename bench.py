@@ -39,6 +39,11 @@ METRIC = "complex MS/s via FreqShift->Filter->Downsampler"
 UNIT = "MS/s"
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from the `ncu --set full`
+# capture of this very command (profiles/r01_ncu_k_front_k_poly2.txt), keyed by (kernel, streams, chunks)
+NCU_TRAFFIC = {("k_front", 4096, 50): 6.860079e9 + 1.619953e9}
+
+
 def stream_shift(stream_id: int) -> float:
     """SURVEY.md 8(d), config C3."""
     return float((stream_id * 577) % 2_400_000 - 1_200_000)
@@ -155,7 +160,7 @@ def run_reference(args):
     cores = host_cores()
     vals = []
     for i in range(args.warmup + args.steps):
-        v, dt, desc = cpu_chain_run(cores, 4, 400)
+        v, dt, desc = cpu_chain_run(cores, 8, 1000)
         if i >= args.warmup:
             vals.append((v, dt))
     value = float(np.mean([v for v, _ in vals]))
@@ -318,17 +323,19 @@ def run_cuda(args):
         "gpu_launches": int(launches),
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-            "traffic": args.traffic, "peak_kind": peak_kind, "kernel": k_name, "kernel_ms": k_avg_ms, "kernel_launches": k_n,
+            "traffic": args.traffic if args.traffic is not None else NCU_TRAFFIC.get((k_name, S, C)), "peak_kind": peak_kind, "kernel": k_name, "kernel_ms": k_avg_ms, "kernel_launches": k_n,
             "algorithmic_bytes_per_launch": samples_step * BYTES_PER_SAMPLE,
             "kernel_share_of_step": (k_ms / elapsed_ms) if elapsed_ms else None,
             "kernels": {nm: {"ms_per_launch": ms / max(n, 1), "launches": n, "share_of_step": ms / elapsed_ms}
                         for nm, (ms, n) in k_all.items()},
+            # the same algorithmic bytes over the whole step (all kernels of a push), for comparison
+            "step_achieved": value * 1e6 * BYTES_PER_SAMPLE / world / 1e9, "step_frac": value * 1e6 * BYTES_PER_SAMPLE / world / 1e9 / peak,
         },
         "output_samples_per_step": out_total // max(args.steps, 1),
     }
     if world == 1 and not args.no_cpu:
         cores = host_cores()
-        v, dt, desc = cpu_chain_run(cores, 4, 400)
+        v, dt, desc = cpu_chain_run(cores, 8, 1000)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc, "seconds": dt}
     print(json.dumps(line), flush=True)
     if dist is not None:
