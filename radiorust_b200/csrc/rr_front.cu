@@ -54,11 +54,21 @@ __global__ void __launch_bounds__(FR_WARPS * 32) k_front(const __grid_constant__
     const int s = blockIdx.y;
     const int P = a.P;
     const int steps = P / 2;
+    // tile row pitch in samples: P, or P + 2 when P/2 is even (an odd number of 16-byte units per row keeps the
+    // lanes' 16-byte loads conflict free); the two extra samples of a row are never used
+    const int pitch = P + ((P & 3) == 0 ? 2 : 0);
     // column pairs of this lane: [st0, st1)
-    const int st0 = hh ? steps / 2 : 0, st1 = hh ? steps : steps / 2;
+    // The split point: with an odd number of 16-byte units per row the 8 lanes of a quarter warp (4 rows x
+    // 2 halves) hit 8 distinct bank groups when the halves start 4 (mod 8) units apart.
+    int split = steps / 2;
+    if (steps >= 20) {
+        for (int d = -1; d <= 1; ++d)
+            if (((steps / 2 + d) & 7) == 4) split = steps / 2 + d;
+    }
+    const int st0 = hh ? split : 0, st1 = hh ? steps : split;
 
     extern __shared__ __align__(128) unsigned char smem[];
-    const int tile_bytes = FR_ROWS * P * 8;
+    const int tile_bytes = FR_ROWS * pitch * 8;
     const int tile_stride = (tile_bytes + 127) / 128 * 128;
     unsigned char* tiles = smem + warp * (FR_STAGES * tile_stride);          // this warp's ring of tiles
     float* coef = reinterpret_cast<float*>(smem + FR_WARPS * FR_STAGES * tile_stride);  // [steps][2][RK]
@@ -108,7 +118,7 @@ __global__ void __launch_bounds__(FR_WARPS * 32) k_front(const __grid_constant__
     const int tile0 = (blockIdx.x * FR_WARPS + warp) * a.tiles_per_warp;
     const int n_tiles = min(a.tiles_per_warp, (a.n_rows - tile0 * FR_ROWS + FR_ROWS - 1) / FR_ROWS);  // may be <= 0
     auto tile_pos0 = [&](int k) -> long long { return ((long long)a.row_first + (long long)(tile0 + k) * FR_ROWS) * P - a.J0; };
-    auto tile_interior = [&](long long pos0) -> bool { return pos0 >= 0 && pos0 + (long long)FR_ROWS * P <= len; };
+    auto tile_interior = [&](long long pos0) -> bool { return pos0 >= 0 && pos0 + (long long)(FR_ROWS - 1) * P + pitch <= len; };
     // start the TMA copy of tile k into ring slot k % FR_STAGES (interior tiles only)
     auto issue = [&](int k) {
         if (k >= n_tiles) return;
@@ -186,6 +196,7 @@ __global__ void __launch_bounds__(FR_WARPS * 32) k_front(const __grid_constant__
                     const int e = e0 + 32 * j;
                     const int er = e < FR_ROWS * P ? e : 0;
                     const int rr_ = er / P, p = er - rr_ * P;
+                    const int de = rr_ * pitch + p;  // position in the (possibly padded) tile
                     if (HAS_NCO) {
                         const float rx = __shfl_sync(0xffffffffu, rowph.x, 2 * rr_), ry = __shfl_sync(0xffffffffu, rowph.y, 2 * rr_);
                         if (pos0 + e < 0) {
@@ -195,7 +206,7 @@ __global__ void __launch_bounds__(FR_WARPS * 32) k_front(const __grid_constant__
                             q[j] = make_float2(y.x, y.y);
                         }
                     }
-                    if (e < FR_ROWS * P) dst[e] = q[j];
+                    if (e < FR_ROWS * P) dst[de] = q[j];
                 }
             }
             __syncwarp();
@@ -203,7 +214,7 @@ __global__ void __launch_bounds__(FR_WARPS * 32) k_front(const __grid_constant__
         pc acc[RK];
 #pragma unroll
         for (int c = 0; c < RK; ++c) acc[c] = pc(0.f, 0.f);
-        const uint32_t row_s = tile_s + row * (P * 8);
+        const uint32_t row_s = tile_s + row * (pitch * 8);
         const long long prow = pos0 + (long long)row * P;  // push offset of this lane's row
         const bool row_ok = v0 + row < a.n_rows;
         auto run_row = [&](auto write_hist) {
@@ -295,8 +306,9 @@ EncodeFn front_encode_fn() {
 }  // namespace
 
 bool front_supported(int rank_pad, long long P) {
-    // lane = row needs P/2 odd (conflict-free 16-byte loads at a pitch of P*8 bytes); one TMA box per tile
-    return rank_pad == 10 && P >= 2 && P <= 256 && (P % 4) == 2 && front_encode_fn() != nullptr;
+    // even P (TMA rows are 16-byte multiples; the tile pitch is padded to an odd number of 16-byte units); one TMA
+    // box per tile
+    return rank_pad == 10 && P >= 2 && P <= 254 && (P % 2) == 0 && front_encode_fn() != nullptr;
 }
 
 cudaError_t launch_front(int rank_pad, int n_streams, const FrontArgs& a0, cudaStream_t st) {
@@ -314,12 +326,13 @@ cudaError_t launch_front(int rank_pad, int n_streams, const FrontArgs& a0, cudaS
     const cuuint64_t dims[3] = {(cuuint64_t)a.len, (cuuint64_t)FR_ROWS, (cuuint64_t)n_streams};
     const cuuint64_t sstride = n_streams > 1 ? (cuuint64_t)a.in_stride * 8 : (((cuuint64_t)a.len * 8 + 15) / 16) * 16;
     const cuuint64_t strides[2] = {(cuuint64_t)a.P * 8, sstride};
-    const cuuint32_t box[3] = {(cuuint32_t)a.P, (cuuint32_t)FR_ROWS, 1};
+    const int pitch = a.P + ((a.P & 3) == 0 ? 2 : 0);
+    const cuuint32_t box[3] = {(cuuint32_t)pitch, (cuuint32_t)FR_ROWS, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void*>(a.in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
-    const int tile_stride = (FR_ROWS * a.P * 8 + 127) / 128 * 128;
+    const int tile_stride = (FR_ROWS * pitch * 8 + 127) / 128 * 128;
     const size_t smem = (size_t)FR_WARPS * FR_STAGES * tile_stride + (size_t)(a.P / 2) * 2 * 10 * 4 + (size_t)a.P * 8 + FR_WARPS * FR_STAGES * 8 + 16;
     const dim3 grid((unsigned)((tiles + FR_WARPS * a.tiles_per_warp - 1) / (FR_WARPS * a.tiles_per_warp)), (unsigned)n_streams);
     cudaError_t e;

@@ -130,7 +130,9 @@ def _fused_rank(lib, resp, sr, n, out_rate, bw, tol, max_rank, window=("kaiser",
     (1_440_000.0, 4096, 3000.0, 48000.0, 6000.0),     # P = 30
     (480_000.0, 1024, 8000.0, 48000.0, 20000.0),      # P = 10
     (3_360_000.0, 4096, 3000.0, 48000.0, 6000.0),     # P = 70
-    (960_000.0, 2048, 10000.0, 48000.0, 20000.0),     # P = 20 (k_poly2 on all branches; the rank is still low)
+    (960_000.0, 2048, 10000.0, 48000.0, 20000.0),     # P = 20
+    (3_072_000.0, 4096, 3000.0, 48000.0, 6000.0),     # P = 64
+    (4_800_000.0, 4096, 3000.0, 48000.0, 6000.0),     # P = 100
 ])
 def test_fused_filter_rank_is_low_and_exact(lib, sr, n, cut, out_rate, bw):
     rc, rank, disc, err = _fused_rank(lib, orc.lowpass(cut), sr, n, out_rate, bw, 2.0e-8, 10)

@@ -66,6 +66,9 @@ def gpu_chain(ctx, shifts, cutoff, ocl, out_rate, bw, sr, x, n, pushes, with_nco
     (1_440_000.0, 4096, 3000.0, 48000.0, 6000.0, 100, 30),
     (480_000.0, 1024, 8000.0, 48000.0, 20000.0, 17, 10),      # odd output chunking
     (3_360_000.0, 4096, 3000.0, 48000.0, 6000.0, 256, 70),
+    (960_000.0, 2048, 10000.0, 48000.0, 20000.0, 17, 20),     # P = 0 (mod 4): padded tile pitch
+    (3_072_000.0, 4096, 3000.0, 48000.0, 6000.0, 64, 64),
+    (4_800_000.0, 4096, 3000.0, 48000.0, 6000.0, 1024, 100),
 ])
 def test_front_path_rates(ctx, sr, n, cutoff, out_rate, bw, ocl, P):
     S = 3
