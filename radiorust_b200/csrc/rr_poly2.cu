@@ -208,16 +208,26 @@ __global__ void __launch_bounds__(2 * P2Cfg<G>::THREADS, 1) k_poly2(const __grid
     auto block_shift = [&](int blk) -> int { return blk == a.n_blocks - 1 ? last_shift : 0; };
     auto block_off = [&](int blk) -> int { return boff0 + blk * bstep - block_shift(blk) * Pd; };
     auto is_interior = [&](int boff) -> bool { return boff >= 0 && boff + need <= len; };
-    // the tile of round Rg of the group that starts at block blk_first (nothing for edge blocks)
-    auto issue_tile = [&](int blk_first, int blk_end, int Rg) {
+    // the tile of round Rg of the group of stream `ss` that starts at block blk_first (nothing for edge blocks)
+    auto issue_tile = [&](int ss, int blk_first, int blk_end, int Rg) {
         const int blk = blk_first + Rg / NR;
         if (blk >= blk_end) return;
         const int boff = block_off(blk);
         if (!is_interior(boff)) return;
         const int stage = Rg & 1;
         const uint32_t bar = bar_full + stage * 8;
+        const uint32_t dst = sbase + C::OFF_STAGE + stage * C::STAGE_BYTES;
         mbar_expect_tx(bar, C::TILE_BYTES);
-        tma_load_4d(sbase + C::OFF_STAGE + stage * C::STAGE_BYTES, &tmap, bar, boff + (Rg % NR) * G, 0, 0, s);
+        if (SINGLE && Pd == G) {
+            // P == G: the K rows of the tile are one contiguous run of the stream (16-byte aligned: boff is a
+            // multiple of G = 10 samples, the stream stride is even)
+            const float2* src = reinterpret_cast<const float2*>(a.in) + (long long)ss * a.in_stride + boff;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                         "r"((uint32_t)C::TILE_BYTES), "r"(bar)
+                         : "memory");
+        } else {
+            tma_load_4d(dst, &tmap, bar, boff + (Rg % NR) * G, 0, 0, ss);
+        }
     };
 
     const uint32_t e_tab = sbase + C::OFF_E;
@@ -232,7 +242,26 @@ __global__ void __launch_bounds__(2 * P2Cfg<G>::THREADS, 1) k_poly2(const __grid
     const float4* __restrict__ gtab = reinterpret_cast<const float4*>(a.gtab);
     uint32_t phase = 0;  // bit `stage`: parity of the next TMA completion to wait for
 
-    for (; s < n_streams; s += s_step) {
+    // work units of this half: (stream, group of nbpc blocks), streams s_first, s_first + s_step, ...
+    const int n_units = ((n_streams - s_first + s_step - 1) / s_step) * a.ngrp;
+    auto unit_blocks = [&](int u, int* b0, int* b1) {
+        *b0 = (blockIdx.x * a.ngrp + (u % a.ngrp)) * a.nbpc;
+        *b1 = min(*b0 + a.nbpc, a.n_blocks);
+    };
+    // next unit after u that has blocks (n_units if none)
+    auto next_unit = [&](int u) -> int {
+        for (int v = u + 1; v < n_units; ++v) {
+            int b0, b1;
+            unit_blocks(v, &b0, &b1);
+            if (b0 < b1) return v;
+        }
+        return n_units;
+    };
+    bool prefetched = false;  // (thread 0) the first two tiles of the current unit are already on their way
+
+    for (int u = next_unit(-1); u < n_units; u = next_unit(u)) {
+    s = s_first + (u / a.ngrp) * s_step;
+    const bool new_stream = (u % a.ngrp) == 0 || u == next_unit(-1);
     const float2* __restrict__ in = reinterpret_cast<const float2*>(a.in) + (long long)s * a.in_stride;
     const float2* __restrict__ hist_end = reinterpret_cast<const float2*>(a.hist2) + ((long long)s + 1) * 2 * a.n;
     float2* __restrict__ out = reinterpret_cast<float2*>(a.out) + (long long)s * a.out_stride;
@@ -250,7 +279,7 @@ __global__ void __launch_bounds__(2 * P2Cfg<G>::THREADS, 1) k_poly2(const __grid
         idx0 = ns.idx;
         start = (float)ns.start_phase;
     }
-    if (HAS_NCO || s == s_first) {  // the tables depend on the stream only through its NCO
+    if ((HAS_NCO && new_stream) || u == next_unit(-1)) {  // the tables depend on the stream only through its NCO
         float2* et = reinterpret_cast<float2*>(smem + C::OFF_E);  // E[32] | rowph[16] | rotG
         if (tid < 49) {
             cx<float> r(1.f, 0.f);
@@ -258,7 +287,7 @@ __global__ void __launch_bounds__(2 * P2Cfg<G>::THREADS, 1) k_poly2(const __grid
             if (HAS_NCO) r = nco_rotation<float>(d, numer_abs, denom, sign);
             et[tid] = make_float2(r.x, r.y);
         }
-        if (tid == 64 && s == s_first) {
+        if (tid == 64 && u == next_unit(-1)) {
             mbar_init(bar_full, 1);
             mbar_init(bar_full + 8, 1);
             *reinterpret_cast<uint2*>(smem + C::OFF_BAR + 16) = make_uint2(0u, 0u);
@@ -284,8 +313,8 @@ __global__ void __launch_bounds__(2 * P2Cfg<G>::THREADS, 1) k_poly2(const __grid
             }
         }
         sync_half();
-        rotG = lds_pc(e_tab + 48 * 8);
     }
+    if (HAS_NCO) rotG = lds_pc(e_tab + 48 * 8);
     const pc rowph = lds_pc(e_tab + (32 + t) * 8);
     // this lane's two entries of the E table (it maintains entries 2t, 2t+1 of its column's E*c_p)
     pc e_mine0(1.f, 0.f), e_mine1(1.f, 0.f);
@@ -300,17 +329,16 @@ __global__ void __launch_bounds__(2 * P2Cfg<G>::THREADS, 1) k_poly2(const __grid
         __syncwarp();
         if (lane == 0) {
             const uint32_t old = atom_add_acqrel_shared(cnt_rel + (R & 1) * 4, 1u);
-            if (old % C::NCW == C::NCW - 1) issue_tile(gb0, gb1, R + 2);
+            if (old % C::NCW == C::NCW - 1) issue_tile(s, gb0, gb1, R + 2);
         }
     };
 
-    for (int grp = 0; grp < a.ngrp; ++grp) {
-        const int blk0 = (blockIdx.x * a.ngrp + grp) * a.nbpc;
-        const int blk1 = min(blk0 + a.nbpc, a.n_blocks);
-        if (blk0 >= blk1) break;
-        if (tid == 0) {
-            issue_tile(blk0, blk1, 0);
-            issue_tile(blk0, blk1, 1);
+    {
+        int blk0, blk1;
+        unit_blocks(u, &blk0, &blk1);
+        if (tid == 0 && !prefetched) {
+            issue_tile(s, blk0, blk1, 0);
+            issue_tile(s, blk0, blk1, 1);
         }
         int R = 0;  // rounds of this group
 
@@ -468,6 +496,16 @@ __global__ void __launch_bounds__(2 * P2Cfg<G>::THREADS, 1) k_poly2(const __grid
             }
         }
         sync_half();
+        // both stages are free now: the next unit's first tile goes into stage 0 while the inverse transforms
+        // exchange through stage 1
+        const int u_next = next_unit(u);
+        int nb0 = 0, nb1 = 0;
+        if (u_next < n_units) unit_blocks(u_next, &nb0, &nb1);
+        const int s_next = s_first + (u_next / a.ngrp) * s_step;
+        if (tid == 0) {
+            prefetched = u_next < n_units;
+            if (prefetched) issue_tile(s_next, nb0, nb1, 0);
+        }
 
         // ---- inverse transforms: branch column g takes job g (one parked block spectrum) -------------
         const int njobs = blk1 - blk0;
@@ -475,7 +513,7 @@ __global__ void __launch_bounds__(2 * P2Cfg<G>::THREADS, 1) k_poly2(const __grid
             if (j0 + 2 * warp >= njobs) continue;  // neither column of this warp has a job (warp-uniform)
             const int job = j0 + g;
             const bool active = job < njobs;
-            const uint32_t stg = sbase + C::OFF_STAGE;
+            const uint32_t stg = sbase + C::OFF_STAGE + C::STAGE_BYTES;
             pc v[32];
             const float2* ys = ysave + (active ? job : 0) * C::YS_STRIDE;
             // conj in, conj out = inverse transform; the table's NCO row part is cancelled on the way in
@@ -509,11 +547,12 @@ __global__ void __launch_bounds__(2 * P2Cfg<G>::THREADS, 1) k_poly2(const __grid
             }
             __syncwarp();
         }
-        // the next group's first tiles go into the stages the inverse just used
+        // the next unit's second tile goes into the stage the inverse just used
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         sync_half();
+        if (tid == 0 && prefetched) issue_tile(s_next, nb0, nb1, 1);
     }
-    }  // streams
+    }  // units
 }
 
 // ---------------------------------------------------------------------------
