@@ -176,3 +176,22 @@ def test_front_full_chunk_structure_properties(ctx):
     assert orc.rel_l2(got[2], lin) < 5e-6                      # linearity
     want = oracle_chain(123457.0, 3000.0, 2048, 48000.0, 6000.0, sr, x[0], n)
     assert orc.rel_l2(got[0], want) <= TOL
+
+
+def test_front_runs_are_bit_reproducible(ctx):
+    """Two fresh chains on the same input give bit-identical outputs (no atomics in the arithmetic, no
+    order-dependent reductions): a cheap detector of shared-memory races in the warp-autonomous kernels.
+    An odd number of streams leaves one CTA half of k_poly2 idle; 37 streams walk several persistent halves."""
+    sr, n, S = 2_400_000.0, 4096, 37
+    pushes = [26, 3, 31]
+    x = np.stack([orc.synth_noise(9000 + s, sum(pushes) * n, "f32") for s in range(S)])
+    shifts = [float((s * 577) % 2_400_000 - 1_200_000) for s in range(S)]   # SURVEY.md 8(d), config C3
+    args = (shifts, 3000.0, 2048, 48000.0, 6000.0, sr, x, n, pushes)
+    a, pa = gpu_chain(ctx, *args)
+    for _ in range(3):
+        b, _ = gpu_chain(ctx, *args)
+        assert np.array_equal(a, b)
+    assert any("front+poly2" in p for p in pa)
+    for s in (0, 17, 36):
+        want = oracle_chain(shifts[s], 3000.0, 2048, 48000.0, 6000.0, sr, x[s], n)
+        assert orc.rel_l2(a[s], want) <= TOL
