@@ -30,7 +30,7 @@ extern "C" {
 #endif
 
 #define RR_VERSION_MAJOR 0
-#define RR_VERSION_MINOR 1
+#define RR_VERSION_MINOR 2
 
 typedef struct rr_ctx rr_ctx;
 typedef struct rr_chain rr_chain;
@@ -53,7 +53,8 @@ typedef enum rr_stage_kind {
     RR_STAGE_DOWNSAMPLE = 3, /* blocks::Downsampler   src/blocks/resampling.rs:14-146 */
     RR_STAGE_UPSAMPLE = 4,   /* blocks::Upsampler     src/blocks/resampling.rs:149-280 */
     RR_STAGE_FMDEMOD = 5,    /* blocks::modulation::FmDemod src/blocks/modulation.rs:83-158 */
-    RR_STAGE_GAIN = 6        /* blocks::GainControl   src/blocks/transform.rs:29-92 */
+    RR_STAGE_GAIN = 6,       /* blocks::GainControl   src/blocks/transform.rs:29-92 */
+    RR_STAGE_FOURIER = 7     /* blocks::analysis::Fourier src/blocks/analysis.rs:15-132 */
 } rr_stage_kind;
 
 typedef enum rr_window_kind {
@@ -89,6 +90,11 @@ typedef struct rr_stage_desc {
     double deviation;
     /* GAIN: GainControl::new(gain) */
     double gain;
+    /* FOURIER: Fourier::with_window(window) / with_window_center_dc(window) (analysis.rs:38-59): window_kind,
+     * window_beta, window_fn as for FILTER (RR_WINDOW_RECTANGULAR = Fourier::new); center_dc != 0 rotates the
+     * DC bin to index n/2 (analysis.rs:113-115).  Output chunks have the input's length and sample rate. */
+    int32_t center_dc;
+    int32_t reserved0;
 } rr_stage_desc;
 
 typedef struct rr_chain_desc {

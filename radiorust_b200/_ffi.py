@@ -19,7 +19,8 @@ RR_ERR_NOMEM = -4
 RR_ERR_CAPACITY = -5
 
 RR_C32, RR_C64 = 0, 1
-(RR_STAGE_FREQSHIFT, RR_STAGE_FILTER, RR_STAGE_DOWNSAMPLE, RR_STAGE_UPSAMPLE, RR_STAGE_FMDEMOD, RR_STAGE_GAIN) = range(1, 7)
+(RR_STAGE_FREQSHIFT, RR_STAGE_FILTER, RR_STAGE_DOWNSAMPLE, RR_STAGE_UPSAMPLE, RR_STAGE_FMDEMOD, RR_STAGE_GAIN,
+ RR_STAGE_FOURIER) = range(1, 8)
 RR_WINDOW_KAISER, RR_WINDOW_RECTANGULAR, RR_WINDOW_CUSTOM = 0, 1, 2
 
 FREQ_RESP_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double))
@@ -43,6 +44,8 @@ class StageDesc(C.Structure):
         ("quality", C.c_double),
         ("deviation", C.c_double),
         ("gain", C.c_double),
+        ("center_dc", C.c_int32),
+        ("reserved0", C.c_int32),
     ]
 
 

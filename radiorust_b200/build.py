@@ -51,6 +51,7 @@ def translation_units():
         ("rr_poly.o", "rr_poly.cu", []),
         ("rr_poly2.o", "rr_poly2.cu", []),
         ("rr_front.o", "rr_front.cu", []),
+        ("rr_fourier.o", "rr_fourier.cu", []),
     ]
     for t, tn in (("float", "f32"), ("double", "f64")):
         for k in (256, 512, 1024):
@@ -58,8 +59,10 @@ def translation_units():
                 tus.append((f"rr_poly_{tn}_{k}_{g}.o", "rr_poly_inst.cu", [f"-DRR_T={t}", f"-DRR_K={k}", f"-DRR_G={g}"]))
     for n in F32_SIZES:
         tus.append((f"rr_chain_os_f32_{n}.o", "rr_chain_os_inst.cu", ["-DRR_T=float", f"-DRR_N={n}"]))
+        tus.append((f"rr_fourier_f32_{n}.o", "rr_fourier_inst.cu", ["-DRR_T=float", f"-DRR_N={n}"]))
     for n in F64_SIZES:
         tus.append((f"rr_chain_os_f64_{n}.o", "rr_chain_os_inst.cu", ["-DRR_T=double", f"-DRR_N={n}"]))
+        tus.append((f"rr_fourier_f64_{n}.o", "rr_fourier_inst.cu", ["-DRR_T=double", f"-DRR_N={n}"]))
     return [t for t in tus if os.path.exists(os.path.join(CSRC, t[1]))]
 
 

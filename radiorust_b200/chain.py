@@ -11,6 +11,7 @@ reference constructors (names and argument meaning):
 ``Upsampler``          ``blocks::Upsampler::with_quality`` (resampling.rs:180)
 ``FmDemod``            ``blocks::modulation::FmDemod::new`` (modulation.rs:97)
 ``GainControl``        ``blocks::GainControl::new`` (transform.rs:43)
+``Fourier``            ``blocks::analysis::Fourier::{new,new_center_dc,with_window,with_window_center_dc}`` (analysis.rs:38-59)
 =====================  ====================================================
 """
 from __future__ import annotations
@@ -128,6 +129,12 @@ class GainControl:
     gain: float = 1.0
 
 
+@dataclass
+class Fourier:
+    window: Tuple = ("rectangular",)  # Fourier::new (analysis.rs:38-40)
+    center_dc: bool = False
+
+
 def _window_fields(window):
     """-> (kind, beta, ctypes fn or None)"""
     if callable(window):
@@ -189,6 +196,14 @@ class Chain:
             elif isinstance(st, GainControl):
                 d.kind = _ffi.RR_STAGE_GAIN
                 d.gain = st.gain
+            elif isinstance(st, Fourier):
+                d.kind = _ffi.RR_STAGE_FOURIER
+                k, beta, wcb = _window_fields(st.window)
+                d.window_kind, d.window_beta = k, beta
+                if wcb is not None:
+                    self._keep.append(wcb)
+                    d.window_fn = wcb
+                d.center_dc = 1 if st.center_dc else 0
             else:
                 raise TypeError(f"not a stage: {st!r}")
         desc = _ffi.ChainDesc()

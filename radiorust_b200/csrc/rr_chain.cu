@@ -200,6 +200,9 @@ struct Stage {
     std::vector<double> ir_host;
     // FMDEMOD
     DevBuf fm_prev, fm_last;
+    // FOURIER: window values (Flt) and twiddles of the current chunk length
+    DevBuf fwin, ftw;
+    size_t fwin_n = 0;
     // generic output buffer
     DevBuf out;
     size_t out_cap = 0;
@@ -272,6 +275,7 @@ int advance_stage(const rr_stage_desc& d, StageHost& h, const Shape& in, StageAc
             h.n_sr = in.rate;
             break;
         case RR_STAGE_GAIN:
+        case RR_STAGE_FOURIER:
             break;
         case RR_STAGE_FMDEMOD:
             a.first_is_history = !h.fm_has_prev;
@@ -1128,6 +1132,39 @@ int run_push(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_chunks,
                 plan += "gain";
                 break;
             }
+            case RR_STAGE_FOURIER: {
+                const size_t n = cur.sh.chunk_len;
+                if (!rr::fourier_fft_supported<T>((int)n) && n > (size_t)rr::kFourierDirectMax)
+                    return fail(RR_ERR_UNSUPPORTED, "Fourier: chunk lengths outside the FFT plans are limited to 4096 samples");
+                if (s.fwin_n != n) {
+                    // analysis.rs:86-103: window sampled at the bin centres, scaled to unit mean power, rounded to Flt
+                    rr::WindowFn w = make_window(s.d.window_kind, s.d.window_beta, s.d.window_fn, s.d.window_user);
+                    std::vector<double> wv(n);
+                    double energy = 0.0;
+                    for (size_t k = 0; k < n; ++k) {
+                        wv[k] = w(2.0 * ((double)k + 0.5) / (double)n - 1.0);
+                        energy += wv[k] * wv[k];
+                    }
+                    const double scale = std::sqrt((double)n / energy);
+                    for (auto& v : wv) v *= scale;
+                    RR_TRY(upload_real<T>(s.fwin, wv, st));
+                    if (rr::fourier_fft_supported<T>((int)n)) {
+                        std::vector<std::complex<double>> tw;
+                        rr::make_twiddles(n, &tw);
+                        RR_TRY(upload_complex<T>(s.ftw, tw, st));
+                    }
+                    s.fwin_n = n;
+                }
+                Dest d;
+                RR_TRY(pick_dest<T>(c, s, last, dev_out, (long long)out_stride, (size_t)len, &d));
+                RR_LAUNCH(1, rr::launch_fourier<T>((int)n, cur.p, cur.stride, d.p, d.stride, (int)cur.sh.n_chunks, S, (const T*)s.fwin.p,
+                                                   s.ftw.p, s.d.center_dc ? (int)(n / 2) : 0, st));
+                cur.p = d.p;
+                cur.stride = d.stride;
+                cur.sh = a.out;
+                plan += "fourier";
+                break;
+            }
             case RR_STAGE_FMDEMOD: {
                 Dest d;
                 RR_TRY(pick_dest<T>(c, s, last, dev_out, (long long)out_stride, (size_t)len, &d));
@@ -1470,6 +1507,7 @@ int rr_chain_create(rr_ctx* ctx, const rr_chain_desc* desc, rr_chain** out) {
                 break;
             case RR_STAGE_FMDEMOD:
             case RR_STAGE_GAIN:
+            case RR_STAGE_FOURIER:
                 break;
             default:
                 return fail(RR_ERR_INVALID, "rr_chain_create: unknown stage kind");

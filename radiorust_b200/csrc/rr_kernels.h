@@ -88,6 +88,14 @@ cudaError_t launch_fmdemod(const void* in, long long in_stride, void* out, long 
                            int n_streams, void* prev_sample, void* last_output, int has_prev, double factor,
                            cudaStream_t st);
 
+// Fourier analysis block (src/blocks/analysis.rs:60-132): out chunk = FFT_n(window * in chunk), bin k at
+// (k + rot) mod n.  Three-pass FFT for the plan sizes, direct DFT for any other n <= kFourierDirectMax.
+constexpr int kFourierDirectMax = 4096;
+template <typename T> bool fourier_fft_supported(int n);
+template <typename T>
+cudaError_t launch_fourier(int n, const void* in, long long in_stride, void* out, long long out_stride, int n_chunks, int n_streams,
+                           const T* window, const void* twN, int rot, cudaStream_t st);
+
 // strided 2-D copy of complex samples (used to stage stream buffers)
 template <typename T>
 cudaError_t launch_copy2d(const void* in, long long in_stride, void* out, long long out_stride, long long len,
