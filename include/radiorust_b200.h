@@ -126,6 +126,12 @@ int rr_device_free(rr_ctx* ctx, void* p);
 int rr_memcpy_h2d(rr_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
 int rr_memcpy_d2h(rr_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
 
+/* ---- metering::level (src/metering.rs:21-30) ------------------------------ */
+/* mean square norm of every chunk of DEVICE samples: host_out[s*n_chunks + c] for chunk c of stream s
+ * (stream s at dev_in + s*in_stride samples); accumulated in f64 like the reference. */
+int rr_metering_level(rr_ctx* ctx, int32_t dtype, const void* dev_in, size_t in_stride, size_t chunk_len, size_t n_chunks,
+                      int n_streams, double* host_out);
+
 /* ---- design math, host only (no GPU needed) ------------------------------ */
 double rr_bessel_i0(double x);                      /* math::bessel_I0  src/math.rs:7-20 */
 double rr_sinc(double x);                           /* math::sinc       src/math.rs:42-49 */

@@ -16,5 +16,6 @@ from .chain import (  # noqa: F401
     GainControl,
     Upsampler,
     kernel_launch_count,
+    level,
 )
 from ._ffi import RadiorustError  # noqa: F401

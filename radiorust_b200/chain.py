@@ -352,5 +352,26 @@ class Chain:
         return self._lib.rr_chain_plan(self._h).decode()
 
 
+def level(ctx: Context, x: np.ndarray, chunk_len: int) -> np.ndarray:
+    """``metering::level`` (metering.rs:21-30) of every chunk of ``x`` ([streams, samples] complex64/128) on the
+    device: mean square norm, f64.  Returns [streams, chunks]."""
+    lib = _ffi.load()
+    x = np.ascontiguousarray(np.atleast_2d(x))
+    if x.dtype not in (np.complex64, np.complex128):
+        raise TypeError("complex64 or complex128 samples")
+    S, total = x.shape
+    n_chunks = total // chunk_len
+    dev = C.c_void_p()
+    check(lib.rr_device_alloc(ctx._h, max(x.nbytes, 16), C.byref(dev)))
+    try:
+        check(lib.rr_memcpy_h2d(ctx._h, dev, x.ctypes.data_as(C.c_void_p), x.nbytes))
+        out = np.zeros((S, n_chunks), dtype=np.float64)
+        check(lib.rr_metering_level(ctx._h, _ffi.RR_C32 if x.dtype == np.complex64 else _ffi.RR_C64, dev, total, chunk_len, n_chunks, S,
+                                    out.ctypes.data_as(C.POINTER(C.c_double))))
+    finally:
+        lib.rr_device_free(ctx._h, dev)
+    return out
+
+
 def kernel_launch_count() -> int:
     return int(_ffi.load().rr_kernel_launch_count())

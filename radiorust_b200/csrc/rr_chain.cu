@@ -1364,6 +1364,29 @@ int rr_memcpy_d2h(rr_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes
     return RR_OK;
 }
 
+// ---- metering (src/metering.rs:21-30) ---------------------------------------------
+int rr_metering_level(rr_ctx* ctx, int32_t dtype, const void* dev_in, size_t in_stride, size_t chunk_len, size_t n_chunks, int n_streams,
+                      double* host_out) {
+    if (!ctx || !host_out || (!dev_in && n_chunks)) return fail(RR_ERR_INVALID, "rr_metering_level: null argument");
+    if (dtype != RR_C32 && dtype != RR_C64) return fail(RR_ERR_INVALID, "rr_metering_level: bad dtype");
+    if (n_streams < 1 || chunk_len == 0) return fail(RR_ERR_INVALID, "rr_metering_level: empty chunk (the reference divides by zero)");
+    if (n_chunks == 0) return RR_OK;
+    RR_CUDA(cudaSetDevice(ctx->device));
+    DevBuf out;
+    RR_TRY(out.ensure(sizeof(double) * n_chunks * (size_t)n_streams));
+    cudaError_t e = dtype == RR_C32 ? rr::launch_level<float>(dev_in, (long long)in_stride, (long long)chunk_len, (long long)n_chunks, n_streams,
+                                                              (double*)out.p, nullptr)
+                                    : rr::launch_level<double>(dev_in, (long long)in_stride, (long long)chunk_len, (long long)n_chunks, n_streams,
+                                                               (double*)out.p, nullptr);
+    if (e == cudaSuccess) {
+        g_launches.fetch_add(1);
+        e = cudaMemcpy(host_out, out.p, sizeof(double) * n_chunks * (size_t)n_streams, cudaMemcpyDeviceToHost);
+    }
+    out.release();
+    if (e != cudaSuccess) return fail_cuda(e, "rr_metering_level");
+    return RR_OK;
+}
+
 // ---- design math ------------------------------------------------------------
 double rr_bessel_i0(double x) { return rr::bessel_i0(x); }
 double rr_sinc(double x) { return rr::sinc(x); }

@@ -96,6 +96,11 @@ template <typename T>
 cudaError_t launch_fourier(int n, const void* in, long long in_stride, void* out, long long out_stride, int n_chunks, int n_streams,
                            const T* window, const void* twN, int rot, cudaStream_t st);
 
+// metering::level (src/metering.rs:21-30): out[s*n_chunks + c] = mean |x|^2 of chunk c of stream s (f64, device)
+template <typename T>
+cudaError_t launch_level(const void* in, long long in_stride, long long chunk_len, long long n_chunks, int n_streams, double* out,
+                         cudaStream_t st);
+
 // strided 2-D copy of complex samples (used to stage stream buffers)
 template <typename T>
 cudaError_t launch_copy2d(const void* in, long long in_stride, void* out, long long out_stride, long long len,

@@ -265,6 +265,40 @@ cudaError_t launch_fmdemod(const void* in, long long in_stride, void* out, long 
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------
+// metering::level (src/metering.rs:21-30): mean square norm of a chunk, accumulated in f64.
+// One CTA per (chunk, stream); the f64 partial sums are combined in a fixed order (deterministic).
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_level(const cx<T>* __restrict__ in, long long in_stride, long long chunk_len,
+                                               double* __restrict__ out, long long n_chunks) {
+    __shared__ double part[8];
+    const cx<T>* src = in + (long long)blockIdx.y * in_stride + (long long)blockIdx.x * chunk_len;
+    double acc = 0.0;
+    for (long long t = threadIdx.x; t < chunk_len; t += blockDim.x) {
+        const cx<T> v = ld_cx(&src[t]);
+        const T nsq = v.x * v.x + v.y * v.y;  // norm_sqr in Flt, then to_f64 (metering.rs:27)
+        acc += (double)nsq;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sum = 0.0;
+        for (int w = 0; w < 8; ++w) sum += part[w];
+        out[(long long)blockIdx.y * n_chunks + blockIdx.x] = sum / (double)chunk_len;
+    }
+}
+template <typename T>
+cudaError_t launch_level(const void* in, long long in_stride, long long chunk_len, long long n_chunks, int n_streams, double* out,
+                         cudaStream_t st) {
+    if (n_chunks <= 0 || chunk_len <= 0) return cudaSuccess;
+    k_level<T><<<dim3((unsigned)n_chunks, (unsigned)n_streams), 256, 0, st>>>(reinterpret_cast<const cx<T>*>(in), in_stride, chunk_len, out,
+                                                                             n_chunks);
+    return cudaGetLastError();
+}
+
 #define RR_INST(T)                                                                                                     \
     template cudaError_t launch_freqshift<T>(const void*, long long, void*, long long, long long, int,                 \
                                              const NcoStream*, long long, cudaStream_t);                                                          \
@@ -276,7 +310,8 @@ cudaError_t launch_fmdemod(const void* in, long long in_stride, void* out, long 
     template cudaError_t launch_upsample<T>(const void*, long long, long long, const void*, void*, const T*, int,      \
                                             RateState, long long, void*, long long, int, cudaStream_t);                \
     template cudaError_t launch_fmdemod<T>(const void*, long long, void*, long long, long long, int, void*, void*,     \
-                                           int, double, cudaStream_t);
+                                           int, double, cudaStream_t);                                                 \
+    template cudaError_t launch_level<T>(const void*, long long, long long, long long, int, double*, cudaStream_t);
 RR_INST(float)
 RR_INST(double)
 #undef RR_INST

@@ -88,3 +88,21 @@ def test_in_a_chain_and_unsupported_length(ctx):
     with pytest.raises(rr.RadiorustError):
         ch.push(48000.0, orc.synth_noise(1, 2 * 5000, "f32"), 5000)
     ch.close()
+
+
+def test_metering_level(ctx):
+    """metering::level (metering.rs:21-30), incl. its doc-test vector: level([0, -0.5j, 1]) = 1.25/3."""
+    import radiorust_b200 as rr
+
+    v = np.array([0.0, -0.5j, 1.0], dtype=np.complex64)
+    assert rr.level(ctx, v, 3)[0, 0] == pytest.approx(1.25 / 3.0, rel=1e-12)
+    assert abs(rr.level(ctx, v, 3)[0, 0] - 0.41666667) < 0.001  # the reference's own assertion
+    for dt, flt in ((np.complex64, "f32"), (np.complex128, "f64")):
+        x = np.stack([orc.synth_noise(5 + s, 7 * 1000, flt) for s in range(3)])
+        got = rr.level(ctx, x, 1000)
+        assert got.shape == (3, 7)
+        for s in range(3):
+            for c in range(7):
+                ch = x[s, c * 1000:(c + 1) * 1000]
+                nsq = (ch.real * ch.real + ch.imag * ch.imag).astype(np.float64)  # norm_sqr in Flt, summed in f64
+                assert got[s, c] == pytest.approx(float(np.sum(nsq)) / 1000.0, rel=1e-6 if flt == "f32" else 1e-12)
