@@ -195,3 +195,51 @@ def test_front_runs_are_bit_reproducible(ctx):
     for s in (0, 17, 36):
         want = oracle_chain(shifts[s], 3000.0, 2048, 48000.0, 6000.0, sr, x[s], n)
         assert orc.rel_l2(a[s], want) <= TOL
+
+
+def test_front_full_baseline_size_on_device(ctx):
+    """BASELINE.json config C3 at its full single-GPU size -- 4096 streams x 50 chunks x 4096 samples per push,
+    device resident (6.7 GB of input) -- through properties that need no oracle run at that size:
+    streams s and s + 2048 get identical samples and shifts and must come out bit-identical (independence,
+    determinism, no cross-stream leakage in the persistent kernels), two pushes, and three streams are checked
+    against the oracle sample by sample."""
+    import torch
+
+    import radiorust_b200 as rr
+
+    sr, n, S, C = 2_400_000.0, 4096, 4096, 50
+    half = S // 2
+    length = C * n
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(20260000 + 3 * 100000)
+    x = torch.empty((S, length, 2), device="cuda", dtype=torch.float32)
+    x[:half] = torch.randn((half, length, 2), device="cuda", dtype=torch.float32, generator=gen)
+    x[half:] = x[:half]
+    shifts = [float((s % half) * 577 % 2_400_000 - 1_200_000) for s in range(S)]   # SURVEY.md 8(d)
+    chain = rr.Chain(ctx, [rr.FreqShifter(0.0), rr.Filter.new(orc.lowpass(3000.0)), rr.Downsampler(2048, 48000.0, 6000.0)],
+                     "f32", n_streams=S)
+    chain.set_shifts(0, shifts)
+    cap = chain.max_output(sr, n, C + 1) + 2048
+    y = torch.zeros((S, cap, 2), device="cuda", dtype=torch.float32)
+    outs = []
+    for push in range(2):
+        cnt, rate = chain.push_device(sr, n, C, x.data_ptr(), length, y.data_ptr(), cap, cap)
+        chain.sync()
+        torch.cuda.synchronize()
+        assert rate == 48000.0 and cnt > 0 and cnt % 2048 == 0
+        assert "front+poly2" in chain.plan, chain.plan
+        got = y[:, :cnt].clone()
+        assert torch.equal(got[:half], got[half:])
+        assert bool(torch.isfinite(got).all())
+        outs.append(got)
+    chain.close()
+    for s in (0, 1000, 2047):
+        xs = x[s].cpu().numpy().view(np.complex64).reshape(-1)
+        oc = orc.Chain([orc.FreqShifter("f32", 1.0, shifts[s]), orc.Filter.new("f32", orc.lowpass(3000.0)),
+                        orc.Downsampler("f32", 2048, 48000.0, 6000.0)])
+        want = oc.run(sr, np.concatenate([xs, xs]), n)
+        g = torch.cat([outs[0][s], outs[1][s]]).cpu().numpy().view(np.complex64).reshape(-1)
+        assert g.shape == want.shape
+        assert orc.rel_l2(g, want) <= TOL
+    del x, y
+    torch.cuda.empty_cache()
