@@ -1,5 +1,9 @@
-// k_poly2: the complex-f32 throughput kernel of the fused chain
+// k_poly2: the complex-f32 polyphase kernel of the fused chain
 // FreqShifter -> Filter -> Downsampler (integer decimation, Q == 1, even P).
+// It runs in two roles: on the output `u` of the rank-reduced front end
+// (rr_front.cu; P = G = 10 branches, one round per block, no NCO: SINGLE) --
+// that is the benchmarked path -- and on all P branches of the input itself
+// when a filter does not factor to rank 10.
 //
 // Same algebra as k_poly (rr_poly.cuh: P branch transforms of K = 512 points, a
 // multiply-accumulate against FFT_K(G[p]) and one inverse transform per block
@@ -22,9 +26,9 @@
 //     32-entry table per branch column that the column's 16 threads rebuild
 //     for the next round while they work on the current one.
 //
-// Thread (g, t), tid = t*G + g: pass 1 transforms rows t + 16*i1 of branch
-// column g, pass 2 the bins k1 in {t, t+16}; it owns the 32 accumulators of
-// bins t + 16*which + 32*k2 of its column group.  The G partial spectra of a
+// Lane (t, column parity) of warp w works on branch column g = 2w + parity:
+// pass 1 transforms rows t + 16*i1 of that column, pass 2 the bins k1 in
+// {t, t+16}; it owns the 32 accumulators of bins t + 16*which + 32*k2.  The G partial spectra of a
 // block are summed through shared memory once per block, parked, and inverted
 // at the end by the same two-pass code (conjugate trick).
 //
@@ -34,7 +38,10 @@
 // hand a tile stage back starts the TMA copy of the round after next into it.
 // One CTA = two independent halves (own stream, shared memory, mbarriers and
 // named barrier): the register file is per SM sub-partition, so 10 warps of 168
-// registers fit where two 5-warp CTAs would be rounded up.
+// registers fit where two 5-warp CTAs would be rounded up.  Halves are
+// persistent: each walks through (stream, group of blocks) units, the first tile
+// of the next unit already in flight while the inverse transforms of the
+// current one run.
 //
 // Blocks that reach before the pushed samples (into hist2, already mixed) take
 // thread-local global loads instead of the TMA tile; a last block that would
