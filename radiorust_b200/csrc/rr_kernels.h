@@ -144,6 +144,7 @@ template <typename T> struct PolyArgs {
     int Lmax, V;           // low-rate filter reach, valid outputs per block and phase
     int n_blocks, nbpc;    // blocks per stream, blocks per CTA (k_poly2: per group)
     int ngrp;              // k_poly2: groups of nbpc blocks that one CTA half works through
+    int halves;            // k_poly2: independent halves per CTA (0 or 2: two; 1: one half per CTA, half the shared memory)
     long long J0, m0;      // filter-output samples consumed / outputs emitted before this push (reduced)
     long long m_lo, m_hi;  // outputs m to produce (inclusive)
     long long I_lo;        // low-rate index of block 0's first valid output

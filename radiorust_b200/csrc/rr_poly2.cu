@@ -179,7 +179,8 @@ __global__ void __launch_bounds__(2 * P2Cfg<G>::THREADS, 1) k_poly2(const __grid
     const int t = lane >> 1, gg = lane & 1;
     const int g = 2 * warp + gg;  // branch column of this lane
     // this half works through streams s_first, s_first + s_step, ...
-    const int s_first = blockIdx.y * 2 + half, s_step = gridDim.y * 2;
+    const int n_halves = a.halves == 1 ? 1 : 2;
+    const int s_first = blockIdx.y * n_halves + half, s_step = gridDim.y * n_halves;
     if (s_first >= n_streams) return;  // the halves never meet at a CTA-wide barrier
     int s = s_first;
     auto sync_half = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(half + 1), "n"(THREADS) : "memory"); };
@@ -584,7 +585,8 @@ EncodeFn encode_fn() {
 
 template <int G> cudaError_t launch_g(int n_streams, const PolyArgs<float>& a, const CUtensorMap& tm, cudaStream_t st) {
     using C = P2Cfg<G>;
-    const size_t smem = C::smem_bytes(a.nbpc);
+    const int halves = a.halves == 1 ? 1 : 2;
+    const size_t smem = C::half_bytes(a.nbpc) * halves;
     const int per_cta = a.nbpc * (a.ngrp > 0 ? a.ngrp : 1);
     // one CTA per SM; a half walks through several streams when there are more stream pairs than SMs
     static int sm_count = 0;
@@ -595,8 +597,9 @@ template <int G> cudaError_t launch_g(int n_streams, const PolyArgs<float>& a, c
         if (sm_count <= 0) sm_count = 1;
     }
     const unsigned gx = (unsigned)((a.n_blocks + per_cta - 1) / per_cta);
-    unsigned gy = (unsigned)((n_streams + 1) / 2);
-    if ((long long)gx * gy > sm_count) gy = (unsigned)std::max(1, std::min((int)gy, (sm_count + (int)gx - 1) / (int)gx));
+    unsigned gy = (unsigned)((n_streams + halves - 1) / halves);
+    const int slots = sm_count * (halves == 1 ? 2 : 1);  // CTAs that can be resident at once
+    if ((long long)gx * gy > slots) gy = (unsigned)std::max(1, std::min((int)gy, (slots + (int)gx - 1) / (int)gx));
     const dim3 grid(gx, gy);
     void (*kern)(const CUtensorMap, const PolyArgs<float>, const int);
     const bool single = a.P <= G;
@@ -604,7 +607,7 @@ template <int G> cudaError_t launch_g(int n_streams, const PolyArgs<float>& a, c
     else kern = single ? k_poly2<G, false, true> : k_poly2<G, false, false>;
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<grid, 2 * C::THREADS, smem, st>>>(tm, a, n_streams);
+    kern<<<grid, halves * C::THREADS, smem, st>>>(tm, a, n_streams);
     return cudaGetLastError();
 }
 
