@@ -80,7 +80,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "10", "-i", str(self.gpu)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -89,7 +89,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark(self, name):
+        """wall-clock bracket of the timed region: only samples inside it are reported"""
+        setattr(self, name, time.time())
 
     def stop(self):
         if self.proc is None:
@@ -102,7 +106,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        t0, t1 = getattr(self, "t0", None), getattr(self, "t1", None)
+        inside = [ln for ts, ln in self.lines if t0 is not None and t1 is not None and t0 <= ts <= t1 + 0.02]
+        scope = "timed region" if inside else "around the timed region"
+        for ln in (inside or [ln for _, ln in self.lines]):
             f = [v.strip() for v in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -118,6 +125,7 @@ class ClockSampler:
             "sm_mhz": float(np.median(sm)) if sm else None,
             "sm_max_mhz": float(max(mx)) if mx else None,
             "samples": len(sm),
+            "scope": scope,
             "reasons": sorted(reasons),
         }
 
@@ -241,6 +249,9 @@ def run_cuda(args):
     chain.set_timing(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     out_total = 0
+    if rank == 0:
+        time.sleep(0.05)  # let the sampler come up
+        sampler.mark("t0")
     with torch.cuda.stream(ext):
         e0.record(ext)
         for _ in range(args.steps):
@@ -249,6 +260,8 @@ def run_cuda(args):
         e1.record(ext)
     chain.sync()
     torch.cuda.synchronize()
+    if rank == 0:
+        sampler.mark("t1")
     if dist is not None:
         dist.barrier()
     clocks = sampler.stop() if rank == 0 else None
