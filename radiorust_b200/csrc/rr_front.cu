@@ -45,6 +45,11 @@ constexpr int FR_ROWS = 16;  // rows per tile: a lane pair per row, each lane ha
 constexpr int FR_STAGES = 2;  // tiles per warp in shared memory (one being filled while the other is used)
 
 __device__ __forceinline__ uint32_t f_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ pc lds_front(uint32_t addr) {
+    pc r;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(addr));
+    return r;
+}
 
 template <int RK, bool HAS_NCO>
 __global__ void __launch_bounds__(FR_WARPS * 32) k_front(const __grid_constant__ CUtensorMap tmap, const FrontArgs a) {
@@ -57,15 +62,18 @@ __global__ void __launch_bounds__(FR_WARPS * 32) k_front(const __grid_constant__
     // tile row pitch in samples: P, or P + 2 when P/2 is even (an odd number of 16-byte units per row keeps the
     // lanes' 16-byte loads conflict free); the two extra samples of a row are never used
     const int pitch = P + ((P & 3) == 0 ? 2 : 0);
-    // column pairs of this lane: [st0, st1)
-    // The split point: with an odd number of 16-byte units per row the 8 lanes of a quarter warp (4 rows x
-    // 2 halves) hit 8 distinct bank groups when the halves start 4 (mod 8) units apart.
-    int split = steps / 2;
-    if (steps >= 20) {
+    // Column pairs of this lane: [st0, st1).  An odd number of pairs (P = 2 mod 4) is split evenly and the last
+    // pair is shared, one sample per lane.  The split point: with an odd number of 16-byte units per row the 8
+    // lanes of a quarter warp (4 rows x 2 halves) hit 8 distinct bank groups when the halves start 4 (mod 8)
+    // units apart.
+    const bool odd_steps = (steps & 1) != 0;
+    const int full = steps - (odd_steps ? 1 : 0);
+    int split = full / 2;
+    if (!odd_steps && steps >= 20) {
         for (int d = -1; d <= 1; ++d)
-            if (((steps / 2 + d) & 7) == 4) split = steps / 2 + d;
+            if (((full / 2 + d) & 7) == 4) split = full / 2 + d;
     }
-    const int st0 = hh ? split : 0, st1 = hh ? steps : split;
+    const int st0 = hh ? split : 0, st1 = hh ? full : split;
 
     extern __shared__ __align__(128) unsigned char smem[];
     const int tile_bytes = FR_ROWS * pitch * 8;
@@ -117,35 +125,38 @@ __global__ void __launch_bounds__(FR_WARPS * 32) k_front(const __grid_constant__
 
     const int tile0 = (blockIdx.x * FR_WARPS + warp) * a.tiles_per_warp;
     const int n_tiles = min(a.tiles_per_warp, (a.n_rows - tile0 * FR_ROWS + FR_ROWS - 1) / FR_ROWS);  // may be <= 0
-    auto tile_pos0 = [&](int k) -> long long { return ((long long)a.row_first + (long long)(tile0 + k) * FR_ROWS) * P - a.J0; };
-    auto tile_interior = [&](long long pos0) -> bool { return pos0 >= 0 && pos0 + (long long)(FR_ROWS - 1) * P + pitch <= len; };
-    // start the TMA copy of tile k into ring slot k % FR_STAGES (interior tiles only)
+    // push offset of the first sample of this warp's tile k (the launcher guarantees that offsets fit 32 bits)
+    const int pos_first = (int)(((long long)a.row_first + (long long)tile0 * FR_ROWS) * P - a.J0), pos_step = FR_ROWS * P;
+    const int len32 = (int)len;
+    auto tile_pos0 = [&](int k) -> int { return pos_first + k * pos_step; };
+    auto tile_interior = [&](int pos0) -> bool { return pos0 >= 0 && pos0 + (FR_ROWS - 1) * P + pitch <= len32; };
+    // start the TMA copy of tile k into ring slot k % FR_STAGES (interior tiles only); the bookkeeping is
+    // warp-uniform, only the two asynchronous instructions are issued by one lane
     auto issue = [&](int k) {
-        if (k >= n_tiles) return;
-        const long long pos0 = tile_pos0(k);
-        if (!tile_interior(pos0)) return;
+        const int pos0 = tile_pos0(k);
+        const bool go = k < n_tiles && tile_interior(pos0);
         const uint32_t bar = bar0 + (k % FR_STAGES) * 8;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tile_bytes) : "memory");
-        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-                         tiles_s + (k % FR_STAGES) * tile_stride),
-                     "l"(&tmap), "r"(bar), "r"((int)pos0), "r"(0), "r"(s)
-                     : "memory");
+        if (go && lane == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tile_bytes) : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                             tiles_s + (k % FR_STAGES) * tile_stride),
+                         "l"(&tmap), "r"(bar), "r"(pos0), "r"(0), "r"(s)
+                         : "memory");
+        }
     };
-    if (lane == 0) {
 #pragma unroll
-        for (int q = 0; q < FR_STAGES - 1; ++q) issue(q);
-    }
+    for (int q = 0; q < FR_STAGES - 1; ++q) issue(q);
 
     uint32_t phase = 0;  // bit q: parity of ring slot q's next completion
     pc rowph(1.f, 0.f);
     for (int k = 0; k < n_tiles; ++k) {
         const int slot = k % FR_STAGES;
         const int v0 = (tile0 + k) * FR_ROWS;  // first row (of this push's u rows) of the tile
-        const long long pos0 = tile_pos0(k);
+        const int pos0 = tile_pos0(k);
         const bool interior = tile_interior(pos0);
         const uint32_t tile_s = tiles_s + slot * tile_stride;
         // the slot of tile k + FR_STAGES - 1 was released at the end of the previous iteration
-        if (lane == 0) issue(k + FR_STAGES - 1);
+        issue(k + FR_STAGES - 1);
         // row phasor: exact at the warp's first tile and every 16th one, rotated in between
         if (HAS_NCO) {
             if ((k & 15) == 0) {
@@ -249,6 +260,26 @@ __global__ void __launch_bounds__(FR_WARPS * 32) k_front(const __grid_constant__
                     acc[c] = pfma_s(x1, cf[RK + c], acc[c]);
                 }
             }
+            if (odd_steps) {
+                // the last column pair: one sample per lane
+                const int p = 2 * full + hh;
+                pc x0 = lds_front(row_s + p * 8);
+                if (HAS_NCO) x0 = pcmul(x0, lds_front(col_s + p * 8));
+                if (decltype(write_hist)::value) {
+                    const long long j = prow + p - a.hist_from;
+                    if (row_ok && j >= 0) {
+                        const pc y0 = HAS_NCO ? pcmul(x0, rowph) : x0;
+                        hist_o[j] = make_float2(y0.x, y0.y);
+                    }
+                }
+                float cf[RK];
+                static_assert(RK % 2 == 0, "coefficient rows are read in pairs");
+#pragma unroll
+                for (int q = 0; q < RK / 2; ++q)
+                    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(cf[2 * q]), "=f"(cf[2 * q + 1]) : "r"(coef_s + p * (RK * 4) + q * 8));
+#pragma unroll
+                for (int c = 0; c < RK; ++c) acc[c] = pfma_s(x0, cf[c], acc[c]);
+            }
         };
         if (hist_o != nullptr && pos0 + (long long)FR_ROWS * P > a.hist_from) run_row(std::true_type{});
         else run_row(std::false_type{});
@@ -257,10 +288,8 @@ __global__ void __launch_bounds__(FR_WARPS * 32) k_front(const __grid_constant__
         __syncwarp();
         // the two column halves of a row meet; lane hh = 0 stores results 0..5, lane hh = 1 results 6..9
 #pragma unroll
-        for (int c = 0; c < RK; ++c) {
-            acc[c].x += __shfl_xor_sync(0xffffffffu, acc[c].x, 1);
-            acc[c].y += __shfl_xor_sync(0xffffffffu, acc[c].y, 1);
-        }
+        for (int c = 0; c < RK; ++c)
+            acc[c] = acc[c] + pc(__shfl_xor_sync(0xffffffffu, acc[c].x, 1), __shfl_xor_sync(0xffffffffu, acc[c].y, 1));
         const int v = v0 + row;
         if (v < a.n_rows) {
             float4* dst = u + ((long long)v * RK) / 2;
