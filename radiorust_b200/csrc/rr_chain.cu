@@ -1566,7 +1566,8 @@ int rr_chain_destroy(rr_chain* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto& s : c->st) {
         DevBuf* bufs[] = {&s.nco_d, &s.hperm, &s.tw, &s.hist2[0], &s.hist2[1], &s.ztmp, &s.gtab, &s.twK, &s.big_h, &s.big_twA, &s.big_twB, &s.big_scratch,
-                          &s.ir, &s.tail[0], &s.tail[1], &s.obuf[0], &s.obuf[1], &s.fm_prev, &s.fm_last, &s.out};
+                          &s.ir, &s.tail[0], &s.tail[1], &s.obuf[0], &s.obuf[1], &s.fm_prev, &s.fm_last, &s.out,
+                          &s.gtab2, &s.twK2, &s.acoef, &s.gtab3, &s.ubuf, &s.fwin, &s.ftw};
         for (DevBuf* b : bufs) b->release();
     }
     c->host_in.release();

@@ -243,3 +243,28 @@ def test_front_full_baseline_size_on_device(ctx):
         assert orc.rel_l2(g, want) <= TOL
     del x, y
     torch.cuda.empty_cache()
+
+
+def test_chain_destroy_releases_device_memory(ctx):
+    """Creating and destroying chains (incl. the front end's scratch buffers) must not leak device memory."""
+    import torch
+
+    import radiorust_b200 as rr
+
+    sr, n, S = 2_400_000.0, 4096, 64
+    x = np.stack([orc.synth_noise(3 + s, 20 * n, "f32") for s in range(S)])
+
+    def once():
+        ch = rr.Chain(ctx, [rr.FreqShifter(1000.0), rr.Filter.new(orc.lowpass(3000.0)), rr.Downsampler(64, 48000.0, 6000.0)], "f32", n_streams=S)
+        ch.push(sr, x, n)
+        assert "front+poly2" in ch.plan
+        ch.close()
+
+    once()
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info()
+    for _ in range(5):
+        once()
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < 8 * 1024 * 1024, (free0, free1)
