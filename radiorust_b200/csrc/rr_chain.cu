@@ -567,12 +567,24 @@ template <typename T> int pick_dest(rr_chain* c, Stage& s, bool last, void* user
 // after a resampler wrote n_new samples behind `pending_before` ones in its
 // staging buffer: hand whole chunks downstream, keep the remainder
 template <typename T>
-int resampler_emit(rr_chain* c, Stage& s, const StageAct& a, bool last, void* user_out, long long user_stride, View* next) {
+int resampler_emit(rr_chain* c, Stage& s, const StageAct& a, bool last, void* user_out, long long user_stride, View* next,
+                   bool direct_done = false) {
     const size_t emit = a.out.len();
     const size_t total = a.pending_before + a.n_new;
     DevBuf& cur = s.obuf[s.obuf_cur];
     DevBuf& other = s.obuf[s.obuf_cur ^ 1];
     const size_t rem = total - emit;
+    if (direct_done) {
+        // the kernel wrote the new samples to user_out / `other` itself: only the samples that were pending
+        // before this push are still in `cur`
+        if (a.pending_before > 0)
+            RR_LAUNCH(1, rr::launch_copy2d<T>(cur.p, (long long)s.obuf_cap, user_out, user_stride, (long long)a.pending_before, c->S, c->stream));
+        next->sh = a.out;
+        next->p = user_out;
+        next->stride = user_stride;
+        s.obuf_cur ^= 1;
+        return RR_OK;
+    }
     if (rem > 0 && emit > 0) {
         const char* src = (const char*)cur.p + emit * 2 * sizeof(T);
         RR_LAUNCH(1, rr::launch_copy2d<T>(src, (long long)s.obuf_cap, other.p, (long long)s.obuf_cap, (long long)rem, c->S, c->stream));
@@ -822,8 +834,17 @@ template <typename T> int poly_prepare(rr_chain* c, Stage& f, Stage& ds) {
 
 // Filter stage `f` (with optional folded NCO) followed by Downsampler `ds`:
 // consumes the whole push, leaves new outputs behind ds's pending samples.
+// `direct` (optional): the Downsampler is the chain's last stage -- when the whole push goes through k_poly2, its
+// outputs are written straight to the caller's buffer (whole output chunks) and to the other obuf (the part
+// behind them), and *direct->done tells resampler_emit that only the old pending samples are left to copy.
+struct DirectOut {
+    void* user_out = nullptr;
+    long long user_stride = 0;
+    bool done = false;
+};
 template <typename T>
-int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const StageAct& fa, const StageAct& da, std::string* plan) {
+int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const StageAct& fa, const StageAct& da, std::string* plan,
+                    DirectOut* direct = nullptr) {
     const size_t n = io.n;
     const int S = c->S;
     cudaStream_t st = c->stream;
@@ -989,6 +1010,16 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
                         b.ngrp = ngrp;
                         b.out = obase;
                         b.out_stride = ostride;
+                        const long long emit = (long long)da.out.len();
+                        if (direct && direct->user_out && ca == 0 && emit >= (long long)da.pending_before && emit > 0) {
+                            // new output o lands at emitted position pending_before + o
+                            b.out = (char*)direct->user_out + da.pending_before * 2 * sizeof(T);
+                            b.out_stride = direct->user_stride;
+                            b.out2 = ds.obuf[ds.obuf_cur ^ 1].p;
+                            b.out2_stride = ostride;
+                            b.out_split = emit - (long long)da.pending_before;
+                            direct->done = true;
+                        }
                         RR_TIMED_LAUNCH(c, "k_poly2", 1, rr::launch_poly2(G2, S, b, st));
                         done = true;
                         used_front = true;
@@ -1205,9 +1236,14 @@ int run_push(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_chunks,
                         RR_TRY(resampler_redesign<T>(c, *ds, a.out.rate));
                     }
                     RR_TRY(obuf_reserve<T>(c, *ds, da.pending_before + da.n_new, da.pending_before));
-                    RR_TRY(run_filter_down<T>(c, s, *ds, io, a, da, &plan));
                     const bool ds_last = (i + 1 == ns - 1);
-                    RR_TRY(resampler_emit<T>(c, *ds, da, ds_last, dev_out, (long long)out_stride, &cur));
+                    DirectOut direct;
+                    if (ds_last) {
+                        direct.user_out = dev_out;
+                        direct.user_stride = (long long)out_stride;
+                    }
+                    RR_TRY(run_filter_down<T>(c, s, *ds, io, a, da, &plan, &direct));
+                    RR_TRY(resampler_emit<T>(c, *ds, da, ds_last, dev_out, (long long)out_stride, &cur, direct.done));
                     took_ds = true;
                 } else {
                     Dest d;

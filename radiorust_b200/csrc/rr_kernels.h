@@ -145,6 +145,10 @@ template <typename T> struct PolyArgs {
     int n_blocks, nbpc;    // blocks per stream, blocks per CTA (k_poly2: per group)
     int ngrp;              // k_poly2: groups of nbpc blocks that one CTA half works through
     int halves;            // k_poly2: independent halves per CTA (0 or 2: two; 1: one half per CTA, half the shared memory)
+    // k_poly2, optional second destination: outputs with index o = m - m0 - 1 >= out_split go to out2[o - out_split]
+    // (the samples behind the last whole output chunk: the Downsampler's next pending part), the others to out[o]
+    void* out2;
+    long long out2_stride, out_split;  // out2 == nullptr: everything to `out`
     long long J0, m0;      // filter-output samples consumed / outputs emitted before this push (reduced)
     long long m_lo, m_hi;  // outputs m to produce (inclusive)
     long long I_lo;        // low-rate index of block 0's first valid output

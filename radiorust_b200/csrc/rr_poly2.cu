@@ -273,6 +273,7 @@ __global__ void __launch_bounds__(2 * P2Cfg<G>::THREADS, 1) k_poly2(const __grid
     const float2* __restrict__ in = reinterpret_cast<const float2*>(a.in) + (long long)s * a.in_stride;
     const float2* __restrict__ hist_end = reinterpret_cast<const float2*>(a.hist2) + ((long long)s + 1) * 2 * a.n;
     float2* __restrict__ out = reinterpret_cast<float2*>(a.out) + (long long)s * a.out_stride;
+    float2* __restrict__ out2 = a.out2 ? reinterpret_cast<float2*>(a.out2) + (long long)s * a.out2_stride : nullptr;
 
     // ---- NCO constants, tables -------------------------------------------------------------
     uint32_t denom = 1, numer_abs = 0, idx0 = 0;
@@ -548,7 +549,11 @@ __global__ void __launch_bounds__(2 * P2Cfg<G>::THREADS, 1) k_poly2(const __grid
                         const int i = t + 16 * which + 32 * k2;
                         if (i >= a.Lmax + d && i < a.Lmax + a.V + (d > 0 ? 1 : 0)) {
                             const long long m = Ibase + i;  // Q == 1
-                            if (m >= a.m_lo && m <= a.m_hi) out[m - a.m0 - 1] = make_float2(x[k2].x, -x[k2].y);
+                            if (m >= a.m_lo && m <= a.m_hi) {
+                                const long long o = m - a.m0 - 1;
+                                float2* dst = (out2 != nullptr && o >= a.out_split) ? out2 + (o - a.out_split) : out + o;
+                                *dst = make_float2(x[k2].x, -x[k2].y);
+                            }
                         }
                     }
                 }
