@@ -30,7 +30,7 @@ extern "C" {
 #endif
 
 #define RR_VERSION_MAJOR 0
-#define RR_VERSION_MINOR 2
+#define RR_VERSION_MINOR 3
 
 typedef struct rr_ctx rr_ctx;
 typedef struct rr_chain rr_chain;
@@ -54,7 +54,10 @@ typedef enum rr_stage_kind {
     RR_STAGE_UPSAMPLE = 4,   /* blocks::Upsampler     src/blocks/resampling.rs:149-280 */
     RR_STAGE_FMDEMOD = 5,    /* blocks::modulation::FmDemod src/blocks/modulation.rs:83-158 */
     RR_STAGE_GAIN = 6,       /* blocks::GainControl   src/blocks/transform.rs:29-92 */
-    RR_STAGE_FOURIER = 7     /* blocks::analysis::Fourier src/blocks/analysis.rs:15-132 */
+    RR_STAGE_FOURIER = 7,    /* blocks::analysis::Fourier src/blocks/analysis.rs:15-132 */
+    RR_STAGE_FMMOD = 8,      /* blocks::modulation::FmMod src/blocks/modulation.rs:13-80 */
+    RR_STAGE_RECHUNK = 9,    /* blocks::chunks::Rechunker src/blocks/chunks.rs:42-176 */
+    RR_STAGE_OVERLAP = 10    /* blocks::chunks::Overlapper src/blocks/chunks.rs:179-248 */
 } rr_stage_kind;
 
 typedef enum rr_window_kind {
@@ -94,7 +97,13 @@ typedef struct rr_stage_desc {
      * window_beta, window_fn as for FILTER (RR_WINDOW_RECTANGULAR = Fourier::new); center_dc != 0 rotates the
      * DC bin to index n/2 (analysis.rs:113-115).  Output chunks have the input's length and sample rate. */
     int32_t center_dc;
-    int32_t reserved0;
+    /* OVERLAP: Overlapper::new(chunk_count) (chunks.rs:194-196), > 0.  Output chunk = the last chunk_count input
+     * chunks concatenated; nothing is emitted until chunk_count chunks have arrived.  The chunks of one history
+     * must share length and sample rate (anything else returns RR_ERR_UNSUPPORTED and leaves the state alone). */
+    int32_t chunk_count;
+    /* FMMOD: FmMod::new(deviation) uses `deviation` above (modulation.rs:27).  The phase accumulator follows the
+     * reference's rounding step by step (product, sum, fmod in Flt; modulation.rs:46-51) and survives events.
+     * RECHUNK: Rechunker::new(output_chunk_len) uses `output_chunk_len` above (chunks.rs:57), > 0. */
 } rr_stage_desc;
 
 typedef struct rr_chain_desc {
@@ -173,15 +182,24 @@ int rr_chain_get_shift(rr_chain* chain, int stage, int stream, double* shift_hz)
  * push and drop the history chunk (filters.rs:187). */
 int rr_chain_update_filter(rr_chain* chain, int stage, rr_freq_resp_fn f, void* f_user, int32_t window_kind,
                            double window_beta, rr_window_fn w, void* w_user, int keep_window);
-/* FmDemod::set_deviation (modulation.rs:154-157) */
+/* FmDemod::set_deviation (modulation.rs:154-157) / FmMod::set_deviation (modulation.rs:76-79) */
 int rr_chain_set_deviation(rr_chain* chain, int stage, double deviation);
+/* Rechunker::set_output_chunk_len (chunks.rs:171-175); takes effect with the next push */
+int rr_chain_set_output_chunk_len(rr_chain* chain, int stage, size_t output_chunk_len);
 /* GainControl::set (transform.rs:89-91) */
 int rr_chain_set_gain(rr_chain* chain, int stage, double gain);
 
 /* In-band event (signal.rs:19-31).  Interrupt events reset Filter history
  * (filters.rs:262-267) and FmDemod's previous sample (modulation.rs:133-138);
- * resamplers and the NCO keep their state. */
+ * resamplers, FmMod and the NCO keep their state.  ANY event makes a Rechunker
+ * drop its partial chunk (chunks.rs:84-91) and an Overlapper its history
+ * (chunks.rs:226-233); each of them then sends `SamplesLost` (an interrupt,
+ * chunks.rs:19-28) ahead of the event, so the stages behind it see an interrupt. */
 int rr_chain_event(rr_chain* chain, int is_interrupt);
+/* Number of `SamplesLost` events the chain's Rechunker / Overlapper stages have generated so far (on events, and
+ * a Rechunker on a sample-rate change with a partial chunk pending, chunks.rs:71-79).  The block task compares the
+ * count before and after rr_chain_event / a push and sends that many SamplesLost downstream first. */
+uint64_t rr_chain_samples_lost_count(rr_chain* chain);
 
 /* Upper bound of output samples per stream for a push of n_chunks*chunk_len
  * input samples at sample_rate. */

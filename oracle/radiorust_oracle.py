@@ -737,6 +737,99 @@ class Fourier:
 
 
 # --------------------------------------------------------------------------
+# chunks.rs -- Rechunker and Overlapper (chunk reorganisers), SamplesLost
+# --------------------------------------------------------------------------
+
+SAMPLES_LOST = Event("SamplesLost", True)  # chunks.rs:17-28: an interrupt event
+
+
+class Rechunker:
+    """chunks.rs:56-176: arbitrary input chunk lengths -> chunks of ``output_chunk_len``.
+
+    ``patchwork`` is the partially filled output chunk (None = the reference's
+    ``patchwork_opt == None``); it is dropped, and ``SamplesLost`` sent, when an
+    event arrives (:84-91) or the sample rate changes (:71-79).
+    """
+
+    def __init__(self, output_chunk_len: int):
+        assert output_chunk_len > 0, "chunk length must be positive"  # :58
+        self.output_chunk_len = int(output_chunk_len)
+        self.patchwork = None  # (sample_rate, ndarray)
+
+    def set_output_chunk_len(self, n: int):  # :171-175
+        assert n > 0, "chunk length must be positive"
+        self.output_chunk_len = int(n)
+
+    def process(self, sig):
+        out = []
+        if isinstance(sig, Event):
+            if self.patchwork is not None:
+                out.append(SAMPLES_LOST)
+                self.patchwork = None
+            out.append(sig)
+            return out
+        sr = sig.sample_rate
+        chunk = np.asarray(sig.chunk)
+        if self.patchwork is not None and self.patchwork[0] != sr:
+            self.patchwork = None
+            out.append(SAMPLES_LOST)
+        ocl = self.output_chunk_len
+        while True:  # one turn of the task loop per pass while an input chunk is in hand (:66-164)
+            if self.patchwork is not None:
+                p_sr, pw = self.patchwork
+                if len(pw) > ocl:  # only after set_output_chunk_len shrank the length (:101-112)
+                    while len(pw) > ocl:
+                        out.append(Samples(p_sr, pw[:ocl].copy()))
+                        pw = pw[ocl:]
+                missing = ocl - len(pw)
+                if len(chunk) < missing:  # :114-117
+                    self.patchwork = (p_sr, np.concatenate([pw, chunk]))
+                    return out
+                if len(chunk) == missing:  # :118-126
+                    out.append(Samples(p_sr, np.concatenate([pw, chunk])))
+                    self.patchwork = None
+                    return out
+                out.append(Samples(p_sr, np.concatenate([pw, chunk[:missing]])))  # :127-136
+                chunk = chunk[missing:]
+                self.patchwork = None
+            else:
+                while len(chunk) > ocl:  # :141-147
+                    out.append(Samples(sr, chunk[:ocl].copy()))
+                    chunk = chunk[ocl:]
+                if len(chunk) == ocl:  # :148-155
+                    out.append(Samples(sr, chunk.copy()))
+                    return out
+                self.patchwork = (sr, chunk[:0].copy())  # :156-159, filled on the next turn
+
+
+class Overlapper:
+    """chunks.rs:188-242: output = the last ``chunk_count`` chunks concatenated, once that many have arrived;
+    sample rate = length-weighted mean (:207-214).  ANY event clears the history and is preceded by
+    ``SamplesLost`` (:226-233)."""
+
+    def __init__(self, chunk_count: int):
+        assert chunk_count > 0, "chunk count must be positive"  # :195
+        self.chunk_count = int(chunk_count)
+        self.history = []
+
+    def process(self, sig):
+        if isinstance(sig, Event):
+            self.history = []
+            return [SAMPLES_LOST, sig]
+        self.history.append((sig.sample_rate, np.asarray(sig.chunk)))
+        if len(self.history) < self.chunk_count:
+            return []
+        count = 0
+        acc = 0.0
+        for sr, ch in self.history:
+            count += len(ch)
+            acc += sr * float(len(ch))
+        res = Samples(acc / float(count), np.concatenate([ch for _, ch in self.history]))
+        self.history.pop(0)
+        return [res]
+
+
+# --------------------------------------------------------------------------
 # A chain = blocks connected with feed_into (flow.rs:233-267); messages are
 # delivered in order, events in-band (signal.rs:170-183).
 # --------------------------------------------------------------------------

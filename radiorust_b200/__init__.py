@@ -2,7 +2,7 @@
 
 Only the hot path of JanBeh/radiorust named in BASELINE.json lives here:
 FreqShifter -> Filter -> Downsampler (+ Upsampler, FmDemod, de-emphasis,
-GainControl, Fourier), as hand-written CUDA kernels (``csrc/``) behind the C ABI of
+GainControl, Fourier, FmMod, Rechunker, Overlapper), as hand-written CUDA kernels (``csrc/``) behind the C ABI of
 ``include/radiorust_b200.h``.  This package is the ctypes face of that ABI.
 """
 from .chain import (  # noqa: F401
@@ -11,9 +11,12 @@ from .chain import (  # noqa: F401
     Downsampler,
     Filter,
     FmDemod,
+    FmMod,
     Fourier,
     FreqShifter,
     GainControl,
+    Overlapper,
+    Rechunker,
     Upsampler,
     kernel_launch_count,
     level,

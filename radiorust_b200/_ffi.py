@@ -20,7 +20,7 @@ RR_ERR_CAPACITY = -5
 
 RR_C32, RR_C64 = 0, 1
 (RR_STAGE_FREQSHIFT, RR_STAGE_FILTER, RR_STAGE_DOWNSAMPLE, RR_STAGE_UPSAMPLE, RR_STAGE_FMDEMOD, RR_STAGE_GAIN,
- RR_STAGE_FOURIER) = range(1, 8)
+ RR_STAGE_FOURIER, RR_STAGE_FMMOD, RR_STAGE_RECHUNK, RR_STAGE_OVERLAP) = range(1, 11)
 RR_WINDOW_KAISER, RR_WINDOW_RECTANGULAR, RR_WINDOW_CUSTOM = 0, 1, 2
 
 FREQ_RESP_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double))
@@ -45,7 +45,7 @@ class StageDesc(C.Structure):
         ("deviation", C.c_double),
         ("gain", C.c_double),
         ("center_dc", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("chunk_count", C.c_int32),
     ]
 
 
@@ -99,6 +99,8 @@ SIGNATURES = {
     "rr_chain_update_filter": (_I, [_P, _I, FREQ_RESP_FN, _P, C.c_int32, _D, WINDOW_FN, _P, _I]),
     "rr_chain_set_deviation": (_I, [_P, _I, _D]),
     "rr_chain_set_gain": (_I, [_P, _I, _D]),
+    "rr_chain_set_output_chunk_len": (_I, [_P, _I, _SZ]),
+    "rr_chain_samples_lost_count": (C.c_uint64, [_P]),
     "rr_chain_event": (_I, [_P, _I]),
     "rr_chain_max_output": (_SZ, [_P, _D, _SZ, _SZ]),
     "rr_chain_push": (_I, [_P, _D, _SZ, _SZ, _P, _SZ, _P, _SZ, _SZ, C.POINTER(_SZ), C.POINTER(_D)]),

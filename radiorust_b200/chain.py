@@ -125,6 +125,21 @@ class FmDemod:
 
 
 @dataclass
+class FmMod:
+    deviation: float
+
+
+@dataclass
+class Rechunker:
+    output_chunk_len: int
+
+
+@dataclass
+class Overlapper:
+    chunk_count: int
+
+
+@dataclass
 class GainControl:
     gain: float = 1.0
 
@@ -193,6 +208,15 @@ class Chain:
             elif isinstance(st, FmDemod):
                 d.kind = _ffi.RR_STAGE_FMDEMOD
                 d.deviation = st.deviation
+            elif isinstance(st, FmMod):
+                d.kind = _ffi.RR_STAGE_FMMOD
+                d.deviation = st.deviation
+            elif isinstance(st, Rechunker):
+                d.kind = _ffi.RR_STAGE_RECHUNK
+                d.output_chunk_len = st.output_chunk_len
+            elif isinstance(st, Overlapper):
+                d.kind = _ffi.RR_STAGE_OVERLAP
+                d.chunk_count = st.chunk_count
             elif isinstance(st, GainControl):
                 d.kind = _ffi.RR_STAGE_GAIN
                 d.gain = st.gain
@@ -257,8 +281,15 @@ class Chain:
     def set_gain(self, stage: int, gain: float):
         check(self._lib.rr_chain_set_gain(self._h, stage, float(gain)))
 
+    def set_output_chunk_len(self, stage: int, output_chunk_len: int):
+        check(self._lib.rr_chain_set_output_chunk_len(self._h, stage, int(output_chunk_len)))
+
     def event(self, is_interrupt: bool = True):
         check(self._lib.rr_chain_event(self._h, 1 if is_interrupt else 0))
+
+    def samples_lost_count(self) -> int:
+        """``SamplesLost`` events generated so far by the chain's Rechunker / Overlapper stages."""
+        return int(self._lib.rr_chain_samples_lost_count(self._h))
 
     # ---- data path ------------------------------------------------------------------
     def max_output(self, sample_rate: float, chunk_len: int, n_chunks: int) -> int:

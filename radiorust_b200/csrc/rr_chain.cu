@@ -129,6 +129,12 @@ struct StageHost {
     bool fm_has_prev = false;
     // FREQSHIFT
     double n_sr = NAN;
+    // RECHUNK: samples of the partial chunk and their sample rate
+    size_t rc_pending = 0;
+    double rc_rate = NAN;
+    // OVERLAP: chunks kept (< chunk_count), their length and sample rate
+    size_t ov_hist = 0, ov_len = 0;
+    double ov_rate = NAN;
 };
 
 struct StageAct {
@@ -140,6 +146,7 @@ struct StageAct {
     long long j0 = 0, m0 = 0;  // resampler counters before the push
     bool nco_recalc = false;
     int seg_before = 0;        // filter: chunks of the current segment seen before this push
+    bool lost = false;         // Rechunker: the partial chunk was dropped (SamplesLost goes downstream first)
     Shape out;
 };
 
@@ -200,6 +207,10 @@ struct Stage {
     std::vector<double> ir_host;
     // FMDEMOD
     DevBuf fm_prev, fm_last;
+    // FMMOD: the phase accumulator per stream (Flt).  RECHUNK keeps its partial chunk in obuf[], OVERLAP its
+    // history chunks in tail[] (both ping-pong)
+    DevBuf fm_phase;
+    size_t tail_cap = 0;  // OVERLAP: samples per stream in tail[]
     // FOURIER: window values (Flt) and twiddles of the current chunk length
     DevBuf fwin, ftw;
     size_t fwin_n = 0;
@@ -219,6 +230,7 @@ struct rr_chain {
     cudaStream_t stream = nullptr;
     DevBuf host_in, host_out;  // device staging of rr_chain_push
     std::string plan;
+    uint64_t samples_lost = 0;  // SamplesLost events generated by Rechunker / Overlapper stages
     bool allow_poly = true;  // rr_chain_set_fast_path
     bool allow_poly2 = true; // RR_DISABLE_POLY2=1: keep the generic polyphase kernel (k_poly) for f32 too
     bool allow_front = true; // RR_DISABLE_FRONT=1: k_poly2 on all P branches instead of the rank-reduced front end
@@ -276,7 +288,41 @@ int advance_stage(const rr_stage_desc& d, StageHost& h, const Shape& in, StageAc
             break;
         case RR_STAGE_GAIN:
         case RR_STAGE_FOURIER:
+        case RR_STAGE_FMMOD:
             break;
+        case RR_STAGE_RECHUNK: {
+            // chunks.rs:71-79: a partial chunk of another sample rate is dropped and reported
+            if (h.rc_pending > 0 && !(h.rc_rate == in.rate)) {
+                h.rc_pending = 0;
+                a.lost = true;
+            }
+            h.rc_rate = in.rate;
+            const size_t ocl = (size_t)d.output_chunk_len;
+            a.pending_before = h.rc_pending;
+            a.n_new = in.len();
+            const size_t total = h.rc_pending + a.n_new;
+            a.out.chunk_len = ocl;
+            a.out.n_chunks = total / ocl;
+            h.rc_pending = total - a.out.n_chunks * ocl;
+            break;
+        }
+        case RR_STAGE_OVERLAP: {
+            const size_t k = (size_t)d.chunk_count;
+            if (h.ov_hist > 0 && (h.ov_len != in.chunk_len || !(h.ov_rate == in.rate)))
+                return fail(RR_ERR_UNSUPPORTED, "Overlapper: the chunks of one history must share length and sample rate");
+            a.pending_before = h.ov_hist;
+            const size_t tot = h.ov_hist + in.n_chunks;
+            a.out.chunk_len = k * in.chunk_len;
+            a.out.n_chunks = tot >= k ? tot - (k - 1) : 0;
+            // chunks.rs:207-214: the length-weighted mean of the k sample rates, evaluated the same way
+            double acc = 0.0;
+            for (size_t i = 0; i < k; ++i) acc += in.rate * (double)in.chunk_len;
+            a.out.rate = acc / (double)(k * in.chunk_len);
+            h.ov_hist = std::min(k - 1, tot);
+            h.ov_len = in.chunk_len;
+            h.ov_rate = in.rate;
+            break;
+        }
         case RR_STAGE_FMDEMOD:
             a.first_is_history = !h.fm_has_prev;
             h.fm_has_prev = true;
@@ -347,6 +393,54 @@ int advance_stage(const rr_stage_desc& d, StageHost& h, const Shape& in, StageAc
             return fail(RR_ERR_INVALID, "unknown stage kind");
     }
     *act = a;
+    return RR_OK;
+}
+
+// An interrupt event reaches stage `h` (filters.rs:262-267, modulation.rs:133-138, chunks.rs:84-91,226-233).
+// Returns the number of SamplesLost events the stage sends on top of it.
+int stage_event(const rr_stage_desc& d, StageHost& h, bool* interrupt) {
+    int lost = 0;
+    switch (d.kind) {
+        case RR_STAGE_RECHUNK:  // any event: the partial chunk is dropped and reported
+            if (h.rc_pending > 0) {
+                h.rc_pending = 0;
+                lost = 1;
+                *interrupt = true;
+            }
+            break;
+        case RR_STAGE_OVERLAP:  // any event: history cleared, SamplesLost always sent
+            h.ov_hist = 0;
+            lost = 1;
+            *interrupt = true;
+            break;
+        case RR_STAGE_FILTER:
+            if (*interrupt) h.f_seg = 0;
+            break;
+        case RR_STAGE_FMDEMOD:
+            if (*interrupt) h.fm_has_prev = false;
+            break;
+        default:
+            break;
+    }
+    return lost;
+}
+
+// output shape of a push without touching any state (capacity check, rr_chain_max_output)
+int dry_shape(const rr_chain* c, const Shape& in, Shape* out) {
+    std::vector<StageHost> hs;
+    hs.reserve(c->st.size());
+    for (const auto& s : c->st) hs.push_back(s.h);
+    Shape sh = in;
+    for (size_t i = 0; i < hs.size(); ++i) {
+        StageAct a;
+        RR_TRY(advance_stage(c->st[i].d, hs[i], sh, &a));
+        if (a.lost) {
+            bool intr = true;
+            for (size_t j = i + 1; j < hs.size(); ++j) stage_event(c->st[j].d, hs[j], &intr);
+        }
+        sh = a.out;
+    }
+    *out = sh;
     return RR_OK;
 }
 
@@ -1089,13 +1183,8 @@ int run_push(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_chunks,
 
     // ---- dry run: output shape + capacity before anything is touched -------
     {
-        Shape sh = in;
-        for (int i = 0; i < ns; ++i) {
-            StageHost h = c->st[i].h;
-            StageAct a;
-            RR_TRY(advance_stage(c->st[i].d, h, sh, &a));
-            sh = a.out;
-        }
+        Shape sh;
+        RR_TRY(dry_shape(c, in, &sh));
         if (sh.len() > out_capacity) return fail(RR_ERR_CAPACITY, "output buffer too small for this push");
         if (sh.len() > out_stride && S > 1) return fail(RR_ERR_INVALID, "out_stride smaller than the produced samples");
     }
@@ -1125,6 +1214,11 @@ int run_push(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_chunks,
         }
         StageAct a;
         RR_TRY(advance_stage(s.d, s.h, cur.sh, &a));
+        if (a.lost) {  // SamplesLost travels ahead of the samples (chunks.rs:71-79)
+            ++c->samples_lost;
+            bool intr = true;
+            for (int j = i + 1; j < ns; ++j) c->samples_lost += (uint64_t)stage_event(c->st[j].d, c->st[j].h, &intr);
+        }
         if (!a.active) {
             cur.sh = a.out;
             continue;
@@ -1194,6 +1288,82 @@ int run_push(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_chunks,
                 cur.stride = d.stride;
                 cur.sh = a.out;
                 plan += "fourier";
+                break;
+            }
+            case RR_STAGE_FMMOD: {
+                Dest d;
+                RR_TRY(pick_dest<T>(c, s, last, dev_out, (long long)out_stride, (size_t)len, &d));
+                RR_TRY(s.fm_phase.ensure((size_t)S * sizeof(T), true));
+                const double factor = s.d.deviation / cur.sh.rate * 6.283185307179586476925286766559;  // modulation.rs:44
+                RR_LAUNCH(1, rr::launch_fmmod<T>(cur.p, cur.stride, d.p, d.stride, len, S, s.fm_phase.p, factor, c->ctx->sm_count, st));
+                cur.p = d.p;
+                cur.stride = d.stride;
+                cur.sh = a.out;
+                plan += "fmmod";
+                break;
+            }
+            case RR_STAGE_RECHUNK: {
+                // the sequence [partial chunk | pushed samples]: whole chunks go on, the rest is kept (chunks.rs:100-164)
+                const size_t p0 = a.pending_before, emit = a.out.len(), n_new = a.n_new;
+                const size_t from_p = std::min(p0, emit), from_in = emit - from_p;
+                RR_TRY(obuf_reserve<T>(c, s, std::max<size_t>((size_t)s.d.output_chunk_len, p0 + (emit ? 0 : n_new)), p0));
+                const long long ocap = (long long)s.obuf_cap;
+                const char* pend = (const char*)s.obuf[s.obuf_cur].p;
+                const char* inp = (const char*)cur.p;
+                const long long in_str = cur.stride;
+                const size_t esz = 2 * sizeof(T);
+                if (emit == 0) {
+                    RR_LAUNCH(1, rr::launch_copy2d<T>(inp, in_str, (char*)s.obuf[s.obuf_cur].p + p0 * esz, ocap, (long long)n_new, S, st));
+                    cur.sh = a.out;
+                    plan += "rechunk(hold)";
+                    break;
+                }
+                char* other = (char*)s.obuf[s.obuf_cur ^ 1].p;
+                if (p0 == 0 && !last) {
+                    plan += "rechunk(view)";  // the pushed buffer itself, seen with the new chunk length
+                } else {
+                    Dest d;
+                    RR_TRY(pick_dest<T>(c, s, last, dev_out, (long long)out_stride, emit, &d));
+                    if (from_p) RR_LAUNCH(1, rr::launch_copy2d<T>(pend, ocap, d.p, d.stride, (long long)from_p, S, st));
+                    if (from_in) RR_LAUNCH(1, rr::launch_copy2d<T>(inp, in_str, (char*)d.p + from_p * esz, d.stride, (long long)from_in, S, st));
+                    cur.p = d.p;
+                    cur.stride = d.stride;
+                    plan += "rechunk";
+                }
+                if (p0 > from_p) RR_LAUNCH(1, rr::launch_copy2d<T>(pend + from_p * esz, ocap, other, ocap, (long long)(p0 - from_p), S, st));
+                if (n_new > from_in)
+                    RR_LAUNCH(1, rr::launch_copy2d<T>(inp + from_in * esz, in_str, other + (p0 - from_p) * esz, ocap, (long long)(n_new - from_in), S, st));
+                s.obuf_cur ^= 1;
+                cur.sh = a.out;
+                break;
+            }
+            case RR_STAGE_OVERLAP: {
+                const size_t k = (size_t)s.d.chunk_count, n = cur.sh.chunk_len, h0 = a.pending_before;
+                const size_t tot = h0 + cur.sh.n_chunks, n_out = a.out.n_chunks, h1 = std::min(k - 1, tot);
+                if ((k - 1) * n > s.tail_cap || (k > 1 && (!s.tail[0].p || !s.tail[1].p))) {
+                    // only reached with an empty history (the history's chunk length is fixed while it holds chunks)
+                    RR_TRY(s.tail[0].ensure((size_t)S * (k - 1) * n * 2 * sizeof(T)));
+                    RR_TRY(s.tail[1].ensure((size_t)S * (k - 1) * n * 2 * sizeof(T)));
+                    s.tail_cap = (k - 1) * n;
+                }
+                const void* hist = s.tail[s.tail_cur].p;
+                const void* inp = cur.p;
+                const long long in_str = cur.stride;
+                if (n_out > 0) {
+                    Dest d;
+                    RR_TRY(pick_dest<T>(c, s, last, dev_out, (long long)out_stride, a.out.len(), &d));
+                    RR_LAUNCH(1, rr::launch_overlap<T>(hist, (long long)s.tail_cap, (long long)(h0 * n), inp, in_str, d.p, d.stride, (long long)n_out,
+                                                       (long long)(k * n), (long long)n, 0, S, st));
+                    cur.p = d.p;
+                    cur.stride = d.stride;
+                }
+                if (h1 > 0) {
+                    RR_LAUNCH(1, rr::launch_overlap<T>(hist, (long long)s.tail_cap, (long long)(h0 * n), inp, in_str, s.tail[s.tail_cur ^ 1].p,
+                                                       (long long)s.tail_cap, 1, (long long)(h1 * n), 0, (long long)((tot - h1) * n), S, st));
+                    s.tail_cur ^= 1;
+                }
+                cur.sh = a.out;
+                plan += "overlap";
                 break;
             }
             case RR_STAGE_FMDEMOD: {
@@ -1565,8 +1735,15 @@ int rr_chain_create(rr_ctx* ctx, const rr_chain_desc* desc, rr_chain** out) {
                 if (!(d.quality >= 1.0)) return fail(RR_ERR_INVALID, "quality must be >= 1.0");
                 break;
             case RR_STAGE_FMDEMOD:
+            case RR_STAGE_FMMOD:
             case RR_STAGE_GAIN:
             case RR_STAGE_FOURIER:
+                break;
+            case RR_STAGE_RECHUNK:  // chunks.rs:58
+                if (d.output_chunk_len == 0) return fail(RR_ERR_INVALID, "chunk length must be positive");
+                break;
+            case RR_STAGE_OVERLAP:  // chunks.rs:195
+                if (d.chunk_count <= 0) return fail(RR_ERR_INVALID, "chunk count must be positive");
                 break;
             default:
                 return fail(RR_ERR_INVALID, "rr_chain_create: unknown stage kind");
@@ -1603,7 +1780,7 @@ int rr_chain_destroy(rr_chain* c) {
     for (auto& s : c->st) {
         DevBuf* bufs[] = {&s.nco_d, &s.hperm, &s.tw, &s.hist2[0], &s.hist2[1], &s.ztmp, &s.gtab, &s.twK, &s.big_h, &s.big_twA, &s.big_twB, &s.big_scratch,
                           &s.ir, &s.tail[0], &s.tail[1], &s.obuf[0], &s.obuf[1], &s.fm_prev, &s.fm_last, &s.out,
-                          &s.gtab2, &s.twK2, &s.acoef, &s.gtab3, &s.ubuf, &s.fwin, &s.ftw};
+                          &s.gtab2, &s.twK2, &s.acoef, &s.gtab3, &s.ubuf, &s.fwin, &s.ftw, &s.fm_phase};
         for (DevBuf* b : bufs) b->release();
     }
     c->host_in.release();
@@ -1675,8 +1852,16 @@ int rr_chain_update_filter(rr_chain* c, int stage, rr_freq_resp_fn f, void* f_us
 }
 int rr_chain_set_deviation(rr_chain* c, int stage, double deviation) {
     Stage* s = nullptr;
-    RR_TRY(stage_of(c, stage, RR_STAGE_FMDEMOD, &s));
+    if (c && stage >= 0 && stage < (int)c->st.size() && c->st[(size_t)stage].d.kind == RR_STAGE_FMMOD) RR_TRY(stage_of(c, stage, RR_STAGE_FMMOD, &s));
+    else RR_TRY(stage_of(c, stage, RR_STAGE_FMDEMOD, &s));
     s->d.deviation = deviation;
+    return RR_OK;
+}
+int rr_chain_set_output_chunk_len(rr_chain* c, int stage, size_t output_chunk_len) {
+    Stage* s = nullptr;
+    RR_TRY(stage_of(c, stage, RR_STAGE_RECHUNK, &s));
+    if (output_chunk_len == 0) return fail(RR_ERR_INVALID, "chunk length must be positive");  // chunks.rs:172
+    s->d.output_chunk_len = output_chunk_len;
     return RR_OK;
 }
 int rr_chain_set_gain(rr_chain* c, int stage, double gain) {
@@ -1688,13 +1873,12 @@ int rr_chain_set_gain(rr_chain* c, int stage, double gain) {
 
 int rr_chain_event(rr_chain* c, int is_interrupt) {
     if (!c) return fail(RR_ERR_INVALID, "null chain");
-    if (!is_interrupt) return RR_OK;  // plain events are forwarded untouched by every block
-    for (auto& s : c->st) {
-        if (s.d.kind == RR_STAGE_FILTER) s.h.f_seg = 0;             // filters.rs:262-267
-        if (s.d.kind == RR_STAGE_FMDEMOD) s.h.fm_has_prev = false;  // modulation.rs:133-138
-    }
+    // plain events pass every block untouched until a Rechunker / Overlapper turns them into an interrupt
+    bool intr = is_interrupt != 0;
+    for (auto& s : c->st) c->samples_lost += (uint64_t)stage_event(s.d, s.h, &intr);
     return RR_OK;
 }
+uint64_t rr_chain_samples_lost_count(rr_chain* c) { return c ? c->samples_lost : 0; }
 
 size_t rr_chain_max_output(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_chunks) {
     if (!c) return 0;
@@ -1702,13 +1886,9 @@ size_t rr_chain_max_output(rr_chain* c, double sample_rate, size_t chunk_len, si
     sh.chunk_len = chunk_len;
     sh.n_chunks = n_chunks;
     sh.rate = sample_rate;
-    for (auto& s : c->st) {
-        StageHost h = s.h;
-        StageAct a;
-        if (advance_stage(s.d, h, sh, &a) != RR_OK) return 0;
-        sh = a.out;
-    }
-    return sh.len();
+    Shape out;
+    if (dry_shape(c, sh, &out) != RR_OK) return 0;
+    return out.len();
 }
 
 int rr_chain_push_device(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_chunks, const void* dev_in, size_t in_stride,

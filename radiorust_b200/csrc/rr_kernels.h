@@ -88,6 +88,17 @@ cudaError_t launch_fmdemod(const void* in, long long in_stride, void* out, long 
                            int n_streams, void* prev_sample, void* last_output, int has_prev, double factor,
                            cudaStream_t st);
 
+// FmMod (src/blocks/modulation.rs:46-51): phase[s] is the accumulator carried across pushes (Flt)
+template <typename T>
+cudaError_t launch_fmmod(const void* in, long long in_stride, void* out, long long out_stride, long long len, int n_streams, void* phase,
+                         double factor, int sm_count, cudaStream_t st);
+
+// Overlapper gather (src/blocks/chunks.rs:203-225): out[j*span + t] = seq[base + j*hop + t], seq = a (a_len samples) | b
+template <typename T>
+cudaError_t launch_overlap(const void* a, long long a_stride, long long a_len, const void* b, long long b_stride, void* out,
+                           long long out_stride, long long n_out, long long span, long long hop, long long base, int n_streams,
+                           cudaStream_t st);
+
 // Fourier analysis block (src/blocks/analysis.rs:60-132): out chunk = FFT_n(window * in chunk), bin k at
 // (k + rot) mod n.  Three-pass FFT for the plan sizes, direct DFT for any other n <= kFourierDirectMax.
 constexpr int kFourierDirectMax = 4096;

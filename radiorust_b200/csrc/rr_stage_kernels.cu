@@ -2,9 +2,40 @@
 // interpolator, FM discriminator, strided copy.  Used when a chain cannot be
 // fused (large FFTs, long resampler kernels, FM chains) and as the reference
 // implementation of each stage on the device.  sm_100a.
+#include <algorithm>
+
 #include "rr_chain_os.cuh"
 
 namespace rr {
+
+// Element-wise pass over one stream: every thread keeps kMapUnroll independent 8/16-byte loads in flight
+// (coalesced: consecutive threads, consecutive samples) before it stores; f(t, sample) -> sample.
+constexpr int kMapUnroll = 4;
+template <typename T, typename F>
+__device__ __forceinline__ void map_stream(const cx<T>* __restrict__ src, cx<T>* __restrict__ dst, long long len, F f) {
+    const long long tile = (long long)blockDim.x * kMapUnroll;
+    for (long long t0 = (long long)blockIdx.x * tile + threadIdx.x; t0 < len; t0 += (long long)gridDim.x * tile) {
+        cx<T> v[kMapUnroll];
+#pragma unroll
+        for (int u = 0; u < kMapUnroll; ++u) {
+            const long long t = t0 + (long long)u * blockDim.x;
+            if (t < len) v[u] = ld_cx(&src[t]);
+        }
+#pragma unroll
+        for (int u = 0; u < kMapUnroll; ++u) {
+            const long long t = t0 + (long long)u * blockDim.x;
+            if (t < len) st_cx(&dst[t], f(t, v[u]));
+        }
+    }
+}
+// CTAs along x for `len` samples per stream when the grid's y dimension runs over n_streams streams
+inline unsigned map_grid_x(long long len, int n_streams) {
+    long long bx = (len + 256 * kMapUnroll - 1) / (256 * kMapUnroll);
+    const long long cap = std::max<long long>(1, (1LL << 16) / std::max(1, n_streams));  // ~64 K CTAs in all
+    if (bx > cap) bx = cap;
+    if (bx > 4096) bx = 4096;
+    return (unsigned)bx;
+}
 
 // ---------------------------------------------------------------------------
 // FreqShifter hot loop, src/blocks/transform.rs:341-348, with phase_vec[idx]
@@ -19,12 +50,11 @@ __global__ void __launch_bounds__(256) k_freqshift(const cx<T>* __restrict__ in,
     const cx<T>* src = in + (long long)s * in_stride;
     cx<T>* dst = out + (long long)s * out_stride;
     const T start = (T)ns.start_phase;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < len; t += (long long)gridDim.x * blockDim.x) {
+    map_stream<T>(src, dst, len, [&](long long t, cx<T> v) {
         const uint32_t k = (uint32_t)(((unsigned long long)ns.idx + (unsigned long long)(nco_offset + t)) % ns.denom);
         const uint32_t i = mulmod_u32(ns.numer_abs, k, ns.denom);
-        const cx<T> ph = nco_phasor<T>(i, ns.denom, ns.sign, start);
-        st_cx(&dst[t], cmul(ld_cx(&src[t]), ph));
-    }
+        return cmul(v, nco_phasor<T>(i, ns.denom, ns.sign, start));
+    });
 }
 
 __global__ void k_nco_advance(NcoStream* nco, int n_streams, long long len) {
@@ -44,9 +74,7 @@ template <typename T>
 cudaError_t launch_freqshift(const void* in, long long in_stride, void* out, long long out_stride, long long len,
                              int n_streams, const NcoStream* nco, long long nco_offset, cudaStream_t st) {
     if (len <= 0) return cudaSuccess;
-    long long bx = (len + 255) / 256;
-    if (bx > 4096) bx = 4096;
-    dim3 grid((unsigned)bx, (unsigned)n_streams);
+    dim3 grid(map_grid_x(len, n_streams), (unsigned)n_streams);
     k_freqshift<T><<<grid, 256, 0, st>>>(reinterpret_cast<const cx<T>*>(in), in_stride, reinterpret_cast<cx<T>*>(out),
                                          out_stride, len, nco, nco_offset);
     return cudaGetLastError();
@@ -61,16 +89,13 @@ __global__ void __launch_bounds__(256) k_gain(const cx<T>* __restrict__ in, long
     const int s = blockIdx.y;
     const cx<T>* src = in + (long long)s * in_stride;
     cx<T>* dst = out + (long long)s * out_stride;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < len; t += (long long)gridDim.x * blockDim.x)
-        st_cx(&dst[t], cscale(ld_cx(&src[t]), gain));
+    map_stream<T>(src, dst, len, [&](long long, cx<T> v) { return cscale(v, gain); });
 }
 template <typename T>
 cudaError_t launch_gain(const void* in, long long in_stride, void* out, long long out_stride, long long len,
                         int n_streams, double gain, cudaStream_t st) {
     if (len <= 0) return cudaSuccess;
-    long long bx = (len + 255) / 256;
-    if (bx > 4096) bx = 4096;
-    dim3 grid((unsigned)bx, (unsigned)n_streams);
+    dim3 grid(map_grid_x(len, n_streams), (unsigned)n_streams);
     k_gain<T><<<grid, 256, 0, st>>>(reinterpret_cast<const cx<T>*>(in), in_stride, reinterpret_cast<cx<T>*>(out),
                                     out_stride, len, (T)gain);
     return cudaGetLastError();
@@ -82,16 +107,13 @@ __global__ void __launch_bounds__(256) k_copy2d(const cx<T>* __restrict__ in, lo
     const int s = blockIdx.y;
     const cx<T>* src = in + (long long)s * in_stride;
     cx<T>* dst = out + (long long)s * out_stride;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < len; t += (long long)gridDim.x * blockDim.x)
-        st_cx(&dst[t], ld_cx(&src[t]));
+    map_stream<T>(src, dst, len, [](long long, cx<T> v) { return v; });
 }
 template <typename T>
 cudaError_t launch_copy2d(const void* in, long long in_stride, void* out, long long out_stride, long long len,
                           int n_streams, cudaStream_t st) {
     if (len <= 0) return cudaSuccess;
-    long long bx = (len + 255) / 256;
-    if (bx > 4096) bx = 4096;
-    dim3 grid((unsigned)bx, (unsigned)n_streams);
+    dim3 grid(map_grid_x(len, n_streams), (unsigned)n_streams);
     k_copy2d<T><<<grid, 256, 0, st>>>(reinterpret_cast<const cx<T>*>(in), in_stride, reinterpret_cast<cx<T>*>(out),
                                       out_stride, len);
     return cudaGetLastError();
@@ -227,17 +249,12 @@ __global__ void __launch_bounds__(256) k_fmdemod(const cx<T>* __restrict__ in, l
     const int s = blockIdx.y;
     const cx<T>* src = in + (long long)s * in_stride;
     cx<T>* dst = out + (long long)s * out_stride;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < len; t += (long long)gridDim.x * blockDim.x) {
-        cx<T> o;
-        if (t == 0 && !has_prev) {
-            o = ld_cx(&last_output[s]);  // repeat the previous output value (modulation.rs:119-124)
-        } else {
-            const cx<T> prev = (t == 0) ? ld_cx(&prev_sample[s]) : ld_cx(&src[t - 1]);
-            const cx<T> p = cmulc(ld_cx(&src[t]), prev);
-            o = cx<T>(atan2_t<T>(p.y, p.x) * factor, (T)0);
-        }
-        st_cx(&dst[t], o);
-    }
+    map_stream<T>(src, dst, len, [&](long long t, cx<T> v) {
+        if (t == 0 && !has_prev) return ld_cx(&last_output[s]);  // repeat the previous output value (modulation.rs:119-124)
+        const cx<T> prev = (t == 0) ? ld_cx(&prev_sample[s]) : ld_cx(&src[t - 1]);  // the neighbour's sample: an L1 hit
+        const cx<T> p = cmulc(v, prev);
+        return cx<T>(atan2_t<T>(p.y, p.x) * factor, (T)0);
+    });
 }
 template <typename T>
 __global__ void k_fm_state(const cx<T>* __restrict__ in, long long in_stride, const cx<T>* __restrict__ out,
@@ -253,9 +270,7 @@ cudaError_t launch_fmdemod(const void* in, long long in_stride, void* out, long 
                            int n_streams, void* prev_sample, void* last_output, int has_prev, double factor,
                            cudaStream_t st) {
     if (len <= 0) return cudaSuccess;
-    long long bx = (len + 255) / 256;
-    if (bx > 4096) bx = 4096;
-    dim3 grid((unsigned)bx, (unsigned)n_streams);
+    dim3 grid(map_grid_x(len, n_streams), (unsigned)n_streams);
     k_fmdemod<T><<<grid, 256, 0, st>>>(reinterpret_cast<const cx<T>*>(in), in_stride, reinterpret_cast<cx<T>*>(out),
                                        out_stride, len, reinterpret_cast<const cx<T>*>(prev_sample),
                                        reinterpret_cast<const cx<T>*>(last_output), has_prev, (T)factor);

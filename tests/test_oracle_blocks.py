@@ -199,3 +199,60 @@ def test_chain_c1_shapes():
     # events pass through in-band and in order
     msgs = ch.push(o.Event("x", False))
     assert len(msgs) == 1 and isinstance(msgs[0], o.Event)
+
+
+# ---------------------------------------------------------------------------------------------------
+# chunks.rs: Rechunker / Overlapper
+# ---------------------------------------------------------------------------------------------------
+def test_rechunker_reference_test():
+    """chunks.rs:250-271 (`test_rechunker`): a 4096-sample chunk into Rechunker(1024) -> the first message out is a
+    1024-sample chunk (and so are the other three)."""
+    r = o.Rechunker(1024)
+    outs = r.process(o.Samples(1.0, np.zeros(4096, dtype=np.uint8)))
+    assert [len(m.chunk) for m in outs] == [1024] * 4 and all(m.sample_rate == 1.0 for m in outs)
+
+
+def test_rechunker_is_a_fifo_and_reports_losses():
+    rng = np.random.default_rng(3)
+    x = rng.integers(0, 1 << 30, 5000)
+    r = o.Rechunker(128)
+    got, pos = [], 0
+    for n in [100, 30, 7, 7, 7, 1000, 64, 36, 256, 5, 1285, 1103]:
+        for m in r.process(o.Samples(8000.0, x[pos:pos + n])):
+            assert len(m.chunk) == 128
+            got.append(m.chunk)
+        pos += n
+    assert pos == 3900 and np.array_equal(np.concatenate(got), x[: 128 * (3900 // 128)])
+    assert r.patchwork is not None and len(r.patchwork[1]) == 3900 % 128
+    # an event drops the partial chunk and is preceded by SamplesLost (chunks.rs:84-91) ...
+    ev = o.Event("retune", False)
+    outs = r.process(ev)
+    assert outs == [o.SAMPLES_LOST, ev] and o.SAMPLES_LOST.is_interrupt() and r.patchwork is None
+    assert r.process(ev) == [ev]  # ... only when there is one
+    # so does a sample-rate change (chunks.rs:71-79)
+    r.process(o.Samples(8000.0, x[:50]))
+    outs = r.process(o.Samples(16000.0, x[:200]))
+    assert outs[0] is o.SAMPLES_LOST and np.array_equal(outs[1].chunk, x[:128]) and outs[1].sample_rate == 16000.0
+    # a shorter length splits a longer partial chunk at the next input (chunks.rs:101-112)
+    r.set_output_chunk_len(20)
+    outs = r.process(o.Samples(16000.0, x[200:203]))
+    assert [len(m.chunk) for m in outs] == [20, 20, 20] and np.array_equal(np.concatenate([m.chunk for m in outs]), x[128:188])
+
+
+def test_overlapper():
+    ov = o.Overlapper(3)
+    chunks = [np.arange(4) + 10 * i for i in range(6)]
+    assert ov.process(o.Samples(2.0, chunks[0])) == [] and ov.process(o.Samples(2.0, chunks[1])) == []
+    for i in range(2, 5):
+        (m,) = ov.process(o.Samples(2.0, chunks[i]))
+        assert np.array_equal(m.chunk, np.concatenate(chunks[i - 2:i + 1])) and m.sample_rate == 2.0
+    ev = o.Event("x", False)
+    assert ov.process(ev) == [o.SAMPLES_LOST, ev] and ov.history == []  # chunks.rs:226-233, even for plain events
+    assert ov.process(o.Samples(2.0, chunks[5])) == []
+    # mixed rates: the length-weighted mean (chunks.rs:207-214)
+    ov = o.Overlapper(2)
+    ov.process(o.Samples(1000.0, np.zeros(10)))
+    (m,) = ov.process(o.Samples(4000.0, np.zeros(30)))
+    assert m.sample_rate == (1000.0 * 10 + 4000.0 * 30) / 40 and len(m.chunk) == 40
+    (m,) = o.Overlapper(1).process(o.Samples(5.0, chunks[0]))
+    assert np.array_equal(m.chunk, chunks[0])
