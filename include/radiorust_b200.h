@@ -135,11 +135,21 @@ int rr_device_free(rr_ctx* ctx, void* p);
 int rr_memcpy_h2d(rr_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
 int rr_memcpy_d2h(rr_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
 
-/* ---- metering::level (src/metering.rs:21-30) ------------------------------ */
+/* ---- metering (src/metering.rs) ------------------------------------------ */
 /* mean square norm of every chunk of DEVICE samples: host_out[s*n_chunks + c] for chunk c of stream s
  * (stream s at dev_in + s*in_stride samples); accumulated in f64 like the reference. */
 int rr_metering_level(rr_ctx* ctx, int32_t dtype, const void* dev_in, size_t in_stride, size_t chunk_len, size_t n_chunks,
                       int n_streams, double* host_out);
+/* metering::bandwidth (src/metering.rs:42-84) of every chunk of Fourier-transformed DEVICE samples (the output
+ * of a FOURIER stage, DC at index 0): hertz that hold all but `double_percentile` of the energy,
+ * host_out[s*n_chunks + c].  n_streams <= 65535. */
+int rr_metering_bandwidth(rr_ctx* ctx, int32_t dtype, const void* dev_bins, size_t in_stride, size_t chunk_len, size_t n_chunks,
+                          int n_streams, double double_percentile, double sample_rate, double* host_out);
+/* metering::rescale_energy (src/metering.rs:93-110): `resolution` energies per chunk (Flt = float for RR_C32,
+ * double for RR_C64), host_out[(s*n_chunks + c)*resolution + o]; expects DC in the centre (center_dc).
+ * n_streams, n_chunks <= 65535. */
+int rr_metering_rescale_energy(rr_ctx* ctx, int32_t dtype, const void* dev_bins, size_t in_stride, size_t chunk_len, size_t n_chunks,
+                               int n_streams, size_t resolution, void* host_out);
 
 /* ---- design math, host only (no GPU needed) ------------------------------ */
 double rr_bessel_i0(double x);                      /* math::bessel_I0  src/math.rs:7-20 */

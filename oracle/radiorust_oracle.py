@@ -830,6 +830,76 @@ class Overlapper:
 
 
 # --------------------------------------------------------------------------
+# metering.rs -- level, bandwidth, rescale_energy (literal; pinned by the reference's tests, metering.rs:113-262)
+# --------------------------------------------------------------------------
+
+
+def _norm_sqr(x: np.ndarray) -> np.ndarray:
+    """num::Complex::norm_sqr in the sample's own precision: re*re + im*im."""
+    R = x.real.dtype.type
+    return (x.real * x.real).astype(R) + (x.imag * x.imag).astype(R)
+
+
+def level(chunk: np.ndarray) -> float:
+    """metering.rs:21-30: mean square norm, accumulated in f64 in order."""
+    acc = 0.0
+    for v in _norm_sqr(np.asarray(chunk)):
+        acc += float(v)
+    return acc / float(len(chunk))
+
+
+def bandwidth(double_percentile: float, sample_rate: float, bins: np.ndarray) -> float:
+    """metering.rs:42-84."""
+    e = [float(v) for v in _norm_sqr(np.asarray(bins))]
+    n = len(e)
+
+    def discount(energy_limit, idcs):  # :49-66
+        old_energy = 0.0
+        used_bins = 0.0
+        for idx in idcs:
+            new_energy = old_energy + e[idx]
+            if new_energy > energy_limit:
+                used_bins += (energy_limit - old_energy) / (new_energy - old_energy)
+                break
+            used_bins += 1.0
+            old_energy = new_energy
+        return used_bins
+
+    total_energy = 0.0
+    for v in e:
+        total_energy += v
+    energy_limit = total_energy * double_percentile / 2.0
+    wrap_idx = (n + 1) // 2
+    idcs = list(range(wrap_idx, n)) + list(range(0, wrap_idx))
+    used = discount(energy_limit, idcs) + discount(energy_limit, idcs[::-1])
+    bw = (float(n) - used) * sample_rate / float(n)
+    return bw if bw > 0.0 else 0.0
+
+
+def rescale_energy(resolution: int, inp: np.ndarray) -> np.ndarray:
+    """metering.rs:93-110: every operation in Flt, in the reference's order."""
+    inp = np.asarray(inp)
+    R = inp.real.dtype.type
+    n = len(inp)
+    assert n > 0
+    nsq = _norm_sqr(inp)
+    out = np.zeros(resolution, dtype=R)
+    for o in range(resolution):
+        left = R(R(R(o) / R(resolution)) * R(n))
+        right = R(R(R(R(o) + R(1)) / R(resolution)) * R(n))
+        left_floor = min(int(np.floor(left)), n - 1)
+        right_ceil = min(int(np.ceil(right)), n)
+        acc = R(0)
+        for idx in range(left_floor, right_ceil):
+            left_bounded = max(R(idx), left)
+            right_bounded = min(R(R(idx) + R(1)), right)
+            scale = R(right_bounded - left_bounded)
+            acc = R(acc + R(nsq[idx] * scale))
+        out[o] = acc
+    return out
+
+
+# --------------------------------------------------------------------------
 # A chain = blocks connected with feed_into (flow.rs:233-267); messages are
 # delivered in order, events in-band (signal.rs:170-183).
 # --------------------------------------------------------------------------

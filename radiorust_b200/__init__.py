@@ -18,7 +18,9 @@ from .chain import (  # noqa: F401
     Overlapper,
     Rechunker,
     Upsampler,
+    bandwidth,
     kernel_launch_count,
     level,
+    rescale_energy,
 )
 from ._ffi import RadiorustError  # noqa: F401

@@ -80,6 +80,8 @@ SIGNATURES = {
     "rr_memcpy_h2d": (_I, [_P, _P, _P, _SZ]),
     "rr_memcpy_d2h": (_I, [_P, _P, _P, _SZ]),
     "rr_metering_level": (_I, [_P, C.c_int32, _P, _SZ, _SZ, _SZ, _I, C.POINTER(_D)]),
+    "rr_metering_bandwidth": (_I, [_P, C.c_int32, _P, _SZ, _SZ, _SZ, _I, _D, _D, C.POINTER(_D)]),
+    "rr_metering_rescale_energy": (_I, [_P, C.c_int32, _P, _SZ, _SZ, _SZ, _I, _SZ, _P]),
     "rr_bessel_i0": (_D, [_D]),
     "rr_sinc": (_D, [_D]),
     "rr_kaiser_rel_with_beta": (_D, [_D, _D]),

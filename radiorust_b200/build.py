@@ -47,6 +47,7 @@ def translation_units():
         ("rr_chain.o", "rr_chain.cu", []),
         ("rr_stage_kernels.o", "rr_stage_kernels.cu", []),
         ("rr_chunk_kernels.o", "rr_chunk_kernels.cu", []),
+        ("rr_metering.o", "rr_metering.cu", []),
         ("rr_big_os.o", "rr_big_os.cu", []),
         ("rr_chain_os_dispatch.o", "rr_chain_os_dispatch.cu", []),
         ("rr_poly.o", "rr_poly.cu", []),

@@ -307,7 +307,7 @@ class Chain:
         assert x.dtype == self.cdtype and x.strides[1] == x.itemsize
         total = x.shape[1]
         assert total % chunk_len == 0
-        n_chunks = total // chunk_len
+        n_chunks = total // chunk_len if chunk_len else 0
         cap = self.max_output(sample_rate, chunk_len, n_chunks)
         if out is None:
             out = np.empty((self.n_streams, max(cap, 1)), dtype=self.cdtype)
@@ -391,7 +391,7 @@ def level(ctx: Context, x: np.ndarray, chunk_len: int) -> np.ndarray:
     if x.dtype not in (np.complex64, np.complex128):
         raise TypeError("complex64 or complex128 samples")
     S, total = x.shape
-    n_chunks = total // chunk_len
+    n_chunks = total // chunk_len if chunk_len else 0
     dev = C.c_void_p()
     check(lib.rr_device_alloc(ctx._h, max(x.nbytes, 16), C.byref(dev)))
     try:
@@ -402,6 +402,56 @@ def level(ctx: Context, x: np.ndarray, chunk_len: int) -> np.ndarray:
     finally:
         lib.rr_device_free(ctx._h, dev)
     return out
+
+
+def _with_device_copy(ctx: Context, x: np.ndarray, fn):
+    lib = _ffi.load()
+    dev = C.c_void_p()
+    check(lib.rr_device_alloc(ctx._h, max(x.nbytes, 16), C.byref(dev)))
+    try:
+        check(lib.rr_memcpy_h2d(ctx._h, dev, x.ctypes.data_as(C.c_void_p), x.nbytes))
+        return fn(lib, dev)
+    finally:
+        lib.rr_device_free(ctx._h, dev)
+
+
+def _bins_2d(bins: np.ndarray) -> np.ndarray:
+    bins = np.ascontiguousarray(np.atleast_2d(bins))
+    if bins.dtype not in (np.complex64, np.complex128):
+        raise TypeError("complex64 or complex128 samples")
+    return bins
+
+
+def bandwidth(ctx: Context, double_percentile: float, sample_rate: float, bins: np.ndarray, chunk_len: int) -> np.ndarray:
+    """``metering::bandwidth`` (metering.rs:42-84) of every chunk of Fourier-transformed ``bins``
+    ([streams, samples]) on the device.  Returns hertz, [streams, chunks]."""
+    bins = _bins_2d(bins)
+    S, total = bins.shape
+    n_chunks = total // chunk_len if chunk_len else 0
+    out = np.zeros((S, n_chunks), dtype=np.float64)
+
+    def run(lib, dev):
+        check(lib.rr_metering_bandwidth(ctx._h, _ffi.RR_C32 if bins.dtype == np.complex64 else _ffi.RR_C64, dev, total, chunk_len, n_chunks,
+                                        S, float(double_percentile), float(sample_rate), out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    return _with_device_copy(ctx, bins, run)
+
+
+def rescale_energy(ctx: Context, resolution: int, bins: np.ndarray, chunk_len: int) -> np.ndarray:
+    """``metering::rescale_energy`` (metering.rs:93-110) of every chunk of ``bins`` on the device.
+    Returns [streams, chunks, resolution] in the real type of ``bins``."""
+    bins = _bins_2d(bins)
+    S, total = bins.shape
+    n_chunks = total // chunk_len if chunk_len else 0
+    out = np.zeros((S, n_chunks, resolution), dtype=np.float32 if bins.dtype == np.complex64 else np.float64)
+
+    def run(lib, dev):
+        check(lib.rr_metering_rescale_energy(ctx._h, _ffi.RR_C32 if bins.dtype == np.complex64 else _ffi.RR_C64, dev, total, chunk_len,
+                                             n_chunks, S, int(resolution), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    return _with_device_copy(ctx, bins, run)
 
 
 def kernel_launch_count() -> int:

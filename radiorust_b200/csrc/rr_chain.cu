@@ -1593,6 +1593,53 @@ int rr_metering_level(rr_ctx* ctx, int32_t dtype, const void* dev_in, size_t in_
     return RR_OK;
 }
 
+int rr_metering_bandwidth(rr_ctx* ctx, int32_t dtype, const void* dev_bins, size_t in_stride, size_t chunk_len, size_t n_chunks,
+                          int n_streams, double double_percentile, double sample_rate, double* host_out) {
+    if (!ctx || !host_out || (!dev_bins && n_chunks)) return fail(RR_ERR_INVALID, "rr_metering_bandwidth: null argument");
+    if (dtype != RR_C32 && dtype != RR_C64) return fail(RR_ERR_INVALID, "rr_metering_bandwidth: bad dtype");
+    if (n_streams < 1 || n_streams > 65535 || chunk_len == 0) return fail(RR_ERR_INVALID, "rr_metering_bandwidth: empty chunk or bad stream count");
+    if (n_chunks == 0) return RR_OK;
+    RR_CUDA(cudaSetDevice(ctx->device));
+    DevBuf out;
+    RR_TRY(out.ensure(sizeof(double) * n_chunks * (size_t)n_streams));
+    cudaError_t e = dtype == RR_C32 ? rr::launch_bandwidth<float>(dev_bins, (long long)in_stride, (long long)chunk_len, (long long)n_chunks, n_streams,
+                                                                  double_percentile, sample_rate, (double*)out.p, nullptr)
+                                    : rr::launch_bandwidth<double>(dev_bins, (long long)in_stride, (long long)chunk_len, (long long)n_chunks, n_streams,
+                                                                   double_percentile, sample_rate, (double*)out.p, nullptr);
+    if (e == cudaSuccess) {
+        g_launches.fetch_add(1);
+        e = cudaMemcpy(host_out, out.p, sizeof(double) * n_chunks * (size_t)n_streams, cudaMemcpyDeviceToHost);
+    }
+    out.release();
+    if (e != cudaSuccess) return fail_cuda(e, "rr_metering_bandwidth");
+    return RR_OK;
+}
+
+int rr_metering_rescale_energy(rr_ctx* ctx, int32_t dtype, const void* dev_bins, size_t in_stride, size_t chunk_len, size_t n_chunks,
+                               int n_streams, size_t resolution, void* host_out) {
+    if (!ctx || !host_out || (!dev_bins && n_chunks)) return fail(RR_ERR_INVALID, "rr_metering_rescale_energy: null argument");
+    if (dtype != RR_C32 && dtype != RR_C64) return fail(RR_ERR_INVALID, "rr_metering_rescale_energy: bad dtype");
+    if (chunk_len == 0) return fail(RR_ERR_INVALID, "rr_metering_rescale_energy: empty input (metering.rs:98 asserts n > 0)");
+    if (n_streams < 1 || n_streams > 65535 || n_chunks > 65535) return fail(RR_ERR_INVALID, "rr_metering_rescale_energy: at most 65535 streams and chunks per call");
+    if (n_chunks == 0 || resolution == 0) return RR_OK;
+    RR_CUDA(cudaSetDevice(ctx->device));
+    const size_t fsz = dtype == RR_C32 ? sizeof(float) : sizeof(double);
+    const size_t bytes = fsz * n_chunks * (size_t)n_streams * resolution;
+    DevBuf out;
+    RR_TRY(out.ensure(bytes));
+    cudaError_t e = dtype == RR_C32 ? rr::launch_rescale_energy<float>(dev_bins, (long long)in_stride, (long long)chunk_len, (long long)n_chunks,
+                                                                       n_streams, (long long)resolution, out.p, nullptr)
+                                    : rr::launch_rescale_energy<double>(dev_bins, (long long)in_stride, (long long)chunk_len, (long long)n_chunks,
+                                                                        n_streams, (long long)resolution, out.p, nullptr);
+    if (e == cudaSuccess) {
+        g_launches.fetch_add(1);
+        e = cudaMemcpy(host_out, out.p, bytes, cudaMemcpyDeviceToHost);
+    }
+    out.release();
+    if (e != cudaSuccess) return fail_cuda(e, "rr_metering_rescale_energy");
+    return RR_OK;
+}
+
 // ---- design math ------------------------------------------------------------
 double rr_bessel_i0(double x) { return rr::bessel_i0(x); }
 double rr_sinc(double x) { return rr::sinc(x); }

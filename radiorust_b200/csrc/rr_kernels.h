@@ -112,6 +112,15 @@ template <typename T>
 cudaError_t launch_level(const void* in, long long in_stride, long long chunk_len, long long n_chunks, int n_streams, double* out,
                          cudaStream_t st);
 
+// metering::bandwidth (src/metering.rs:42-84) of every chunk of Fourier-transformed samples: out[s*n_chunks + c] (f64, device)
+template <typename T>
+cudaError_t launch_bandwidth(const void* in, long long in_stride, long long chunk_len, long long n_chunks, int n_streams,
+                             double double_percentile, double sample_rate, double* out, cudaStream_t st);
+// metering::rescale_energy (src/metering.rs:93-110): out[(s*n_chunks + c)*resolution + o] (Flt, device)
+template <typename T>
+cudaError_t launch_rescale_energy(const void* in, long long in_stride, long long chunk_len, long long n_chunks, int n_streams,
+                                  long long resolution, void* out, cudaStream_t st);
+
 // strided 2-D copy of complex samples (used to stage stream buffers)
 template <typename T>
 cudaError_t launch_copy2d(const void* in, long long in_stride, void* out, long long out_stride, long long len,

@@ -4,6 +4,7 @@ transform.rs:397-416."""
 import math
 
 import numpy as np
+import pytest
 
 from oracle import radiorust_oracle as o
 
@@ -88,3 +89,40 @@ def test_deemphasis_factor():  # filters.rs:20-27
     want = 1.0 / complex(1.0, 50e-6 * 2 * math.pi * 1000.0)
     assert abs(z - want) < 1e-15
     assert o.deemphasis_factor(50e-6, 0.0) == 1.0
+
+
+# ---------------------------------------------------------------------------------------------------
+# metering.rs:113-262 -- the reference's own tests of level / bandwidth / rescale_energy
+# ---------------------------------------------------------------------------------------------------
+METERING_BANDWIDTH_CASES = [
+    # (bins, expected hertz) at double_percentile 0.01, 48 kHz
+    ([0j, 0j], 0.0),                                                                   # test_bandwidth_silence
+    ([1, 1, 1, 1, 1, 1, -1, complex(math.sqrt(0.5), -math.sqrt(0.5))], 0.99 * 48000.0),  # test_bandwidth_spreadspectrum
+    ([complex(7.4, -2.1)] * 3, 0.99 * 48000.0),                                        # test_bandwidth_spreadspectrum_odd
+    ([0, 0, 0, 0, 0, 0, 2.1, 0], 0.99 * 48000.0 / 8.0),                                # test_bandwidth_carrier
+    ([1.5, 0, 0, 0, 0, 0, 1.5, 0], 2.98 * 48000.0 / 8.0),                              # test_bandwidth_two_carriers
+]
+METERING_RESCALE_CASES = [
+    ([0j, complex(2, 1), -0.5], 3, [0.0, 5.0, 0.25]),                                  # test_rescale_energy_same_size
+    ([1, 2, 3, 4], 3, [2.3333333333333, 8.6666666666667, 19.0]),                       # test_rescale_energy_smaller
+    ([1, 2, 3], 4, [0.75, 2.25, 4.25, 6.75]),                                          # test_rescale_energy_larger
+]
+
+
+def test_metering_level_reference_tests():
+    h = 1.0 / math.sqrt(2.0)
+    osc = np.array([1, complex(h, h), 1j, complex(-h, h), -1, complex(-h, -h), -1j, complex(h, -h)], dtype=np.complex128)
+    assert abs(10.0 * math.log10(o.level(osc))) <= 1e-10                   # test_level_complex_osc
+    assert abs(o.level(np.array([0, -0.5j, 1], dtype=np.complex128)) - 1.25 / 3.0) <= 1e-15  # doc test, metering.rs:9-19
+
+
+@pytest.mark.parametrize("bins,want", METERING_BANDWIDTH_CASES)
+def test_metering_bandwidth_reference_tests(bins, want):
+    got = o.bandwidth(0.01, 48000.0, np.array(bins, dtype=np.complex128))
+    assert abs(got - want) <= 1e-10 * max(1.0, abs(want))
+
+
+@pytest.mark.parametrize("inp,res,want", METERING_RESCALE_CASES)
+def test_metering_rescale_energy_reference_tests(inp, res, want):
+    got = o.rescale_energy(res, np.array(inp, dtype=np.complex128))
+    assert got.shape == (res,) and np.allclose(got, want, rtol=0, atol=1e-10)
