@@ -233,6 +233,7 @@ struct rr_chain {
     uint64_t samples_lost = 0;  // SamplesLost events generated by Rechunker / Overlapper stages
     bool allow_poly = true;  // rr_chain_set_fast_path
     bool allow_poly2 = true; // RR_DISABLE_POLY2=1: keep the generic polyphase kernel (k_poly) for f32 too
+    size_t big_os_scratch_bytes = (size_t)2 << 30;  // RR_BIG_OS_SCRATCH_MB
     bool allow_front = true; // RR_DISABLE_FRONT=1: k_poly2 on all P branches instead of the rank-reduced front end
     // optional CUDA-event timing of the dominant kernel of a push (bench.py's roofline)
     bool timing = false;
@@ -769,29 +770,38 @@ int run_os(rr_chain* c, Stage& s, const FilterIo& io, size_t k, bool fih, void* 
     const size_t first = fih ? 1 : 0;  // first chunk that produces output
     const size_t n_blocks = k - first;
     if (n_blocks == 0) return RR_OK;
-    size_t max_blocks = ((size_t)48 << 20) / (N * 2 * sizeof(T));  // keep the scratch L2 resident
+    // the three kernels of a launch group exchange their blocks through `scratch`.  Measured (256 x 8 blocks of 2^17
+    // points f32, 16 x 4 blocks of 2^20 points f64): groups small enough to keep the scratch in L2 (24-96 MiB) are
+    // 15-30 % SLOWER than one large launch -- the kernels are not bound by that traffic -- so the bound only limits
+    // the memory taken (2 GiB)
+    size_t max_blocks = c->big_os_scratch_bytes / (N * 2 * sizeof(T));
     if (max_blocks < 1) max_blocks = 1;
-    size_t per_launch = max_blocks / (size_t)S;
+    const size_t sg = std::min<size_t>((size_t)S, max_blocks);  // streams per launch group
+    size_t per_launch = max_blocks / sg;
     if (per_launch < 1) per_launch = 1;
     if (per_launch > n_blocks) per_launch = n_blocks;
-    RR_TRY(s.big_scratch.ensure((size_t)S * per_launch * N * 2 * sizeof(T)));
-    for (size_t b0 = 0; b0 < n_blocks; b0 += per_launch) {
-        const size_t nb = std::min(per_launch, n_blocks - b0);
-        rr::BigOsArgs<T> a{};
-        a.in = src;
-        a.in_stride = src_stride;
-        a.hist = hist_newer;
-        a.hist_stride = (long long)(2 * n);
-        a.first_chunk = (int)(first + b0);
-        a.n_blocks = (int)nb;
-        a.scratch = s.big_scratch.p;
-        a.hbig = s.big_h.p;
-        a.twN = s.tw.p;
-        a.twA = s.big_twA.p;
-        a.twB = s.big_twB.p;
-        a.out = (char*)dst + b0 * n * 2 * sizeof(T);
-        a.out_stride = dst_stride;
-        RR_TIMED_LAUNCH(c, "k_big_os(3 kernels)", 3, rr::launch_big_os<T>((int)n, S, a, c->stream));
+    RR_TRY(s.big_scratch.ensure(sg * per_launch * N * 2 * sizeof(T)));
+    const size_t esz = 2 * sizeof(T);
+    for (size_t s0 = 0; s0 < (size_t)S; s0 += sg) {
+        const int sn = (int)std::min(sg, (size_t)S - s0);
+        for (size_t b0 = 0; b0 < n_blocks; b0 += per_launch) {
+            const size_t nb = std::min(per_launch, n_blocks - b0);
+            rr::BigOsArgs<T> a{};
+            a.in = (const char*)src + s0 * (size_t)src_stride * esz;
+            a.in_stride = src_stride;
+            a.hist = hist_newer + s0 * 2 * n * esz;
+            a.hist_stride = (long long)(2 * n);
+            a.first_chunk = (int)(first + b0);
+            a.n_blocks = (int)nb;
+            a.scratch = s.big_scratch.p;
+            a.hbig = s.big_h.p;
+            a.twN = s.tw.p;
+            a.twA = s.big_twA.p;
+            a.twB = s.big_twB.p;
+            a.out = (char*)dst + (s0 * (size_t)dst_stride + b0 * n) * esz;
+            a.out_stride = dst_stride;
+            RR_TIMED_LAUNCH(c, "k_big_os(3 kernels)", 3, rr::launch_big_os<T>((int)n, sn, a, c->stream));
+        }
     }
     return RR_OK;
 }
@@ -1237,7 +1247,7 @@ int run_push(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_chunks,
                 } else {
                     Dest d;
                     RR_TRY(pick_dest<T>(c, s, last, dev_out, (long long)out_stride, (size_t)len, &d));
-                    RR_LAUNCH(1, rr::launch_freqshift<T>(cur.p, cur.stride, d.p, d.stride, len, S, (const rr::NcoStream*)s.nco_d.p, 0, st));
+                    RR_TIMED_LAUNCH(c, "k_freqshift", 1, rr::launch_freqshift<T>(cur.p, cur.stride, d.p, d.stride, len, S, (const rr::NcoStream*)s.nco_d.p, 0, st));
                     RR_LAUNCH(1, rr::launch_nco_advance((rr::NcoStream*)s.nco_d.p, S, len, st));
                     nco_host_advance(s, len);
                     cur.p = d.p;
@@ -1250,7 +1260,7 @@ int run_push(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_chunks,
             case RR_STAGE_GAIN: {
                 Dest d;
                 RR_TRY(pick_dest<T>(c, s, last, dev_out, (long long)out_stride, (size_t)len, &d));
-                RR_LAUNCH(1, rr::launch_gain<T>(cur.p, cur.stride, d.p, d.stride, len, S, s.d.gain, st));
+                RR_TIMED_LAUNCH(c, "k_gain", 1, rr::launch_gain<T>(cur.p, cur.stride, d.p, d.stride, len, S, s.d.gain, st));
                 cur.p = d.p;
                 cur.stride = d.stride;
                 cur.sh = a.out;
@@ -1282,7 +1292,7 @@ int run_push(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_chunks,
                 }
                 Dest d;
                 RR_TRY(pick_dest<T>(c, s, last, dev_out, (long long)out_stride, (size_t)len, &d));
-                RR_LAUNCH(1, rr::launch_fourier<T>((int)n, cur.p, cur.stride, d.p, d.stride, (int)cur.sh.n_chunks, S, (const T*)s.fwin.p,
+                RR_TIMED_LAUNCH(c, "k_fourier", 1, rr::launch_fourier<T>((int)n, cur.p, cur.stride, d.p, d.stride, (int)cur.sh.n_chunks, S, (const T*)s.fwin.p,
                                                    s.ftw.p, s.d.center_dc ? (int)(n / 2) : 0, st));
                 cur.p = d.p;
                 cur.stride = d.stride;
@@ -1295,7 +1305,7 @@ int run_push(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_chunks,
                 RR_TRY(pick_dest<T>(c, s, last, dev_out, (long long)out_stride, (size_t)len, &d));
                 RR_TRY(s.fm_phase.ensure((size_t)S * sizeof(T), true));
                 const double factor = s.d.deviation / cur.sh.rate * 6.283185307179586476925286766559;  // modulation.rs:44
-                RR_LAUNCH(1, rr::launch_fmmod<T>(cur.p, cur.stride, d.p, d.stride, len, S, s.fm_phase.p, factor, c->ctx->sm_count, st));
+                RR_TIMED_LAUNCH(c, "k_fmmod", 1, rr::launch_fmmod<T>(cur.p, cur.stride, d.p, d.stride, len, S, s.fm_phase.p, factor, c->ctx->sm_count, st));
                 cur.p = d.p;
                 cur.stride = d.stride;
                 cur.sh = a.out;
@@ -1372,7 +1382,7 @@ int run_push(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_chunks,
                 RR_TRY(s.fm_prev.ensure((size_t)S * 2 * sizeof(T), true));
                 RR_TRY(s.fm_last.ensure((size_t)S * 2 * sizeof(T), true));
                 const double factor = cur.sh.rate / s.d.deviation / 6.283185307179586476925286766559;  // modulation.rs:116
-                RR_LAUNCH(2, rr::launch_fmdemod<T>(cur.p, cur.stride, d.p, d.stride, len, S, s.fm_prev.p, s.fm_last.p,
+                RR_TIMED_LAUNCH(c, "k_fmdemod", 2, rr::launch_fmdemod<T>(cur.p, cur.stride, d.p, d.stride, len, S, s.fm_prev.p, s.fm_last.p,
                                                    a.first_is_history ? 0 : 1, factor, st));
                 cur.p = d.p;
                 cur.stride = d.stride;
@@ -1425,7 +1435,7 @@ int run_push(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_chunks,
                     plan += rr::chain_os_supported<T>((int)n, 0, 0) ? "fused_os[filter]" : "big_os";
                 }
                 // new history: the last two mixed chunks (filters.rs:260 keeps one; the polyphase path needs two)
-                RR_LAUNCH(1, rr::launch_hist2_update<T>(io.in, io.in_stride, len, s.hist2[s.hist_cur].p, s.hist2[s.hist_cur ^ 1].p, (long long)n,
+                RR_TIMED_LAUNCH(c, "k_hist2_update", 1, rr::launch_hist2_update<T>(io.in, io.in_stride, len, s.hist2[s.hist_cur].p, s.hist2[s.hist_cur ^ 1].p, (long long)n,
                                                         io.nco ? (const rr::NcoStream*)io.nco->nco_d.p : nullptr, S, st,
                                                         s.hist_fused_jlo > 0 ? s.hist_fused_jlo : 0));
                 s.hist_fused_jlo = -1;
@@ -1449,11 +1459,11 @@ int run_push(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_chunks,
                 rs.j0 = a.j0;
                 rs.m0 = a.m0;
                 if (down) {
-                    RR_LAUNCH(2, rr::launch_downsample<T>(cur.p, cur.stride, len, s.tail[s.tail_cur].p, s.tail[s.tail_cur ^ 1].p,
+                    RR_TIMED_LAUNCH(c, "k_downsample", 2, rr::launch_downsample<T>(cur.p, cur.stride, len, s.tail[s.tail_cur].p, s.tail[s.tail_cur ^ 1].p,
                                                           (const T*)s.ir.p, s.h.r_L, rs, (long long)a.n_new, o, (long long)s.obuf_cap, S, st));
                     plan += "downsample";
                 } else {
-                    RR_LAUNCH(1, rr::launch_upsample<T>(cur.p, cur.stride, len, s.tail[s.tail_cur].p, s.tail[s.tail_cur ^ 1].p,
+                    RR_TIMED_LAUNCH(c, "k_upsample", 1, rr::launch_upsample<T>(cur.p, cur.stride, len, s.tail[s.tail_cur].p, s.tail[s.tail_cur ^ 1].p,
                                                         (const T*)s.ir.p, s.h.r_L, rs, (long long)a.n_new, o, (long long)s.obuf_cap, S, st));
                     plan += "upsample";
                 }
@@ -1815,6 +1825,7 @@ int rr_chain_create(rr_ctx* ctx, const rr_chain_desc* desc, rr_chain** out) {
     if (const char* e = std::getenv("RR_DISABLE_POLY")) c->allow_poly = !(e[0] == '1');
     if (const char* e = std::getenv("RR_DISABLE_POLY2")) c->allow_poly2 = !(e[0] == '1');
     if (const char* e = std::getenv("RR_DISABLE_FRONT")) c->allow_front = !(e[0] == '1');
+    if (const char* e = std::getenv("RR_BIG_OS_SCRATCH_MB")) c->big_os_scratch_bytes = (size_t)std::max(1, std::atoi(e)) << 20;
     RR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     *out = c.release();
     return RR_OK;
