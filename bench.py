@@ -287,6 +287,33 @@ def run_cuda(args):
     samples_step = S * length
     value = samples_step * world * args.steps / (elapsed_ms * 1e-3) / 1e6
 
+    # ---- the one collective of the path: gathering the channelizer outputs --------------
+    # Outside the timed region and reported separately: every rank contributes its streams' decimated
+    # samples of one step; NCCL all-gather over NVLink, timed on the device, max over ranks.
+    gather = None
+    if dist is not None:
+        per_stream = out_total // max(args.steps, 1)
+        mine = y[:, :per_stream].contiguous()
+        everyone = torch.empty((world * S, per_stream, 2), device="cuda", dtype=torch.float32)
+        dist.all_gather_into_tensor(everyone, mine)  # warm-up (communicator set-up)
+        torch.cuda.synchronize()
+        dist.barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        g0.record()
+        for _ in range(reps):
+            dist.all_gather_into_tensor(everyone, mine)
+        g1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([g0.elapsed_time(g1) / reps], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gms = float(t.item())
+        same = bool(torch.equal(everyone[rank * S:(rank + 1) * S], mine))
+        gather = {"collective": "nccl all_gather of one step's outputs (outside the timed region)", "ms": gms,
+                  "bytes_per_rank": mine.numel() * 4, "bytes_total": everyone.numel() * 4,
+                  "share_of_step": gms / (elapsed_ms / args.steps), "own_slice_intact": same}
+        del everyone, mine
+
     # ---- end to end: pinned host chunks in, host result out, through rr_chain_push ----
     e2e = None
     if not args.no_e2e:
@@ -342,6 +369,7 @@ def run_cuda(args):
         "plan": plan,
         "clocks": clocks,
         "e2e": e2e,
+        "gather": gather,
         "gpu_launches": int(launches),
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
