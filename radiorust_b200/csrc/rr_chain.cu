@@ -198,6 +198,7 @@ struct Stage {
     bool poly2_tw_own = false;
     // rank-reduced front end (k_front) + k_poly2 on its output: coefficient table, low-rate table, scratch
     DevBuf acoef, gtab3, ubuf;
+    long long ubuf_stride = -1;  // layout the zeroed pad rows of ubuf belong to
     bool front_valid = false;
     int front_rank = 0;
     double front_discarded = 0.0;
@@ -1055,9 +1056,21 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
                     const int G2 = RK;
                     const long long n_out = m_hi - m_lo + 1;
                     const long long n_rows = n_out + ds.poly_Lmax;
-                    const long long u_stride = (n_rows * RK + 1) / 2 * 2;
+                    // every stream's rows are followed by one transform length of zero rows, so that the low-rate part
+                    // reads whole tiles by TMA up to and including its last block (no edge path, no shifted block)
+                    // (rows beyond n_rows only feed outputs that are not stored; the stride is rounded so that pushes whose
+                    // output count differs by a few keep the layout, and what an earlier push left there is that stream's own)
+                    const long long pad_rows = 512;
+                    const long long u_stride = (((n_rows + 127) / 128 * 128 + pad_rows) * RK + 1) / 2 * 2;
                     if (n_rows < (1LL << 27)) {
-                        RR_TRY(ds.ubuf.ensure((size_t)S * (size_t)u_stride * 2 * sizeof(float)));
+                        const size_t ubytes = (size_t)S * (size_t)u_stride * 2 * sizeof(float);
+                        if (ds.ubuf.bytes < ubytes || ds.ubuf_stride != u_stride) {
+                            // a new layout: the pad rows must read as zeros (they only ever feed outputs that are not stored,
+                            // but a NaN there would spread through the transform)
+                            RR_TRY(ds.ubuf.ensure(ubytes));
+                            RR_CUDA(cudaMemsetAsync(ds.ubuf.p, 0, ubytes, st));
+                            ds.ubuf_stride = u_stride;
+                        }
                         rr::FrontArgs fa{};
                         fa.in = a.in;
                         fa.in_stride = a.in_stride;
@@ -1086,7 +1099,7 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
                         rr::PolyArgs<float> b{};
                         b.in = ds.ubuf.p;
                         b.in_stride = u_stride;
-                        b.len = n_rows * RK;
+                        b.len = (n_rows + pad_rows) * RK;
                         b.hist2 = ds.ubuf.p;
                         b.n = 0;
                         b.nco = nullptr;
