@@ -52,7 +52,7 @@ __device__ __forceinline__ pc lds_front(uint32_t addr) {
 }
 
 template <int RK, bool HAS_NCO>
-__global__ void __launch_bounds__(FR_WARPS * 32) k_front(const __grid_constant__ CUtensorMap tmap, const FrontArgs a) {
+__global__ void __launch_bounds__(FR_WARPS * 32, 4) k_front(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_h, const FrontArgs a) {
     static_assert(RK == 10, "the store split below (6 + 4 results per lane pair) is written for ten columns");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = lane >> 1, hh = lane & 1;  // row of the tile, half of its columns
@@ -132,15 +132,20 @@ __global__ void __launch_bounds__(FR_WARPS * 32) k_front(const __grid_constant__
     auto tile_interior = [&](int pos0) -> bool { return pos0 >= 0 && pos0 + (FR_ROWS - 1) * P + pitch <= len32; };
     // start the TMA copy of tile k into ring slot k % FR_STAGES (interior tiles only); the bookkeeping is
     // warp-uniform, only the two asynchronous instructions are issued by one lane
+    // a tile that lies completely in the history is copied the same way from hist2 (same overlapping-row map) and
+    // un-mixed in shared memory; only a tile that straddles the start or the end of the push is filled by hand
+    const int hist32 = a.has_hist_map ? (int)hist_len : 0;
+    auto tile_history = [&](int pos0) -> bool { return hist32 > 0 && pos0 >= -hist32 && pos0 + (FR_ROWS - 1) * P + pitch <= 0; };
     auto issue = [&](int k) {
         const int pos0 = tile_pos0(k);
-        const bool go = k < n_tiles && tile_interior(pos0);
+        const bool live = k < n_tiles;
+        const bool from_in = live && tile_interior(pos0), from_hist = live && !from_in && tile_history(pos0);
         const uint32_t bar = bar0 + (k % FR_STAGES) * 8;
-        if (go && lane == 0) {
+        if ((from_in || from_hist) && lane == 0) {
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tile_bytes) : "memory");
             asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
                              tiles_s + (k % FR_STAGES) * tile_stride),
-                         "l"(&tmap), "r"(bar), "r"(pos0), "r"(0), "r"(s)
+                         "l"(from_in ? &tmap : &tmap_h), "r"(bar), "r"(from_in ? pos0 : pos0 + hist32), "r"(0), "r"(s)
                          : "memory");
         }
     };
@@ -153,7 +158,8 @@ __global__ void __launch_bounds__(FR_WARPS * 32) k_front(const __grid_constant__
         const int slot = k % FR_STAGES;
         const int v0 = (tile0 + k) * FR_ROWS;  // first row (of this push's u rows) of the tile
         const int pos0 = tile_pos0(k);
-        const bool interior = tile_interior(pos0);
+        const bool history = tile_history(pos0);
+        const bool interior = tile_interior(pos0) || history;  // arrives by TMA
         const uint32_t tile_s = tiles_s + slot * tile_stride;
         // the slot of tile k + FR_STAGES - 1 was released at the end of the previous iteration
         issue(k + FR_STAGES - 1);
@@ -181,12 +187,25 @@ __global__ void __launch_bounds__(FR_WARPS * 32) k_front(const __grid_constant__
                 "r"((phase >> slot) & 1)
                 : "memory");
             phase ^= 1u << slot;
+            if (HAS_NCO && history) {
+                // history samples are already mixed: give them the conjugate of the phasors applied below
+                float2* dst = reinterpret_cast<float2*>(tiles + slot * tile_stride);
+                for (int r = 0; r < FR_ROWS; ++r) {
+                    const pc rp(__shfl_sync(0xffffffffu, rowph.x, 2 * r), __shfl_sync(0xffffffffu, rowph.y, 2 * r));
+                    for (int p = lane; p < P; p += 32) {
+                        const float2 c = colph[p], q = dst[r * pitch + p];
+                        const pc y = pcmulc(pc(q.x, q.y), pcmul(rp, pc(c.x, c.y)));
+                        dst[r * pitch + p] = make_float2(y.x, y.y);
+                    }
+                }
+                __syncwarp();
+            }
         } else {
             // edge tile (reaches before the pushed samples or past them): the warp fills its slot itself,
             // coalesced.  History samples are already mixed: they get the conjugate of the phasors that the
             // loop below and the row's results apply.
             float2* dst = reinterpret_cast<float2*>(tiles + slot * tile_stride);
-            constexpr int UNR = 5;  // loads in flight per lane
+            constexpr int UNR = 13;  // loads in flight per lane: a 16 x 50 tile in two round trips
             for (int e0 = lane; e0 < FR_ROWS * P; e0 += 32 * UNR) {
                 float2 q[UNR];
 #pragma unroll
@@ -361,6 +380,16 @@ cudaError_t launch_front(int rank_pad, int n_streams, const FrontArgs& a0, cudaS
     const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void*>(a.in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    // the history as the same kind of map: element (c0, i, s) = hist2[s*2n + c0 + i*P]
+    CUtensorMap tmh = tm;
+    a.has_hist_map = 0;
+    if (a.hist2 && a.n > 0 && ((uintptr_t)a.hist2 % 16) == 0 && 2 * a.n >= (long long)FR_ROWS * a.P + pitch) {
+        const cuuint64_t hdims[3] = {(cuuint64_t)(2 * a.n), (cuuint64_t)FR_ROWS, (cuuint64_t)n_streams};
+        const cuuint64_t hstrides[2] = {(cuuint64_t)a.P * 8, (cuuint64_t)(2 * a.n) * 8};
+        if (enc(&tmh, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void*>(a.hist2), hdims, hstrides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+            a.has_hist_map = 1;
+    }
     const int tile_stride = (FR_ROWS * pitch * 8 + 127) / 128 * 128;
     const size_t smem = (size_t)FR_WARPS * FR_STAGES * tile_stride + (size_t)(a.P / 2) * 2 * 10 * 4 + (size_t)a.P * 8 + FR_WARPS * FR_STAGES * 8 + 16;
     const dim3 grid((unsigned)((tiles + FR_WARPS * a.tiles_per_warp - 1) / (FR_WARPS * a.tiles_per_warp)), (unsigned)n_streams);
@@ -369,12 +398,12 @@ cudaError_t launch_front(int rank_pad, int n_streams, const FrontArgs& a0, cudaS
         auto kern = k_front<10, true>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        kern<<<grid, FR_WARPS * 32, smem, st>>>(tm, a);
+        kern<<<grid, FR_WARPS * 32, smem, st>>>(tm, tmh, a);
     } else {
         auto kern = k_front<10, false>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        kern<<<grid, FR_WARPS * 32, smem, st>>>(tm, a);
+        kern<<<grid, FR_WARPS * 32, smem, st>>>(tm, tmh, a);
     }
     return cudaGetLastError();
 }

@@ -206,6 +206,7 @@ struct FrontArgs {
     void* u;               // [S][u_stride] complex<float>, row-major [row][rank_pad]
     long long u_stride;    // complex elements, even
     int tiles_per_warp;    // set by the launcher
+    int has_hist_map;      // set by the launcher: history tiles come by TMA from hist2
     // optional: the mixed samples at push offsets >= hist_from also go to hist_out[s][offset - hist_from]
     // (the Filter's next history, [S][hist_stride]), for every offset inside the rows this launch covers
     void* hist_out;
