@@ -178,7 +178,8 @@ struct Stage {
     DevBuf hperm, tw;
     DevBuf hist2[2];  // [S][2n] post-NCO samples preceding the next push (older chunk | newer chunk), ping-pong
     int hist_cur = 0;
-    long long hist_fused_jlo = -1;  // >= 0: this push's k_front already wrote entries [0, jlo) of the new hist2
+    // >= 0: this push's k_front already wrote entries [hist_fused_jfirst, hist_fused_jlo) of the new hist2
+    long long hist_fused_jlo = -1, hist_fused_jfirst = 0;
     DevBuf ztmp;      // filter-output scratch of the unfused stateful path
     std::vector<std::complex<double>> taps;  // windowed impulse response (Flt-rounded), for the polyphase tables
     bool taps_valid = false;
@@ -197,8 +198,13 @@ struct Stage {
     DevBuf gtab2, twK2;
     bool poly2_tw_own = false;
     // rank-reduced front end (k_front) + k_poly2 on its output: coefficient table, low-rate table, scratch
-    DevBuf acoef, gtab3, ubuf;
-    long long ubuf_stride = -1;  // layout the zeroed pad rows of ubuf belong to
+    DevBuf acoef, gtab3, ubuf[2];
+    long long ubuf_stride[2] = {-1, -1};  // layout the zeroed pad rows of each ubuf belong to
+    // the last Lmax rows of u written by the previous push (in ubuf[ubuf_cur ^ 1]) are the history rows of the next
+    // one as long as every push in between went through the front end
+    int ubuf_cur = 0;
+    bool ucache_valid = false;
+    long long ucache_rows = 0;  // rows of the previous push
     bool front_valid = false;
     int front_rank = 0;
     double front_discarded = 0.0;
@@ -235,6 +241,7 @@ struct rr_chain {
     bool allow_poly = true;  // rr_chain_set_fast_path
     bool allow_poly2 = true; // RR_DISABLE_POLY2=1: keep the generic polyphase kernel (k_poly) for f32 too
     size_t big_os_scratch_bytes = (size_t)2 << 30;  // RR_BIG_OS_SCRATCH_MB
+    bool allow_ucache = true; // RR_DISABLE_UCACHE=1: recompute the history rows of u from hist2 in every push
     bool allow_front = true; // RR_DISABLE_FRONT=1: k_poly2 on all P branches instead of the rank-reduced front end
     // optional CUDA-event timing of the dominant kernel of a push (bench.py's roofline)
     bool timing = false;
@@ -958,6 +965,9 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
     const long long ostride = (long long)ds.obuf_cap;
 
     if (c->allow_poly) RR_TRY(poly_prepare<T>(c, f, ds));
+    // the kept u rows stay usable only from one front-end push to the very next one
+    const bool was_ucache_valid = ds.ucache_valid;
+    ds.ucache_valid = false;
     // chunks the stateful path must take: those whose outputs still depend on pre-segment state
     size_t ca = io.n_chunks;
     if (c->allow_poly && ds.poly_valid) {
@@ -1064,12 +1074,22 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
                     const long long u_stride = (((n_rows + 127) / 128 * 128 + pad_rows) * RK + 1) / 2 * 2;
                     if (n_rows < (1LL << 27)) {
                         const size_t ubytes = (size_t)S * (size_t)u_stride * 2 * sizeof(float);
-                        if (ds.ubuf.bytes < ubytes || ds.ubuf_stride != u_stride) {
+                        DevBuf& ub = ds.ubuf[ds.ubuf_cur];
+                        if (ub.bytes < ubytes || ds.ubuf_stride[ds.ubuf_cur] != u_stride) {
                             // a new layout: the pad rows must read as zeros (they only ever feed outputs that are not stored,
                             // but a NaN there would spread through the transform)
-                            RR_TRY(ds.ubuf.ensure(ubytes));
-                            RR_CUDA(cudaMemsetAsync(ds.ubuf.p, 0, ubytes, st));
-                            ds.ubuf_stride = u_stride;
+                            RR_TRY(ub.ensure(ubytes));
+                            RR_CUDA(cudaMemsetAsync(ub.p, 0, ubytes, st));
+                            ds.ubuf_stride[ds.ubuf_cur] = u_stride;
+                        }
+                        // history rows: kept from the previous push when it went through here too, else recomputed from hist2
+                        const long long Lh = ds.poly_Lmax;
+                        const bool cached = was_ucache_valid && c->allow_ucache && ca == 0 && ds.ucache_rows >= Lh && n_out > 0;
+                        if (cached) {
+                            const int pv = ds.ubuf_cur ^ 1;
+                            const char* src = (const char*)ds.ubuf[pv].p + (size_t)(ds.ucache_rows - Lh) * RK * 2 * sizeof(float);
+                            RR_TIMED_LAUNCH(c, "k_copy2d(u history)", 1,
+                                            rr::launch_copy2d<float>(src, ds.ubuf_stride[pv], ub.p, u_stride, Lh * RK, S, st));
                         }
                         rr::FrontArgs fa{};
                         fa.in = a.in;
@@ -1081,26 +1101,32 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
                         fa.acoef = (const float*)ds.acoef.p;
                         fa.P = (int)Pq;
                         fa.J0 = a.J0;
-                        fa.row_first = m_lo - 1 - ds.poly_Lmax;
-                        fa.n_rows = (int)n_rows;
-                        fa.u = ds.ubuf.p;
+                        fa.row_first = m_lo - 1 - (cached ? 0 : Lh);
+                        fa.n_rows = (int)(cached ? n_out : n_rows);
+                        fa.u = (char*)ub.p + (cached ? (size_t)Lh * RK * 2 * sizeof(float) : 0);
                         fa.u_stride = u_stride;
                         // the rows cover push offsets [row_first*P - J0, m_hi*P - J0): when that reaches back to
                         // len - 2n the kernel also writes the Filter's next history up to its last row
                         const long long cover_lo = fa.row_first * Pq - a.J0, cover_hi = m_hi * Pq - a.J0;
                         f.hist_fused_jlo = -1;
-                        if (a.len >= 2 * a.n && cover_lo <= a.len - 2 * a.n && cover_hi > a.len - 2 * a.n) {
+                        f.hist_fused_jfirst = 0;
+                        // (a push shorter than 2n keeps the end of the old history in front: those entries, [0, 2n - len),
+                        // are copied by k_hist2_update)
+                        const long long hfrom = a.len - 2 * a.n, hstart = std::max<long long>(hfrom, 0);
+                        if (cover_lo <= hstart && cover_hi > hstart) {
                             fa.hist_out = f.hist2[f.hist_cur ^ 1].p;
-                            fa.hist_from = a.len - 2 * a.n;
+                            fa.hist_from = hfrom;
                             fa.hist_stride = 2 * a.n;
-                            f.hist_fused_jlo = cover_hi - fa.hist_from;
+                            fa.hist_staged = a.len < 4 * a.n ? 1 : 0;  // measured: pays off up to 3 chunks per push
+                            f.hist_fused_jlo = cover_hi - hfrom;
+                            f.hist_fused_jfirst = hstart - hfrom;
                         }
                         RR_TIMED_LAUNCH(c, "k_front", 1, rr::launch_front(RK, S, fa, st));
                         rr::PolyArgs<float> b{};
-                        b.in = ds.ubuf.p;
+                        b.in = ub.p;
                         b.in_stride = u_stride;
                         b.len = (n_rows + pad_rows) * RK;
-                        b.hist2 = ds.ubuf.p;
+                        b.hist2 = ub.p;
                         b.n = 0;
                         b.nco = nullptr;
                         b.gtab = ds.gtab3.p;
@@ -1138,6 +1164,9 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
                             direct->done = true;
                         }
                         RR_TIMED_LAUNCH(c, "k_poly2", 1, rr::launch_poly2(G2, S, b, st));
+                        ds.ucache_valid = true;
+                        ds.ucache_rows = n_rows;
+                        ds.ubuf_cur ^= 1;
                         done = true;
                         used_front = true;
                     }
@@ -1439,6 +1468,7 @@ int run_push(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_chunks,
                     RR_TRY(resampler_emit<T>(c, *ds, da, ds_last, dev_out, (long long)out_stride, &cur, direct.done));
                     took_ds = true;
                 } else {
+                    if (ds) ds->ucache_valid = false;
                     Dest d;
                     RR_TRY(pick_dest<T>(c, s, last, dev_out, (long long)out_stride, a.out.len(), &d));
                     RR_TRY(run_os<T>(c, s, io, io.n_chunks, a.first_is_history, d.p, d.stride));
@@ -1448,9 +1478,21 @@ int run_push(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_chunks,
                     plan += rr::chain_os_supported<T>((int)n, 0, 0) ? "fused_os[filter]" : "big_os";
                 }
                 // new history: the last two mixed chunks (filters.rs:260 keeps one; the polyphase path needs two)
-                RR_TIMED_LAUNCH(c, "k_hist2_update", 1, rr::launch_hist2_update<T>(io.in, io.in_stride, len, s.hist2[s.hist_cur].p, s.hist2[s.hist_cur ^ 1].p, (long long)n,
-                                                        io.nco ? (const rr::NcoStream*)io.nco->nco_d.p : nullptr, S, st,
-                                                        s.hist_fused_jlo > 0 ? s.hist_fused_jlo : 0));
+                {
+                    const void* hin = s.hist2[s.hist_cur].p;
+                    void* hout = s.hist2[s.hist_cur ^ 1].p;
+                    const rr::NcoStream* ncop = io.nco ? (const rr::NcoStream*)io.nco->nco_d.p : nullptr;
+                    if (s.hist_fused_jlo > 0) {
+                        // k_front wrote [jfirst, jlo): the old history in front of it and the samples behind its last row remain
+                        if (s.hist_fused_jfirst > 0)
+                            RR_TIMED_LAUNCH(c, "k_hist2_update", 1, rr::launch_hist2_update<T>(io.in, io.in_stride, len, hin, hout, (long long)n, ncop, S,
+                                                                                                st, 0, s.hist_fused_jfirst));
+                        RR_TIMED_LAUNCH(c, "k_hist2_update", 1, rr::launch_hist2_update<T>(io.in, io.in_stride, len, hin, hout, (long long)n, ncop, S, st,
+                                                                                            s.hist_fused_jlo, -1));
+                    } else {
+                        RR_TIMED_LAUNCH(c, "k_hist2_update", 1, rr::launch_hist2_update<T>(io.in, io.in_stride, len, hin, hout, (long long)n, ncop, S, st, 0, -1));
+                    }
+                }
                 s.hist_fused_jlo = -1;
                 s.hist_cur ^= 1;
                 if (io.nco) {
@@ -1838,6 +1880,7 @@ int rr_chain_create(rr_ctx* ctx, const rr_chain_desc* desc, rr_chain** out) {
     if (const char* e = std::getenv("RR_DISABLE_POLY")) c->allow_poly = !(e[0] == '1');
     if (const char* e = std::getenv("RR_DISABLE_POLY2")) c->allow_poly2 = !(e[0] == '1');
     if (const char* e = std::getenv("RR_DISABLE_FRONT")) c->allow_front = !(e[0] == '1');
+    if (const char* e = std::getenv("RR_DISABLE_UCACHE")) c->allow_ucache = !(e[0] == '1');
     if (const char* e = std::getenv("RR_BIG_OS_SCRATCH_MB")) c->big_os_scratch_bytes = (size_t)std::max(1, std::atoi(e)) << 20;
     RR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     *out = c.release();
@@ -1851,7 +1894,7 @@ int rr_chain_destroy(rr_chain* c) {
     for (auto& s : c->st) {
         DevBuf* bufs[] = {&s.nco_d, &s.hperm, &s.tw, &s.hist2[0], &s.hist2[1], &s.ztmp, &s.gtab, &s.twK, &s.big_h, &s.big_twA, &s.big_twB, &s.big_scratch,
                           &s.ir, &s.tail[0], &s.tail[1], &s.obuf[0], &s.obuf[1], &s.fm_prev, &s.fm_last, &s.out,
-                          &s.gtab2, &s.twK2, &s.acoef, &s.gtab3, &s.ubuf, &s.fwin, &s.ftw, &s.fm_phase};
+                          &s.gtab2, &s.twK2, &s.acoef, &s.gtab3, &s.ubuf[0], &s.ubuf[1], &s.fwin, &s.ftw, &s.fm_phase};
         for (DevBuf* b : bufs) b->release();
     }
     c->host_in.release();
@@ -1946,7 +1989,10 @@ int rr_chain_event(rr_chain* c, int is_interrupt) {
     if (!c) return fail(RR_ERR_INVALID, "null chain");
     // plain events pass every block untouched until a Rechunker / Overlapper turns them into an interrupt
     bool intr = is_interrupt != 0;
-    for (auto& s : c->st) c->samples_lost += (uint64_t)stage_event(s.d, s.h, &intr);
+    for (auto& s : c->st) {
+        c->samples_lost += (uint64_t)stage_event(s.d, s.h, &intr);
+        if (intr) s.ucache_valid = false;  // the Filter in front starts a new segment
+    }
     return RR_OK;
 }
 uint64_t rr_chain_samples_lost_count(rr_chain* c) { return c ? c->samples_lost : 0; }

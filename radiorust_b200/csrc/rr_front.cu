@@ -247,6 +247,9 @@ __global__ void __launch_bounds__(FR_WARPS * 32, 4) k_front(const __grid_constan
         const uint32_t row_s = tile_s + row * (pitch * 8);
         const long long prow = pos0 + (long long)row * P;  // push offset of this lane's row
         const bool row_ok = v0 + row < a.n_rows;
+        // history samples leave either straight from the registers (8/16-byte pieces per lane: fine when few tiles do it)
+        // or, when most tiles of the launch do, through the tile with coalesced stores
+        const bool staged = a.hist_staged != 0;
         auto run_row = [&](auto write_hist) {
 #pragma unroll 4
             for (int st = st0; st < st1; ++st) {
@@ -259,12 +262,19 @@ __global__ void __launch_bounds__(FR_WARPS * 32, 4) k_front(const __grid_constan
                     x1 = pcmul(x1, c1);
                 }
                 if (decltype(write_hist)::value) {
-                    // the Filter's next history: the fully mixed samples near the end of the push
-                    const long long j = prow + 2 * st - a.hist_from;
-                    if (row_ok && j >= -1) {
-                        const pc y0 = HAS_NCO ? pcmul(x0, rowph) : x0, y1 = HAS_NCO ? pcmul(x1, rowph) : x1;
-                        if (j >= 0) hist_o[j] = make_float2(y0.x, y0.y);
-                        hist_o[j + 1] = make_float2(y1.x, y1.y);
+                    // the Filter's next history = the fully mixed samples
+                    const pc y0 = HAS_NCO ? pcmul(x0, rowph) : x0, y1 = HAS_NCO ? pcmul(x1, rowph) : x1;
+                    if (staged) {
+                        // parked in the tile (each lane overwrites what it has just read), written out row by row after the loop
+                        if (HAS_NCO)
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row_s + st * 16), "f"(y0.x), "f"(y0.y), "f"(y1.x), "f"(y1.y)
+                                         : "memory");
+                    } else {
+                        const long long j = prow + 2 * st - a.hist_from;
+                        if (row_ok && j >= -1) {
+                            if (j >= 0) hist_o[j] = make_float2(y0.x, y0.y);
+                            hist_o[j + 1] = make_float2(y1.x, y1.y);
+                        }
                     }
                 }
                 float cf[2 * RK];
@@ -285,10 +295,12 @@ __global__ void __launch_bounds__(FR_WARPS * 32, 4) k_front(const __grid_constan
                 pc x0 = lds_front(row_s + p * 8);
                 if (HAS_NCO) x0 = pcmul(x0, lds_front(col_s + p * 8));
                 if (decltype(write_hist)::value) {
-                    const long long j = prow + p - a.hist_from;
-                    if (row_ok && j >= 0) {
-                        const pc y0 = HAS_NCO ? pcmul(x0, rowph) : x0;
-                        hist_o[j] = make_float2(y0.x, y0.y);
+                    const pc y0 = HAS_NCO ? pcmul(x0, rowph) : x0;
+                    if (staged) {
+                        if (HAS_NCO) asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(row_s + p * 8), "f"(y0.x), "f"(y0.y) : "memory");
+                    } else {
+                        const long long j = prow + p - a.hist_from;
+                        if (row_ok && j >= 0) hist_o[j] = make_float2(y0.x, y0.y);
                     }
                 }
                 float cf[RK];
@@ -300,8 +312,20 @@ __global__ void __launch_bounds__(FR_WARPS * 32, 4) k_front(const __grid_constan
                 for (int c = 0; c < RK; ++c) acc[c] = pfma_s(x0, cf[c], acc[c]);
             }
         };
-        if (hist_o != nullptr && pos0 + (long long)FR_ROWS * P > a.hist_from) run_row(std::true_type{});
+        const bool to_hist = hist_o != nullptr && pos0 + (long long)FR_ROWS * P > a.hist_from;
+        if (to_hist) run_row(std::true_type{});
         else run_row(std::false_type{});
+        if (to_hist && staged) {
+            // rows are consecutive in the stream: coalesced 8-byte stores, a row per pass
+            __syncwarp();
+            const float2* src = reinterpret_cast<const float2*>(tiles + slot * tile_stride);
+            const int rows_ok = min(FR_ROWS, a.n_rows - v0);
+            for (int r = 0; r < rows_ok; ++r) {
+                const long long j0 = (long long)pos0 + (long long)r * P - a.hist_from;
+                for (int p = lane; p < P; p += 32)
+                    if (j0 + p >= 0) hist_o[j0 + p] = src[r * pitch + p];
+            }
+        }
         // every lane is done with the slot: it may be refilled (generic-proxy accesses ordered before the copy)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();

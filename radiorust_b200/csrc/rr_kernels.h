@@ -211,14 +211,15 @@ struct FrontArgs {
     // (the Filter's next history, [S][hist_stride]), for every offset inside the rows this launch covers
     void* hist_out;
     long long hist_from, hist_stride;
+    int hist_staged;       // != 0: history samples go through the shared-memory tile (coalesced stores)
 };
 bool front_supported(int rank_pad, long long P);
 cudaError_t launch_front(int rank_pad, int n_streams, const FrontArgs& a, cudaStream_t st);
 
-// new hist2 = last 2n post-NCO samples of [hist2_in | in]; j_lo > 0: only entries [j_lo, 2n) (the rest was
-// written by k_front)
+// new hist2 = last 2n post-NCO samples of [hist2_in | in]; only entries [j_lo, j_hi) (j_hi < 0: 2n) -- the
+// others were written by k_front
 template <typename T>
 cudaError_t launch_hist2_update(const void* in, long long in_stride, long long len, const void* hist2_in, void* hist2_out,
-                                long long n, const NcoStream* nco, int n_streams, cudaStream_t st, long long j_lo = 0);
+                                long long n, const NcoStream* nco, int n_streams, cudaStream_t st, long long j_lo = 0, long long j_hi = -1);
 
 }  // namespace rr

@@ -77,10 +77,10 @@ template cudaError_t launch_poly<double>(int, int, int, int, const PolyArgs<doub
 template <typename T>
 __global__ void __launch_bounds__(256) k_hist2_update(const cx<T>* __restrict__ in, long long in_stride, long long len,
                                                       const cx<T>* __restrict__ hist2_in, cx<T>* __restrict__ hist2_out,
-                                                      long long n, const NcoStream* __restrict__ nco, long long j_lo) {
+                                                      long long n, const NcoStream* __restrict__ nco, long long j_lo, long long j_hi) {
     const int s = blockIdx.y;
     const long long j = j_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= 2 * n) return;
+    if (j >= j_hi) return;
     const long long off = len - 2 * n + j;
     cx<T> v;
     if (off >= 0) {
@@ -96,16 +96,17 @@ __global__ void __launch_bounds__(256) k_hist2_update(const cx<T>* __restrict__ 
 }
 template <typename T>
 cudaError_t launch_hist2_update(const void* in, long long in_stride, long long len, const void* hist2_in, void* hist2_out,
-                                long long n, const NcoStream* nco, int n_streams, cudaStream_t st, long long j_lo) {
-    if (j_lo >= 2 * n) return cudaSuccess;
-    dim3 grid((unsigned)((2 * n - j_lo + 255) / 256), (unsigned)n_streams);
+                                long long n, const NcoStream* nco, int n_streams, cudaStream_t st, long long j_lo, long long j_hi) {
+    if (j_hi < 0 || j_hi > 2 * n) j_hi = 2 * n;
+    if (j_lo >= j_hi) return cudaSuccess;
+    dim3 grid((unsigned)((j_hi - j_lo + 255) / 256), (unsigned)n_streams);
     k_hist2_update<T><<<grid, 256, 0, st>>>(reinterpret_cast<const cx<T>*>(in), in_stride, len,
-                                            reinterpret_cast<const cx<T>*>(hist2_in), reinterpret_cast<cx<T>*>(hist2_out), n, nco, j_lo);
+                                            reinterpret_cast<const cx<T>*>(hist2_in), reinterpret_cast<cx<T>*>(hist2_out), n, nco, j_lo, j_hi);
     return cudaGetLastError();
 }
 template cudaError_t launch_hist2_update<float>(const void*, long long, long long, const void*, void*, long long, const NcoStream*,
-                                                int, cudaStream_t, long long);
+                                                int, cudaStream_t, long long, long long);
 template cudaError_t launch_hist2_update<double>(const void*, long long, long long, const void*, void*, long long, const NcoStream*,
-                                                 int, cudaStream_t, long long);
+                                                 int, cudaStream_t, long long, long long);
 
 }  // namespace rr

@@ -268,3 +268,66 @@ def test_chain_destroy_releases_device_memory(ctx):
     torch.cuda.synchronize()
     free1, _ = torch.cuda.mem_get_info()
     assert free0 - free1 < 8 * 1024 * 1024, (free0, free1)
+
+
+def test_kept_u_rows_match_recomputed_history(ctx, monkeypatch):
+    """Pushes that follow a front-end push reuse its last Lmax rows of u instead of recomputing them from hist2
+    (`k_copy2d(u history)` in the kernel breakdown); RR_DISABLE_UCACHE=1 recomputes.  Both match the oracle, through
+    ragged push sizes, a retune (the kept rows stay valid: the mixed signal is phase continuous), an interrupt and a
+    filter update (both start a new segment: nothing is kept across them)."""
+    import radiorust_b200 as rr
+
+    sr, n, S = 2_400_000.0, 4096, 3
+    lp = orc.lowpass(3000.0)
+    rng = np.random.default_rng(99)
+    script = [3, 1, 1, 2, 1, "retune", 1, 5, 1, "interrupt", 1, 1, 1, 2, "update", 1, 1, 1, 1]
+    total = sum(k for k in script if isinstance(k, int))
+    x = (rng.standard_normal((S, total * n)) + 1j * rng.standard_normal((S, total * n))).astype(np.complex64)
+
+    def run(disable):
+        if disable:
+            monkeypatch.setenv("RR_DISABLE_UCACHE", "1")
+        else:
+            monkeypatch.delenv("RR_DISABLE_UCACHE", raising=False)
+        ch = rr.Chain(ctx, [rr.FreqShifter(12345.0), rr.Filter.new(lp), rr.Downsampler(16, 48000.0, 6000.0)], "f32", n_streams=S)
+        ch.set_timing(True)
+        outs, pos = [], 0
+        for k in script:
+            if k == "retune":
+                ch.set_shift(0, -77777.0)
+            elif k == "interrupt":
+                ch.event(True)
+            elif k == "update":
+                ch.update_filter(1, orc.lowpass(2500.0))
+            else:
+                y, _ = ch.push(sr, x[:, pos * n:(pos + k) * n], n)
+                outs.append(y.copy())
+                pos += k
+        ch.kernel_time()
+        bd = ch.kernel_breakdown()
+        ch.close()
+        return np.concatenate(outs, axis=1), bd
+
+    got, bd = run(False)
+    got_nc, bd_nc = run(True)
+    assert bd.get("k_copy2d(u history)", (0, 0))[1] >= 8 and "k_copy2d(u history)" not in bd_nc
+    assert bd["k_front"][1] == bd_nc["k_front"][1]
+    for s in range(S):
+        blocks = [orc.FreqShifter("f32", 1.0, 12345.0), orc.Filter.new("f32", lp), orc.Downsampler("f32", 16, 48000.0, 6000.0)]
+        chain = orc.Chain(blocks)
+        want, pos = [], 0
+        for k in script:
+            if k == "retune":
+                blocks[0].set_shift(-77777.0)
+            elif k == "interrupt":
+                chain.push(orc.Event("x", True))
+            elif k == "update":
+                blocks[1].update(orc.lowpass(2500.0))
+            else:
+                for c in range(k):
+                    want += [m.chunk for m in chain.push(orc.Samples(sr, x[s, (pos + c) * n:(pos + c + 1) * n])) if isinstance(m, orc.Samples)]
+                pos += k
+        want = np.concatenate(want)
+        assert got.shape[1] == len(want) == got_nc.shape[1]
+        assert orc.rel_l2(got[s], want) <= 1e-5 and orc.rel_l2(got_nc[s], want) <= 1e-5
+        assert orc.rel_l2(got[s], got_nc[s]) <= 2e-6
