@@ -41,7 +41,7 @@ UNIT = "MS/s"
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from the `ncu --set full`
 # capture of this very command (profiles/r01_ncu_k_front_k_poly2.txt), keyed by (kernel, streams, chunks)
-NCU_TRAFFIC = {("k_front", 4096, 50): 6.859980e9 + 1.622492e9}
+NCU_TRAFFIC = {("k_front", 4096, 50): 6.715032e9 + 1.591369e9}
 
 
 def stream_shift(stream_id: int) -> float:
