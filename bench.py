@@ -224,6 +224,7 @@ def run_cuda(args):
         import torch.distributed as dist_mod
 
         dist = dist_mod
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")  # the gather runs under the next push's kernels
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     S, C = args.streams, args.chunks
@@ -312,7 +313,45 @@ def run_cuda(args):
         gather = {"collective": "nccl all_gather of one step's outputs (outside the timed region)", "ms": gms,
                   "bytes_per_rank": mine.numel() * 4, "bytes_total": everyone.numel() * 4,
                   "share_of_step": gms / (elapsed_ms / args.steps), "own_slice_intact": same}
-        del everyone, mine
+        # the same steps again with every step's gather running on a second stream while the next step computes
+        # (two output buffers; a push waits for the gather that last read its buffer)
+        ys = [y, torch.zeros_like(y)]
+        side = torch.cuda.Stream(priority=-1)  # its kernels take freed SM slots ahead of the next push's CTAs
+        staged = torch.empty_like(mine)
+        busy = [None, None]
+
+        def overlapped(k_steps):
+            for i in range(k_steps):
+                yi = ys[i & 1]
+                with torch.cuda.stream(ext):
+                    if busy[i & 1] is not None:
+                        ext.wait_event(busy[i & 1])
+                    chain.push_device(SAMPLE_RATE, CHUNK_LEN, C, x.data_ptr(), length, yi.data_ptr(), cap, cap)
+                    done = torch.cuda.Event()
+                    done.record(ext)
+                with torch.cuda.stream(side):
+                    side.wait_event(done)
+                    staged.copy_(yi[:, :per_stream])
+                    dist.all_gather_into_tensor(everyone, staged)
+                    busy[i & 1] = torch.cuda.Event()
+                    busy[i & 1].record(side)
+
+        overlapped(2)
+        torch.cuda.synchronize()
+        dist.barrier()
+        o0, o1, o2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        o0.record(ext)
+        overlapped(args.steps)
+        o1.record(ext)
+        o2.record(side)
+        chain.sync()
+        torch.cuda.synchronize()
+        t = torch.tensor([max(o0.elapsed_time(o1), o0.elapsed_time(o2))], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        oms = float(t.item())
+        gather["overlapped"] = {"ms_per_step": oms / args.steps, "value": S * length * world * args.steps / (oms * 1e-3) / 1e6, "unit": UNIT,
+                                "what": "steps with each step's all_gather on a second stream under the next step's kernels"}
+        del everyone, mine, staged, ys
 
     # ---- end to end: pinned host chunks in, host result out, through rr_chain_push ----
     e2e = None
