@@ -241,6 +241,7 @@ struct rr_chain {
     bool allow_poly = true;  // rr_chain_set_fast_path
     bool allow_poly2 = true; // RR_DISABLE_POLY2=1: keep the generic polyphase kernel (k_poly) for f32 too
     size_t big_os_scratch_bytes = (size_t)2 << 30;  // RR_BIG_OS_SCRATCH_MB
+    bool allow_sab = true;    // RR_DISABLE_SAB=1: short pushes keep one low-rate block (and inverse round) per stream
     bool allow_ucache = true; // RR_DISABLE_UCACHE=1: recompute the history rows of u from hist2 in every push
     bool allow_front = true; // RR_DISABLE_FRONT=1: k_poly2 on all P branches instead of the rank-reduced front end
     // optional CUDA-event timing of the dominant kernel of a push (bench.py's roofline)
@@ -1073,7 +1074,13 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
                     const long long pad_rows = 512;
                     const long long u_stride = (((n_rows + 127) / 128 * 128 + pad_rows) * RK + 1) / 2 * 2;
                     if (n_rows < (1LL << 27)) {
-                        const size_t ubytes = (size_t)S * (size_t)u_stride * 2 * sizeof(float);
+                        // short pushes (one block per stream): the low-rate part takes runs of sab_nb streams as the blocks of
+                        // one "stream", so that an inverse round serves several streams (PolyArgs::sab_*)
+                        const int n_blocks1 = (int)((n_out - 1) / ds.poly2_V + 1);
+                        const int halves_total = 2 * c->ctx->sm_count;
+                        const int sab_nb = (c->allow_sab && n_blocks1 == 1 && S > halves_total) ? (S + halves_total - 1) / halves_total : 0;
+                        const size_t S_alloc = sab_nb ? (size_t)((S + sab_nb - 1) / sab_nb) * sab_nb : (size_t)S;
+                        const size_t ubytes = S_alloc * (size_t)u_stride * 2 * sizeof(float);
                         DevBuf& ub = ds.ubuf[ds.ubuf_cur];
                         if (ub.bytes < ubytes || ds.ubuf_stride[ds.ubuf_cur] != u_stride) {
                             // a new layout: the pad rows must read as zeros (they only ever feed outputs that are not stored,
@@ -1153,6 +1160,21 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
                         b.ngrp = ngrp;
                         b.out = obase;
                         b.out_stride = ostride;
+                        int S2 = S;  // streams of the low-rate launch
+                        if (sab_nb) {
+                            int nb2 = std::min(G2, sab_nb);
+                            while (nb2 > 1 && rr::poly2_smem_bytes(G2, nb2) > (size_t)226 * 1024) --nb2;
+                            const int groups2 = (sab_nb + nb2 - 1) / nb2;
+                            b.n_blocks = sab_nb;
+                            b.nbpc = (sab_nb + groups2 - 1) / groups2;
+                            b.ngrp = groups2;  // a half takes all groups of its run of streams
+                            b.sab_blocks = sab_nb;
+                            b.sab_streams = S;
+                            b.sab_in_step = u_stride;
+                            b.in_stride = (long long)sab_nb * u_stride;
+                            b.len = (long long)sab_nb * u_stride;
+                            S2 = (S + sab_nb - 1) / sab_nb;
+                        }
                         const long long emit = (long long)da.out.len();
                         if (direct && direct->user_out && ca == 0 && emit >= (long long)da.pending_before && emit > 0) {
                             // new output o lands at emitted position pending_before + o
@@ -1163,7 +1185,13 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
                             b.out_split = emit - (long long)da.pending_before;
                             direct->done = true;
                         }
-                        RR_TIMED_LAUNCH(c, "k_poly2", 1, rr::launch_poly2(G2, S, b, st));
+                        if (sab_nb) {
+                            b.sab_out_step = b.out_stride;
+                            b.sab_out2_step = b.out2_stride;
+                            b.out_stride *= sab_nb;
+                            b.out2_stride *= sab_nb;
+                        }
+                        RR_TIMED_LAUNCH(c, "k_poly2", 1, rr::launch_poly2(G2, S2, b, st));
                         ds.ucache_valid = true;
                         ds.ucache_rows = n_rows;
                         ds.ubuf_cur ^= 1;
@@ -1881,6 +1909,7 @@ int rr_chain_create(rr_ctx* ctx, const rr_chain_desc* desc, rr_chain** out) {
     if (const char* e = std::getenv("RR_DISABLE_POLY2")) c->allow_poly2 = !(e[0] == '1');
     if (const char* e = std::getenv("RR_DISABLE_FRONT")) c->allow_front = !(e[0] == '1');
     if (const char* e = std::getenv("RR_DISABLE_UCACHE")) c->allow_ucache = !(e[0] == '1');
+    if (const char* e = std::getenv("RR_DISABLE_SAB")) c->allow_sab = !(e[0] == '1');
     if (const char* e = std::getenv("RR_BIG_OS_SCRATCH_MB")) c->big_os_scratch_bytes = (size_t)std::max(1, std::atoi(e)) << 20;
     RR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     *out = c.release();

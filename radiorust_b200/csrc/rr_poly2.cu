@@ -199,7 +199,10 @@ __global__ void __launch_bounds__(2 * P2Cfg<G>::THREADS, 1) k_poly2(const __grid
     // the pushed samples is moved back by `d` rows so that it still lies inside them (its first d
     // outputs repeat the previous block's and are not stored).
     const int need = (K2 - 1) * Pd + NR * G;  // samples a tile sweep touches
-    const int boff0 = (int)((a.I_lo - a.Lmax) * Pd - a.J0 - Pd), bstep = a.V * Pd;  // window start of block 0, per block
+    const bool sab = a.sab_blocks > 0;  // streams as blocks (short pushes)
+    const int boff0 = (int)((a.I_lo - a.Lmax) * Pd - a.J0 - Pd);  // window start of block 0
+    const int bstep = sab ? (int)a.sab_in_step : a.V * Pd;       // per block
+    const int istep = sab ? 0 : a.V;                              // low-rate index step per block
     // only the last block can run past the end; block 0 has no predecessor to cover skipped outputs
     int last_shift = 0;
     {
@@ -207,7 +210,7 @@ __global__ void __launch_bounds__(2 * P2Cfg<G>::THREADS, 1) k_poly2(const __grid
         const int boff = boff0 + blk * bstep;
         if (blk > 0 && boff + need > len) {
             const int d = (boff + need - len + Pd - 1) / Pd;
-            const long long Ibase = a.I_lo + (long long)blk * a.V - a.Lmax;
+            const long long Ibase = a.I_lo + (long long)blk * istep - a.Lmax;
             // with Q == 1 the l = -1 slot of every branch filter is empty, so row K-1 is a valid output too:
             // the moved block may use it to reach m_hi
             if (d < a.V && boff - d * Pd >= 0 && a.m_hi - (Ibase - d) <= K2 - 1) last_shift = d;
@@ -536,7 +539,11 @@ __global__ void __launch_bounds__(2 * P2Cfg<G>::THREADS, 1) k_poly2(const __grid
             __syncwarp();
             const int blk = blk0 + (active ? job : 0);
             const int d = block_shift(blk);
-            const long long Ibase = a.I_lo + (long long)blk * a.V - a.Lmax - d;
+            const long long Ibase = a.I_lo + (long long)blk * istep - a.Lmax - d;
+            // streams as blocks: block blk is real stream s*sab_blocks + blk with its own destinations
+            const bool exists = !sab || (long long)s * a.sab_blocks + blk < a.sab_streams;
+            float2* outb = sab ? out + (long long)blk * a.sab_out_step : out;
+            float2* out2b = (sab && out2 != nullptr) ? out2 + (long long)blk * a.sab_out2_step : out2;
 #pragma unroll
             for (int which = 0; which < 2; ++which) {
                 pc x[16];
@@ -549,9 +556,9 @@ __global__ void __launch_bounds__(2 * P2Cfg<G>::THREADS, 1) k_poly2(const __grid
                         const int i = t + 16 * which + 32 * k2;
                         if (i >= a.Lmax + d && i < a.Lmax + a.V + (d > 0 ? 1 : 0)) {
                             const long long m = Ibase + i;  // Q == 1
-                            if (m >= a.m_lo && m <= a.m_hi) {
+                            if (m >= a.m_lo && m <= a.m_hi && exists) {
                                 const long long o = m - a.m0 - 1;
-                                float2* dst = (out2 != nullptr && o >= a.out_split) ? out2 + (o - a.out_split) : out + o;
+                                float2* dst = (out2b != nullptr && o >= a.out_split) ? out2b + (o - a.out_split) : outb + o;
                                 *dst = make_float2(x[k2].x, -x[k2].y);
                             }
                         }

@@ -331,3 +331,41 @@ def test_kept_u_rows_match_recomputed_history(ctx, monkeypatch):
         assert got.shape[1] == len(want) == got_nc.shape[1]
         assert orc.rel_l2(got[s], want) <= 1e-5 and orc.rel_l2(got_nc[s], want) <= 1e-5
         assert orc.rel_l2(got[s], got_nc[s]) <= 2e-6
+
+
+def test_short_pushes_of_many_streams_group_streams_per_inverse_round(ctx, monkeypatch):
+    """More streams than CTA halves and one low-rate block per stream (pushes of 1-5 chunks): k_poly2 takes runs of
+    streams as the blocks of one launch "stream" (PolyArgs::sab_*).  Same arithmetic per block, so the result is
+    bit-identical to RR_DISABLE_SAB=1; 601 streams leave two padded, non-existent streams in the last run."""
+    import radiorust_b200 as rr
+
+    sr, n, S = 2_400_000.0, 4096, 601
+    lp = orc.lowpass(3000.0)
+    rng = np.random.default_rng(7)
+    sizes = [3, 1, 2, 1, 5, 1, 1, 9, 2]
+    total = sum(sizes)
+    x = (rng.standard_normal((S, total * n)) + 1j * rng.standard_normal((S, total * n))).astype(np.complex64)
+    shifts = [(s * 577) % 2_400_000 - 1_200_000 for s in range(S)]
+
+    def run(disable):
+        if disable:
+            monkeypatch.setenv("RR_DISABLE_SAB", "1")
+        else:
+            monkeypatch.delenv("RR_DISABLE_SAB", raising=False)
+        ch = rr.Chain(ctx, [rr.FreqShifter(0.0), rr.Filter.new(lp), rr.Downsampler(16, 48000.0, 6000.0)], "f32", n_streams=S)
+        ch.set_shifts(0, shifts)
+        outs, pos = [], 0
+        for k in sizes:
+            y, _ = ch.push(sr, x[:, pos * n:(pos + k) * n], n)
+            outs.append(y.copy())
+            pos += k
+        ch.close()
+        return np.concatenate(outs, axis=1)
+
+    got, ref = run(False), run(True)
+    assert got.shape == ref.shape and got.shape[1] > 1000
+    assert np.array_equal(got, ref)
+    for s in (0, 299, 600):
+        chain = orc.Chain([orc.FreqShifter("f32", 1.0, float(shifts[s])), orc.Filter.new("f32", lp), orc.Downsampler("f32", 16, 48000.0, 6000.0)])
+        want = chain.run(sr, x[s], n)
+        assert len(want) == got.shape[1] and orc.rel_l2(got[s], want) <= 1e-5
