@@ -110,6 +110,36 @@ int main(int argc, char** argv) {
         return 1;
     }
     if (rr_chain_event(chain, 1) != RR_OK) return fail("rr_chain_event");
+    if (rr_chain_samples_lost_count(chain) != 0) return fail("no Rechunker/Overlapper: no SamplesLost");
+    {
+        /* Rechunker(256) -> FmMod: 100 samples stay in the partial chunk; an event drops them (one SamplesLost);
+         * 256 zeros then leave as one chunk of (cos 0, sin 0) */
+        rr_stage_desc tx[2];
+        memset(tx, 0, sizeof tx);
+        tx[0].kind = RR_STAGE_RECHUNK;
+        tx[0].output_chunk_len = 256;
+        tx[1].kind = RR_STAGE_FMMOD;
+        tx[1].deviation = 5000.0;
+        rr_chain_desc d2;
+        memset(&d2, 0, sizeof d2);
+        d2.dtype = RR_C32;
+        d2.n_streams = 1;
+        d2.n_stages = 2;
+        d2.stages = tx;
+        rr_chain* c2 = NULL;
+        if (rr_chain_create(ctx, &d2, &c2) != RR_OK) return fail("rr_chain_create (tx)");
+        memset(in, 0, 256 * 8);
+        size_t cnt = 7;
+        if (rr_chain_push(c2, 48000.0, 100, 1, in, 100, out, cap, cap, &cnt, &rate) != RR_OK || rr_chain_sync(c2) != RR_OK || cnt != 0)
+            return fail("Rechunker holds a partial chunk");
+        if (rr_chain_event(c2, 0) != RR_OK || rr_chain_samples_lost_count(c2) != 1) return fail("SamplesLost count");
+        if (rr_chain_set_output_chunk_len(c2, 0, 0) == RR_OK) return fail("chunk length 0 accepted");
+        if (rr_chain_push(c2, 48000.0, 256, 1, in, 256, out, cap, cap, &cnt, &rate) != RR_OK || rr_chain_sync(c2) != RR_OK || cnt != 256)
+            return fail("Rechunker emits a whole chunk");
+        for (size_t i = 0; i < 256; ++i)
+            if (out[2 * i] != 1.0f || out[2 * i + 1] != 0.0f) return fail("FmMod of silence");
+        rr_chain_destroy(c2);
+    }
     printf("abi_check ok: %zu output samples at %.0f S/s, plan %s, %llu kernel launches\n", total, rate, rr_chain_plan(chain),
            (unsigned long long)rr_kernel_launch_count());
     rr_pinned_free(ctx, in);
