@@ -206,6 +206,26 @@ def workload_config(args, world):
     }
 
 
+def bind_to_gpu_cpus(index):
+    """Keep this rank's threads (and, by first touch, its pinned host buffers) on the CPUs next to its GPU, as a
+    multi-GPU host application would: eight ranks copying from one NUMA node share that node's memory bandwidth.
+    Returns the number of CPUs bound to, or None when NVML / the affinity call is not available."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 # ---------------------------------------------------------------------------
 # CUDA arm
 # ---------------------------------------------------------------------------
@@ -219,6 +239,7 @@ def run_cuda(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_cpus(local) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -389,6 +410,7 @@ def run_cuda(args):
             "value": samples_step * world * e_steps / (ems * 1e-3) / 1e6, "unit": UNIT,
             "h2d_bytes_per_step": samples_step * 8, "d2h_bytes_per_step": d2h // e_steps, "steps": e_steps,
             "api": "rr_chain_push (pinned host chunks -> H2D -> kernels -> D2H), per rank",
+            "cpus_bound_per_rank": numa,
         }
         del hx, hy
 
