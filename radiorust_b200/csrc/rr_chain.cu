@@ -1078,8 +1078,9 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
                         // one "stream", so that an inverse round serves several streams (PolyArgs::sab_*)
                         const int n_blocks1 = (int)((n_out - 1) / ds.poly2_V + 1);
                         const int halves_total = 2 * c->ctx->sm_count;
-                        const int sab_nb = (c->allow_sab && n_blocks1 == 1 && S > halves_total) ? (S + halves_total - 1) / halves_total : 0;
-                        const size_t S_alloc = sab_nb ? (size_t)((S + sab_nb - 1) / sab_nb) * sab_nb : (size_t)S;
+                        const int sab_run = (c->allow_sab && n_blocks1 <= 3 && S > halves_total) ? (S + halves_total - 1) / halves_total : 0;  // streams
+                        const int sab_nb = sab_run * n_blocks1;  // blocks of a run
+                        const size_t S_alloc = sab_run ? (size_t)((S + sab_run - 1) / sab_run) * sab_run : (size_t)S;
                         const size_t ubytes = S_alloc * (size_t)u_stride * 2 * sizeof(float);
                         DevBuf& ub = ds.ubuf[ds.ubuf_cur];
                         if (ub.bytes < ubytes || ds.ubuf_stride[ds.ubuf_cur] != u_stride) {
@@ -1169,11 +1170,12 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
                             b.nbpc = (sab_nb + groups2 - 1) / groups2;
                             b.ngrp = groups2;  // a half takes all groups of its run of streams
                             b.sab_blocks = sab_nb;
+                            b.sab_rb = n_blocks1;
                             b.sab_streams = S;
                             b.sab_in_step = u_stride;
-                            b.in_stride = (long long)sab_nb * u_stride;
-                            b.len = (long long)sab_nb * u_stride;
-                            S2 = (S + sab_nb - 1) / sab_nb;
+                            b.in_stride = (long long)sab_run * u_stride;
+                            b.len = (long long)sab_run * u_stride;
+                            S2 = (S + sab_run - 1) / sab_run;
                         }
                         const long long emit = (long long)da.out.len();
                         if (direct && direct->user_out && ca == 0 && emit >= (long long)da.pending_before && emit > 0) {
@@ -1188,8 +1190,8 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
                         if (sab_nb) {
                             b.sab_out_step = b.out_stride;
                             b.sab_out2_step = b.out2_stride;
-                            b.out_stride *= sab_nb;
-                            b.out2_stride *= sab_nb;
+                            b.out_stride *= sab_run;
+                            b.out2_stride *= sab_run;
                         }
                         RR_TIMED_LAUNCH(c, "k_poly2", 1, rr::launch_poly2(G2, S2, b, st));
                         ds.ucache_valid = true;

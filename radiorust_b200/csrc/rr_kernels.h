@@ -169,12 +169,12 @@ template <typename T> struct PolyArgs {
     // (the samples behind the last whole output chunk: the Downsampler's next pending part), the others to out[o]
     void* out2;
     long long out2_stride, out_split;  // out2 == nullptr: everything to `out`
-    // k_poly2, streams as blocks (sab_blocks > 0; used when every stream has ONE block, i.e. short pushes): a "stream" of
-    // this launch is a run of sab_blocks real streams and its block b is the single block of real stream
-    // s*sab_blocks + b -- window start b*sab_in_step, same output indices for every b, destinations moved by
-    // b*sab_out_step (out) and b*sab_out2_step (out2); real streams >= sab_streams do not exist.  One inverse
-    // round then serves up to nbpc streams instead of one.
-    int sab_blocks, sab_streams;
+    // k_poly2, streams as blocks (sab_blocks > 0; used when a stream has only sab_rb <= 3 blocks, i.e. short pushes): a
+    // "stream" of this launch is a run of sab_blocks/sab_rb real streams; its block b is block b % sab_rb of real
+    // stream s*(sab_blocks/sab_rb) + b/sab_rb -- window start (b/sab_rb)*sab_in_step + (b%sab_rb)*V*P, destinations
+    // moved by (b/sab_rb)*sab_out_step (out) and *sab_out2_step (out2); real streams >= sab_streams do not exist.
+    // One inverse round then serves up to nbpc blocks of several streams instead of one stream's few.
+    int sab_blocks, sab_rb, sab_streams;
     long long sab_in_step, sab_out_step, sab_out2_step;
     long long J0, m0;      // filter-output samples consumed / outputs emitted before this push (reduced)
     long long m_lo, m_hi;  // outputs m to produce (inclusive)

@@ -201,23 +201,28 @@ __global__ void __launch_bounds__(2 * P2Cfg<G>::THREADS, 1) k_poly2(const __grid
     const int need = (K2 - 1) * Pd + NR * G;  // samples a tile sweep touches
     const bool sab = a.sab_blocks > 0;  // streams as blocks (short pushes)
     const int boff0 = (int)((a.I_lo - a.Lmax) * Pd - a.J0 - Pd);  // window start of block 0
-    const int bstep = sab ? (int)a.sab_in_step : a.V * Pd;       // per block
-    const int istep = sab ? 0 : a.V;                              // low-rate index step per block
+    // block blk of a run of streams: real stream blk / rb within the run, its block blk % rb
+    const int rb = sab ? max(1, a.sab_rb) : 1;
+    auto blk_stream = [&](int blk) -> int { return sab ? blk / rb : 0; };
+    auto blk_block = [&](int blk) -> int { return sab ? blk % rb : blk; };
+    auto blk_start = [&](int blk) -> int {  // window start without any shift
+        return boff0 + blk_stream(blk) * (int)a.sab_in_step + blk_block(blk) * a.V * Pd;
+    };
     // only the last block can run past the end; block 0 has no predecessor to cover skipped outputs
     int last_shift = 0;
     {
         const int blk = a.n_blocks - 1;
-        const int boff = boff0 + blk * bstep;
+        const int boff = blk_start(blk);
         if (blk > 0 && boff + need > len) {
             const int d = (boff + need - len + Pd - 1) / Pd;
-            const long long Ibase = a.I_lo + (long long)blk * istep - a.Lmax;
+            const long long Ibase = a.I_lo + (long long)blk_block(blk) * a.V - a.Lmax;
             // with Q == 1 the l = -1 slot of every branch filter is empty, so row K-1 is a valid output too:
             // the moved block may use it to reach m_hi
             if (d < a.V && boff - d * Pd >= 0 && a.m_hi - (Ibase - d) <= K2 - 1) last_shift = d;
         }
     }
     auto block_shift = [&](int blk) -> int { return blk == a.n_blocks - 1 ? last_shift : 0; };
-    auto block_off = [&](int blk) -> int { return boff0 + blk * bstep - block_shift(blk) * Pd; };
+    auto block_off = [&](int blk) -> int { return blk_start(blk) - block_shift(blk) * Pd; };
     auto is_interior = [&](int boff) -> bool { return boff >= 0 && boff + need <= len; };
     // the tile of round Rg of the group of stream `ss` that starts at block blk_first (nothing for edge blocks)
     auto issue_tile = [&](int ss, int blk_first, int blk_end, int Rg) {
@@ -539,11 +544,12 @@ __global__ void __launch_bounds__(2 * P2Cfg<G>::THREADS, 1) k_poly2(const __grid
             __syncwarp();
             const int blk = blk0 + (active ? job : 0);
             const int d = block_shift(blk);
-            const long long Ibase = a.I_lo + (long long)blk * istep - a.Lmax - d;
-            // streams as blocks: block blk is real stream s*sab_blocks + blk with its own destinations
-            const bool exists = !sab || (long long)s * a.sab_blocks + blk < a.sab_streams;
-            float2* outb = sab ? out + (long long)blk * a.sab_out_step : out;
-            float2* out2b = (sab && out2 != nullptr) ? out2 + (long long)blk * a.sab_out2_step : out2;
+            const long long Ibase = a.I_lo + (long long)blk_block(blk) * a.V - a.Lmax - d;
+            // streams as blocks: the block belongs to real stream s*(sab_blocks/rb) + blk/rb with its own destinations
+            const int rs = blk_stream(blk);
+            const bool exists = !sab || (long long)s * (a.sab_blocks / rb) + rs < a.sab_streams;
+            float2* outb = sab ? out + (long long)rs * a.sab_out_step : out;
+            float2* out2b = (sab && out2 != nullptr) ? out2 + (long long)rs * a.sab_out2_step : out2;
 #pragma unroll
             for (int which = 0; which < 2; ++which) {
                 pc x[16];

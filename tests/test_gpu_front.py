@@ -334,15 +334,15 @@ def test_kept_u_rows_match_recomputed_history(ctx, monkeypatch):
 
 
 def test_short_pushes_of_many_streams_group_streams_per_inverse_round(ctx, monkeypatch):
-    """More streams than CTA halves and one low-rate block per stream (pushes of 1-5 chunks): k_poly2 takes runs of
-    streams as the blocks of one launch "stream" (PolyArgs::sab_*).  Same arithmetic per block, so the result is
+    """More streams than CTA halves and at most three low-rate blocks per stream (pushes of 1-15 chunks): k_poly2 takes
+    runs of streams as the blocks of one launch "stream" (PolyArgs::sab_*).  Same arithmetic per block, so the result is
     bit-identical to RR_DISABLE_SAB=1; 601 streams leave two padded, non-existent streams in the last run."""
     import radiorust_b200 as rr
 
     sr, n, S = 2_400_000.0, 4096, 601
     lp = orc.lowpass(3000.0)
     rng = np.random.default_rng(7)
-    sizes = [3, 1, 2, 1, 5, 1, 1, 9, 2]
+    sizes = [3, 1, 2, 1, 5, 1, 1, 9, 2, 12, 7, 16, 1]  # one, two and three low-rate blocks per stream; 16 chunks: four (per-stream form)
     total = sum(sizes)
     x = (rng.standard_normal((S, total * n)) + 1j * rng.standard_normal((S, total * n))).astype(np.complex64)
     shifts = [(s * 577) % 2_400_000 - 1_200_000 for s in range(S)]
