@@ -16,15 +16,17 @@
 
 namespace rr {
 
-constexpr int kColG = 8;
+// columns a CTA interleaves
+template <typename T> constexpr int kColGOf = 8;  // (16 f32 columns = 128-byte rows was measured: slower at 2^17 points, 1024-thread CTAs)
 
 template <typename T, int NA>
-__global__ void __launch_bounds__(PlanFor<T, NA, kColG>::type::NT* kColG)
+__global__ void __launch_bounds__(PlanFor<T, NA, kColGOf<T>>::type::NT* kColGOf<T>)
 k_big_cols_fwd(const cx<T>* __restrict__ in, long long in_stride, const cx<T>* __restrict__ hist, long long hist_stride, int first_chunk, int n_blocks,
                int Nb, cx<T>* __restrict__ scratch, const cx<T>* __restrict__ twN, const cx<T>* __restrict__ twA) {
-    using P = typename PlanFor<T, NA, kColG>::type;
+    using P = typename PlanFor<T, NA, kColGOf<T>>::type;
     constexpr int NT = P::NT, R1 = P::R1, B1 = P::B1, S1 = P::S1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int kColG = kColGOf<T>;
     const int g = threadIdx.x % kColG, t = threadIdx.x / kColG;
     cx<T>* sm = reinterpret_cast<cx<T>*>(smem_raw) + g;
     const int w = blockIdx.y;
@@ -53,20 +55,25 @@ k_big_cols_fwd(const cx<T>* __restrict__ in, long long in_stride, const cx<T>* _
     P::template p3<+1>(sm, t);
     __syncthreads();
     cx<T>* dst = scratch + (long long)w * NA * Nb;
+    // four-step twiddle W_N^(k1*col), k1 = t + NT*i: two gathered table reads per thread and a rotation per step (a
+    // gathered 8/16-byte read per point cost 32 wavefronts per warp instruction and saturated the LSU pipe)
+    cx<T> tw = ld_cx(&twN[(long long)t * col]);  // k1*col < Na*Nb = N
+    const cx<T> tw_step = ld_cx(&twN[(long long)NT * col]);
     for (int k1 = t; k1 < NA; k1 += NT) {
         const cx<T> x = ld_cx(&sm[P::sidx(P::bin_position(k1))]);
-        const cx<T> tw = ld_cx(&twN[(long long)k1 * col]);  // k1*col < Na*Nb = N
         st_cx(&dst[(long long)k1 * Nb + col], cmul(x, tw));
+        tw = cmul(tw, tw_step);
     }
 }
 
 template <typename T, int NA>
-__global__ void __launch_bounds__(PlanFor<T, NA, kColG>::type::NT* kColG)
+__global__ void __launch_bounds__(PlanFor<T, NA, kColGOf<T>>::type::NT* kColGOf<T>)
 k_big_cols_inv(const cx<T>* __restrict__ scratch, int n_blocks, int Nb, const cx<T>* __restrict__ twN,
                const cx<T>* __restrict__ twA, cx<T>* __restrict__ out, long long out_stride) {
-    using P = typename PlanFor<T, NA, kColG>::type;
+    using P = typename PlanFor<T, NA, kColGOf<T>>::type;
     constexpr int NT = P::NT, R1 = P::R1, B1 = P::B1, S1 = P::S1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int kColG = kColGOf<T>;
     const int g = threadIdx.x % kColG, t = threadIdx.x / kColG;
     cx<T>* sm = reinterpret_cast<cx<T>*>(smem_raw) + g;
     const int w = blockIdx.y;
@@ -77,10 +84,12 @@ k_big_cols_inv(const cx<T>* __restrict__ scratch, int n_blocks, int Nb, const cx
 
     P plan;
     plan.init(twA, t);
+    cx<T> tw = ld_cx(&twN[(long long)t * col]);
+    const cx<T> tw_step = ld_cx(&twN[(long long)NT * col]);
     for (int k1 = t; k1 < NA; k1 += NT) {
         const cx<T> x = ld_cx(&src[(long long)k1 * Nb + col]);
-        const cx<T> tw = ld_cx(&twN[(long long)k1 * col]);
         st_cx(&sm[P::sidx(P::bin_position(k1))], cmulc(x, tw));
+        tw = cmul(tw, tw_step);
     }
     __syncthreads();
     P::template p3<-1>(sm, t);
@@ -181,7 +190,8 @@ template <> long long big_os_hperm_index<double>(int n, long long k) {
 }
 
 template <typename T, int NA> static cudaError_t launch_cols(bool fwd, int Nb, int n_streams, const BigOsArgs<T>& a, cudaStream_t st) {
-    using P = typename PlanFor<T, NA, kColG>::type;
+    constexpr int kColG = kColGOf<T>;
+    using P = typename PlanFor<T, NA, kColGOf<T>>::type;
     const size_t smem = sizeof(cx<T>) * P::SMEM_ELEMS;
     dim3 grid((unsigned)(Nb / kColG), (unsigned)(n_streams * a.n_blocks));
     cudaError_t e;
