@@ -52,17 +52,25 @@ k_big_cols_fwd(const cx<T>* __restrict__ in, long long in_stride, const cx<T>* _
     __syncthreads();
     plan.template p2<+1>(sm, t);
     __syncthreads();
-    P::template p3<+1>(sm, t);
-    __syncthreads();
+    // pass 3 in registers, then straight to the scratch: run u = (k1, k2) holds bins k = k1 + R1*k2 + R1*R2*k3 of its
+    // column, each times the four-step twiddle W_N^(k*col) -- one gathered table read per run and a rotation per bin
+    // (a gathered read per point cost 32 wavefronts per warp instruction and saturated the LSU pipe)
+    constexpr int R2 = P::R2, R3 = P::R3, B3 = P::B3;
     cx<T>* dst = scratch + (long long)w * NA * Nb;
-    // four-step twiddle W_N^(k1*col), k1 = t + NT*i: two gathered table reads per thread and a rotation per step (a
-    // gathered 8/16-byte read per point cost 32 wavefronts per warp instruction and saturated the LSU pipe)
-    cx<T> tw = ld_cx(&twN[(long long)t * col]);  // k1*col < Na*Nb = N
-    const cx<T> tw_step = ld_cx(&twN[(long long)NT * col]);
-    for (int k1 = t; k1 < NA; k1 += NT) {
-        const cx<T> x = ld_cx(&sm[P::sidx(P::bin_position(k1))]);
-        st_cx(&dst[(long long)k1 * Nb + col], cmul(x, tw));
-        tw = cmul(tw, tw_step);
+    const cx<T> tw_step = ld_cx(&twN[(long long)(R1 * R2) * col]);  // R1*R2 < Na, col < Nb: inside the table
+#pragma unroll
+    for (int rb = 0; rb < B3; ++rb) {
+        const int u = B3 * t + rb;
+        cx<T> y[R3];
+        P::p3_load(sm, u, y);
+        dft_regs<R3, +1, T>(y);
+        const int k0 = u / R2 + R1 * (u % R2);
+        cx<T> tw = ld_cx(&twN[(long long)k0 * col]);
+#pragma unroll
+        for (int k3 = 0; k3 < R3; ++k3) {
+            st_cx(&dst[(long long)(k0 + R1 * R2 * k3) * Nb + col], cmul(y[k3], tw));
+            tw = cmul(tw, tw_step);
+        }
     }
 }
 
@@ -84,15 +92,23 @@ k_big_cols_inv(const cx<T>* __restrict__ scratch, int n_blocks, int Nb, const cx
 
     P plan;
     plan.init(twA, t);
-    cx<T> tw = ld_cx(&twN[(long long)t * col]);
-    const cx<T> tw_step = ld_cx(&twN[(long long)NT * col]);
-    for (int k1 = t; k1 < NA; k1 += NT) {
-        const cx<T> x = ld_cx(&src[(long long)k1 * Nb + col]);
-        st_cx(&sm[P::sidx(P::bin_position(k1))], cmulc(x, tw));
-        tw = cmul(tw, tw_step);
+    // the mirror image of the forward kernel's tail: bins straight from the scratch into pass 3's registers
+    constexpr int R2 = P::R2, R3 = P::R3, B3 = P::B3;
+    const cx<T> tw_step = ld_cx(&twN[(long long)(R1 * R2) * col]);
+#pragma unroll
+    for (int rb = 0; rb < B3; ++rb) {
+        const int u = B3 * t + rb;
+        const int k0 = u / R2 + R1 * (u % R2);
+        cx<T> tw = ld_cx(&twN[(long long)k0 * col]);
+        cx<T> y[R3];
+#pragma unroll
+        for (int k3 = 0; k3 < R3; ++k3) {
+            y[k3] = cmulc(ld_cx(&src[(long long)(k0 + R1 * R2 * k3) * Nb + col]), tw);
+            tw = cmul(tw, tw_step);
+        }
+        dft_regs<R3, -1, T>(y);
+        P::p3_store(sm, u, y);
     }
-    __syncthreads();
-    P::template p3<-1>(sm, t);
     __syncthreads();
     plan.template p2<-1>(sm, t);
     __syncthreads();
