@@ -32,15 +32,18 @@ template <typename T, int R1_, int R2_, int R3_, int NT_, int G_ = 1> struct Fft
     static constexpr int B1 = N / R1 / NT, B2 = N / R2 / NT, B3 = N / R3 / NT;
     static_assert(B1 * R1 * NT == N && B2 * R2 * NT == N && B3 * R3 * NT == N, "thread count must divide every pass");
     static_assert(R3 >= 2 && (R3 & (R3 - 1)) == 0, "R3 must be a power of two");
-    // padding: PAD elements after every run of R3 (keeps pass-3's per-thread
-    // contiguous runs on distinct banks and 16-byte aligned)
-    static constexpr int PAD = (sizeof(T) == 4) ? 2 : 1;
+    // padding: PAD elements after every run of R3.  One element: pass 3's per-thread runs start (R3+1)*sizeof(cx) bytes
+    // apart (all of a half warp's 8-byte pieces on distinct banks), and the groups of R3 lanes that pass 2 puts
+    // (R2*R3 + R2)*sizeof(cx) bytes apart alternate between the two halves of the 128-byte bank window.  (Two elements --
+    // 16-byte aligned runs and vector accesses for f32 -- were measured 4-9 % slower in the overlap-save kernels: the
+    // vector stores of pass 1 and the 8-byte accesses of pass 2 then take twice their minimum of wavefronts.)
+    static constexpr int PAD = 1;
     static constexpr int LOG_R3 = ilog2c(R3);
     static constexpr int G = G_;
     static constexpr int SMEM_ELEMS = G * (N + PAD * (N / R3));
-    static constexpr bool VEC1 = (G == 1) && (sizeof(T) == 4) && (B1 % 2 == 0);
-    static constexpr bool VEC2 = (G == 1) && (sizeof(T) == 4) && (B2 % 2 == 0);
-    static constexpr bool VEC3 = (G == 1) && (sizeof(T) == 4);
+    static constexpr bool VEC1 = (G == 1) && (sizeof(T) == 4) && (B1 % 2 == 0) && (PAD % 2 == 0);
+    static constexpr bool VEC2 = (G == 1) && (sizeof(T) == 4) && (B2 % 2 == 0) && (PAD % 2 == 0);
+    static constexpr bool VEC3 = (G == 1) && (sizeof(T) == 4) && (PAD % 2 == 0);
 
     __host__ __device__ static constexpr int sidx(int p) { return G * (p + PAD * (p >> LOG_R3)); }
 
