@@ -1093,13 +1093,13 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
                         // history rows: kept from the previous push when it went through here too, else recomputed from hist2
                         const long long Lh = ds.poly_Lmax;
                         const bool cached = was_ucache_valid && c->allow_ucache && ca == 0 && ds.ucache_rows >= Lh && n_out > 0;
-                        if (cached) {
-                            const int pv = ds.ubuf_cur ^ 1;
-                            const char* src = (const char*)ds.ubuf[pv].p + (size_t)(ds.ucache_rows - Lh) * RK * 2 * sizeof(float);
-                            RR_TIMED_LAUNCH(c, "k_copy2d(u history)", 1,
-                                            rr::launch_copy2d<float>(src, ds.ubuf_stride[pv], ub.p, u_stride, Lh * RK, S, st));
-                        }
                         rr::FrontArgs fa{};
+                        if (cached) {  // k_front moves them over itself
+                            const int pv = ds.ubuf_cur ^ 1;
+                            fa.kept_src = (const char*)ds.ubuf[pv].p + (size_t)(ds.ucache_rows - Lh) * RK * 2 * sizeof(float);
+                            fa.kept_stride = ds.ubuf_stride[pv];
+                            fa.kept_rows = (int)Lh;
+                        }
                         fa.in = a.in;
                         fa.in_stride = a.in_stride;
                         fa.len = a.len;

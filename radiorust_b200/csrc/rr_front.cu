@@ -152,6 +152,14 @@ __global__ void __launch_bounds__(FR_WARPS * 32, 4) k_front(const __grid_constan
 #pragma unroll
     for (int q = 0; q < FR_STAGES - 1; ++q) issue(q);
 
+    if (a.kept_rows > 0 && tile0 == 0) {
+        // the history rows of u kept from the previous push (its buffer) move in front of this push's rows, while the
+        // first tile is on its way
+        const float4* __restrict__ src4 = reinterpret_cast<const float4*>(reinterpret_cast<const float2*>(a.kept_src) + (long long)s * a.kept_stride);
+        float4* __restrict__ dst4 = u - (long long)a.kept_rows * RK / 2;
+        for (int e = lane; e < a.kept_rows * RK / 2; e += 32) dst4[e] = __ldg(src4 + e);
+    }
+
     uint32_t phase = 0;  // bit q: parity of ring slot q's next completion
     pc rowph(1.f, 0.f);
     for (int k = 0; k < n_tiles; ++k) {

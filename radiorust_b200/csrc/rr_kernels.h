@@ -219,6 +219,11 @@ struct FrontArgs {
     void* hist_out;
     long long hist_from, hist_stride;
     int hist_staged;       // != 0: history samples go through the shared-memory tile (coalesced stores)
+    // optional: kept_rows rows of u computed by the previous push ([S][kept_stride] complex, rows of rank_pad) are copied
+    // to the kept_rows rows in front of `u` (the history rows of this push)
+    const void* kept_src;
+    long long kept_stride;
+    int kept_rows;
 };
 bool front_supported(int rank_pad, long long P);
 cudaError_t launch_front(int rank_pad, int n_streams, const FrontArgs& a, cudaStream_t st);
