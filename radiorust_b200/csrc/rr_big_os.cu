@@ -122,39 +122,65 @@ k_big_cols_inv(const cx<T>* __restrict__ scratch, int n_blocks, int Nb, const cx
             st_cx(&dst[(long long)(B1 * t + bb + S1 * r) * Nb + col], v[bb][r]);
 }
 
-// ROWS rows per CTA, each by its own group of NT threads
+// ROWS rows per CTA, each by its own group of NT threads.  The groups are independent: they synchronise among
+// themselves only (a warp barrier up to 32 threads, a named barrier above), not across the CTA.
+template <int NT> __device__ __forceinline__ void row_group_sync(int grp) {
+    if constexpr (NT <= 32) {
+        __syncwarp();
+    } else {
+        asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(NT) : "memory");
+    }
+}
+
 template <typename T, int NB, int ROWS>
 __global__ void __launch_bounds__(PlanFor<T, NB>::type::NT* ROWS)
 k_big_rows(cx<T>* __restrict__ scratch, int Na, const cx<T>* __restrict__ hbig, const cx<T>* __restrict__ twB) {
     using P = typename PlanFor<T, NB>::type;
     constexpr int NT = P::NT, R1 = P::R1, B1 = P::B1, S1 = P::S1;
+    static_assert(NT <= 32 || ROWS <= 15, "one named barrier per row group");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int grp = threadIdx.x / NT, t = threadIdx.x % NT;
     cx<T>* sm = reinterpret_cast<cx<T>*>(smem_raw) + (size_t)grp * P::SMEM_ELEMS;
     const int k1 = blockIdx.x * ROWS + grp;
     cx<T>* row = scratch + ((long long)blockIdx.y * Na + k1) * NB;
     const cx<T>* hrow = hbig + (long long)k1 * NB;
+    // a thread's B1 consecutive points travel as 16-byte pairs where the type allows it
+    constexpr bool PAIRS = sizeof(T) == 4 && (B1 % 2) == 0;
 
     P plan;
     plan.init(twB, t);
     cx<T> v[B1][R1];
+    if constexpr (PAIRS) {
 #pragma unroll
-    for (int bb = 0; bb < B1; ++bb)
+        for (int bb = 0; bb < B1; bb += 2)
 #pragma unroll
-        for (int r = 0; r < R1; ++r) v[bb][r] = ld_cx(&row[B1 * t + bb + S1 * r]);
+            for (int r = 0; r < R1; ++r) ld_cx2(&row[B1 * t + bb + S1 * r], v[bb][r], v[bb + 1][r]);
+    } else {
+#pragma unroll
+        for (int bb = 0; bb < B1; ++bb)
+#pragma unroll
+            for (int r = 0; r < R1; ++r) v[bb][r] = ld_cx(&row[B1 * t + bb + S1 * r]);
+    }
     plan.p1_forward(sm, t, v);
-    __syncthreads();
+    row_group_sync<NT>(grp);
     plan.template p2<+1>(sm, t);
-    __syncthreads();
+    row_group_sync<NT>(grp);
     P::p3_fwd_mul_inv(sm, t, hrow);
-    __syncthreads();
+    row_group_sync<NT>(grp);
     plan.template p2<-1>(sm, t);
-    __syncthreads();
+    row_group_sync<NT>(grp);
     plan.p1_inverse(sm, t, v);
+    if constexpr (PAIRS) {
 #pragma unroll
-    for (int bb = 0; bb < B1; ++bb)
+        for (int bb = 0; bb < B1; bb += 2)
 #pragma unroll
-        for (int r = 0; r < R1; ++r) st_cx(&row[B1 * t + bb + S1 * r], v[bb][r]);
+            for (int r = 0; r < R1; ++r) st_cx2(&row[B1 * t + bb + S1 * r], v[bb][r], v[bb + 1][r]);
+    } else {
+#pragma unroll
+        for (int bb = 0; bb < B1; ++bb)
+#pragma unroll
+            for (int r = 0; r < R1; ++r) st_cx(&row[B1 * t + bb + S1 * r], v[bb][r]);
+    }
 }
 
 // ---- shapes -------------------------------------------------------------------
