@@ -78,28 +78,40 @@ template <typename T>
 __global__ void __launch_bounds__(256) k_hist2_update(const cx<T>* __restrict__ in, long long in_stride, long long len,
                                                       const cx<T>* __restrict__ hist2_in, cx<T>* __restrict__ hist2_out,
                                                       long long n, const NcoStream* __restrict__ nco, long long j_lo, long long j_hi) {
+    // four independent loads in flight per thread (coalesced: consecutive threads, consecutive entries), then the stores
+    constexpr int UNR = 4;
     const int s = blockIdx.y;
-    const long long j = j_lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= j_hi) return;
-    const long long off = len - 2 * n + j;
-    cx<T> v;
-    if (off >= 0) {
-        v = ld_cx(&in[(long long)s * in_stride + off]);
-        if (nco) {
-            const NcoStream ns = nco[s];
-            v = cmul(v, nco_phasor_at<T>(off, ns.idx, ns.numer_abs, ns.denom, ns.sign, (T)ns.start_phase));
+    const cx<T>* src_in = in + (long long)s * in_stride;
+    const cx<T>* src_h = hist2_in + (long long)s * 2 * n;
+    cx<T>* dst = hist2_out + (long long)s * 2 * n;
+    NcoStream ns{};
+    if (nco) ns = nco[s];
+    const long long j0 = j_lo + (long long)blockIdx.x * (256 * UNR) + threadIdx.x;
+    cx<T> v[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+        const long long j = j0 + 256 * u;
+        if (j < j_hi) {
+            const long long off = len - 2 * n + j;
+            v[u] = off >= 0 ? ld_cx(&src_in[off]) : ld_cx(&src_h[off + 2 * n]);
         }
-    } else {
-        v = ld_cx(&hist2_in[(long long)s * 2 * n + off + 2 * n]);
     }
-    st_cx(&hist2_out[(long long)s * 2 * n + j], v);
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+        const long long j = j0 + 256 * u;
+        if (j < j_hi) {
+            const long long off = len - 2 * n + j;
+            if (off >= 0 && nco) v[u] = cmul(v[u], nco_phasor_at<T>(off, ns.idx, ns.numer_abs, ns.denom, ns.sign, (T)ns.start_phase));
+            st_cx(&dst[j], v[u]);
+        }
+    }
 }
 template <typename T>
 cudaError_t launch_hist2_update(const void* in, long long in_stride, long long len, const void* hist2_in, void* hist2_out,
                                 long long n, const NcoStream* nco, int n_streams, cudaStream_t st, long long j_lo, long long j_hi) {
     if (j_hi < 0 || j_hi > 2 * n) j_hi = 2 * n;
     if (j_lo >= j_hi) return cudaSuccess;
-    dim3 grid((unsigned)((j_hi - j_lo + 255) / 256), (unsigned)n_streams);
+    dim3 grid((unsigned)((j_hi - j_lo + 1023) / 1024), (unsigned)n_streams);
     k_hist2_update<T><<<grid, 256, 0, st>>>(reinterpret_cast<const cx<T>*>(in), in_stride, len,
                                             reinterpret_cast<const cx<T>*>(hist2_in), reinterpret_cast<cx<T>*>(hist2_out), n, nco, j_lo, j_hi);
     return cudaGetLastError();
