@@ -204,18 +204,39 @@ __global__ void __launch_bounds__(256) k_upsample(const cx<T>* __restrict__ in, 
     const cx<T>* src = in + (long long)s * in_stride;
     cx<T> acc = (o < L) ? ld_cx(&acc_in[(long long)s * L + o]) : cx<T>((T)0, (T)0);
     // inputs p (global index) with ceil(p*Q/P) <= q  <=>  p <= floor(q*P/Q)
-    long long p_hi = (q * P) / Q;
-    long long p_lo = (q - L < 0) ? rate.j0 : ((q - L) * P) / Q + 1;
+    long long p_hi, p_lo;
+    if (P == 1 && q < (1LL << 31) && Q < (1LL << 31)) {  // 32-bit divisions are several times cheaper
+        const uint32_t q32 = (uint32_t)q, Q32 = (uint32_t)Q;
+        p_hi = q32 / Q32;
+        p_lo = (q - L < 0) ? rate.j0 : (long long)((q32 - (uint32_t)L) / Q32) + 1;
+    } else {
+        p_hi = (q * P) / Q;
+        p_lo = (q - L < 0) ? rate.j0 : ((q - L) * P) / Q + 1;
+    }
     if (p_lo < rate.j0) p_lo = rate.j0;
     if (p_hi > rate.j0 + len - 1) p_hi = rate.j0 + len - 1;
-    for (long long p = p_lo; p <= p_hi; ++p) {
-        const long long qp = (p * Q + P - 1) / P;
-        const int t = (int)(q - qp);
-        if (t >= 0 && t < L) {
-            const cx<T> x = ld_cx(&src[p - rate.j0]);
-            const T h = ir[t];
-            acc.x = fma(x.x, h, acc.x);
-            acc.y = fma(x.y, h, acc.y);
+    if (P == 1) {
+        // integer interpolation factor (q_p = p*Q): the tap index walks in steps of Q, no division per tap.  Same
+        // order of accumulation (p ascending) as the general loop below.
+        long long t = q - p_lo * Q;  // tap of input p_lo, decreasing by Q per input
+        for (long long p = p_lo; p <= p_hi; ++p, t -= Q) {
+            if (t >= 0 && t < L) {
+                const cx<T> x = ld_cx(&src[p - rate.j0]);
+                const T h = ir[t];
+                acc.x = fma(x.x, h, acc.x);
+                acc.y = fma(x.y, h, acc.y);
+            }
+        }
+    } else {
+        for (long long p = p_lo; p <= p_hi; ++p) {
+            const long long qp = (p * Q + P - 1) / P;
+            const int t = (int)(q - qp);
+            if (t >= 0 && t < L) {
+                const cx<T> x = ld_cx(&src[p - rate.j0]);
+                const T h = ir[t];
+                acc.x = fma(x.x, h, acc.x);
+                acc.y = fma(x.y, h, acc.y);
+            }
         }
     }
     if (o < n_out) st_cx(&out[(long long)s * out_stride + o], acc);
