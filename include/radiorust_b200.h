@@ -10,7 +10,13 @@
  *
  * Conventions
  *  - plain C types, opaque handles, int status (0 = ok, < 0 = rr_status);
- *    rr_last_error() returns a thread-local message; nothing unwinds or aborts.
+ *    rr_last_error() returns a THREAD-LOCAL message: read it on the thread that
+ *    got the error code, before the next `.await` (Tokio tasks migrate between
+ *    worker threads); nothing unwinds or aborts.
+ *  - a push that is refused (RR_ERR_INVALID / UNSUPPORTED / CAPACITY) leaves the
+ *    chain untouched.  A push that fails behind that check (RR_ERR_CUDA / NOMEM
+ *    in mid-flight) resets the chain's streaming state: every block restarts as
+ *    after rr_chain_create, parameters kept.
  *  - samples are interleaved complex (re, im): RR_C32 = num::Complex<f32>
  *    (8 bytes), RR_C64 = num::Complex<f64> (16 bytes) -- #[repr(C)] layout.
  *  - a chain processes `n_streams` independent streams in lock step; stream s
@@ -30,10 +36,11 @@ extern "C" {
 #endif
 
 #define RR_VERSION_MAJOR 0
-#define RR_VERSION_MINOR 3
+#define RR_VERSION_MINOR 4
 
 typedef struct rr_ctx rr_ctx;
 typedef struct rr_chain rr_chain;
+typedef struct rr_pool rr_pool;
 
 typedef enum rr_status {
     RR_OK = 0,
@@ -125,17 +132,34 @@ int rr_ctx_create(int device, rr_ctx** out);
 int rr_ctx_destroy(rr_ctx* ctx);
 int rr_ctx_device(const rr_ctx* ctx);
 
-/* ---- pinned chunk pool at the chain edges (replaces bufferpool.rs:187-222) */
+/* ---- pinned chunk pool at the chain edges (replaces bufferpool.rs:187-222) ---
+ * ChunkBufPool for page-locked memory.  rr_pool_get = ChunkBufPool::get_with_capacity (bufferpool.rs:210-222): the
+ * OLDEST recycled buffer is handed out again when it holds min_bytes (a smaller one is replaced: a Vec would grow in
+ * place, pinned memory cannot), otherwise a new one is allocated; *capacity = its size.  rr_pool_put is the recycler
+ * (Chunk::drop, bufferpool.rs:82-90): call it when the last owner of the chunk lets go.  get/put may come from any
+ * thread (the reference's recycler is an mpsc channel).  rr_pool_destroy frees idle buffers and those still on loan. */
+int rr_pool_create(rr_ctx* ctx, rr_pool** out);
+int rr_pool_destroy(rr_pool* pool);
+int rr_pool_get(rr_pool* pool, size_t min_bytes, void** out, size_t* capacity);
+int rr_pool_put(rr_pool* pool, void* p);
+int rr_pool_trim(rr_pool* pool); /* free the idle buffers */
+int rr_pool_stats(rr_pool* pool, uint64_t* allocated, uint64_t* reused, uint64_t* idle_buffers, uint64_t* live_buffers);
+/* one-off pinned allocations and in-place pinning of a recycled Vec (bufferpool.rs:202-222 reuses its Vecs, so a
+ * registration amortises) */
 int rr_pinned_alloc(rr_ctx* ctx, size_t bytes, void** out);
 int rr_pinned_free(rr_ctx* ctx, void* p);
-int rr_host_register(rr_ctx* ctx, void* p, size_t bytes); /* pin a recycled Vec in place */
+int rr_host_register(rr_ctx* ctx, void* p, size_t bytes);
 int rr_host_unregister(rr_ctx* ctx, void* p);
 int rr_device_alloc(rr_ctx* ctx, size_t bytes, void** out);
 int rr_device_free(rr_ctx* ctx, void* p);
+/* synchronous copies; both first wait for ALL work queued on the device (chains run on their own non-blocking
+ * streams), so they are safe right behind rr_chain_push_device without an rr_chain_sync */
 int rr_memcpy_h2d(rr_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
 int rr_memcpy_d2h(rr_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
 
-/* ---- metering (src/metering.rs) ------------------------------------------ */
+/* ---- metering (src/metering.rs) ------------------------------------------
+ * Synchronous; each call first waits for all work queued on the device, so the output of rr_chain_push_device can
+ * be metered directly (no rr_chain_sync needed in between).  n_streams <= 65535. */
 /* mean square norm of every chunk of DEVICE samples: host_out[s*n_chunks + c] for chunk c of stream s
  * (stream s at dev_in + s*in_stride samples); accumulated in f64 like the reference. */
 int rr_metering_level(rr_ctx* ctx, int32_t dtype, const void* dev_in, size_t in_stride, size_t chunk_len, size_t n_chunks,

@@ -1039,6 +1039,27 @@ def synth_noise(seed: int, n: int, flt: str = "f32") -> np.ndarray:
     return x
 
 
+def synth_fm_station(seed: int, n: int, sample_rate: float, deviation: float = 75000.0, audio_bw: float = 15000.0,
+                     noise_db: float = -30.0, flt: str = "f32") -> np.ndarray:
+    """Config 4's input: a unit carrier FM-modulated (``FmMod``, modulation.rs:44-51) with band-limited
+    noise ("audio": white noise low-passed to ``audio_bw``, peak-normalised to +-1 like a full-scale programme) plus
+    white Gaussian noise ``noise_db`` below the carrier.  The modulator's phase recurrence
+    ``phase = (phase + re*factor) % TAU`` is evaluated here in closed form in f64 (a cumulative sum) -- this is an
+    INPUT generator, the sample-by-sample ``FmMod`` restatement above stays the parity oracle of that block."""
+    rng = np.random.default_rng(seed)
+    spec = np.fft.rfft(rng.standard_normal(n))
+    f = np.fft.rfftfreq(n, 1.0 / sample_rate)
+    spec[f > audio_bw] = 0.0
+    spec[0] = 0.0
+    audio = np.fft.irfft(spec, n)
+    audio /= np.max(np.abs(audio))
+    factor = deviation / sample_rate * TAU  # modulation.rs:44
+    phase = np.fmod(np.cumsum(audio * factor), TAU)
+    sigma = 10.0 ** (noise_db / 20.0) / math.sqrt(2.0)
+    x = np.exp(1j * phase) + sigma * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    return x.astype(complex_dtype(flt))
+
+
 def lowpass(cutoff_hz: float):
     """The configs' ``|f| <= cutoff -> 1 else 0`` response."""
 

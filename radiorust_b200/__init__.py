@@ -16,6 +16,7 @@ from .chain import (  # noqa: F401
     FreqShifter,
     GainControl,
     Overlapper,
+    PinnedChunkBufPool,
     Rechunker,
     Upsampler,
     bandwidth,

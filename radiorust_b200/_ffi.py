@@ -71,6 +71,12 @@ SIGNATURES = {
     "rr_ctx_create": (_I, [_I, C.POINTER(_P)]),
     "rr_ctx_destroy": (_I, [_P]),
     "rr_ctx_device": (_I, [_P]),
+    "rr_pool_create": (_I, [_P, C.POINTER(_P)]),
+    "rr_pool_destroy": (_I, [_P]),
+    "rr_pool_get": (_I, [_P, _SZ, C.POINTER(_P), C.POINTER(_SZ)]),
+    "rr_pool_put": (_I, [_P, _P]),
+    "rr_pool_trim": (_I, [_P]),
+    "rr_pool_stats": (_I, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "rr_pinned_alloc": (_I, [_P, _SZ, C.POINTER(_P)]),
     "rr_pinned_free": (_I, [_P, _P]),
     "rr_host_register": (_I, [_P, _P, _SZ]),

@@ -59,6 +59,54 @@ class Context:
         return _Pinned(arr, self, p)
 
 
+class PinnedChunkBufPool:
+    """``rr_pool``: recycling pool of pinned host buffers, the chain-edge stand-in for ``ChunkBufPool``
+    (bufferpool.rs:187-222).  ``get`` returns a numpy array over a pinned buffer (recycled when one is idle);
+    ``put`` is the recycler (``Chunk::drop``, bufferpool.rs:82-90)."""
+
+    def __init__(self, ctx: Context):
+        self._lib = _ffi.load()
+        self.ctx = ctx
+        h = C.c_void_p()
+        check(self._lib.rr_pool_create(ctx._h, C.byref(h)))
+        self._h = h
+        self._loans = {}
+
+    def get(self, shape, dtype) -> np.ndarray:
+        dtype = np.dtype(dtype)
+        count = int(np.prod(shape))
+        p, cap = C.c_void_p(), C.c_size_t()
+        check(self._lib.rr_pool_get(self._h, count * dtype.itemsize, C.byref(p), C.byref(cap)))
+        buf = (C.c_char * max(cap.value, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+        self._loans[arr.ctypes.data] = p.value
+        return arr
+
+    def put(self, arr: np.ndarray):
+        ptr = self._loans.pop(arr.ctypes.data)
+        check(self._lib.rr_pool_put(self._h, C.c_void_p(ptr)))
+
+    def stats(self):
+        """(allocated, reused, idle buffers, buffers on loan)"""
+        v = [C.c_uint64() for _ in range(4)]
+        check(self._lib.rr_pool_stats(self._h, *[C.byref(x) for x in v]))
+        return tuple(int(x.value) for x in v)
+
+    def trim(self):
+        check(self._lib.rr_pool_trim(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.rr_pool_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class _Pinned(np.ndarray):
     """numpy view of a pinned allocation that frees it when collected."""
 

@@ -19,9 +19,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <memory>
+#include <mutex>
 #include <numeric>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/radiorust_b200.h"
@@ -63,7 +66,9 @@ struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
     // grow-only; contents are NOT preserved
-    int ensure(size_t need, bool zero = false) {
+    // zero = true clears a NEW allocation on `st` (the stream whose kernels use the buffer: a memset on the legacy
+    // stream would not be ordered against a non-blocking stream)
+    int ensure(size_t need, bool zero = false, cudaStream_t st = nullptr) {
         if (need <= bytes && p) {
             return RR_OK;
         }
@@ -79,8 +84,8 @@ struct DevBuf {
         }
         bytes = need;
         if (zero) {
-            e = cudaMemset(p, 0, need);
-            if (e != cudaSuccess) return fail_cuda(e, "cudaMemset");
+            e = cudaMemsetAsync(p, 0, need, st);
+            if (e != cudaSuccess) return fail_cuda(e, "cudaMemsetAsync");
         }
         return RR_OK;
     }
@@ -162,6 +167,21 @@ struct rr_ctx {
     int sm_count = 0;
 };
 
+
+// Recycling pool of pinned host buffers (the chain-edge stand-in for bufferpool.rs:187-222).  `idle` is the
+// recycler channel (FIFO, bufferpool.rs:82-90 sends, :203-207 / :213-219 receive); `live` are the buffers handed out.
+struct rr_pool {
+    rr_ctx* ctx = nullptr;
+    std::mutex mu;
+    struct Buf {
+        void* p;
+        size_t cap;
+    };
+    std::deque<Buf> idle;
+    std::unordered_map<void*, size_t> live;
+    uint64_t n_alloc = 0, n_reuse = 0;
+};
+
 namespace {
 
 struct Stage {
@@ -235,9 +255,15 @@ struct rr_chain {
     int S = 1;
     std::vector<Stage> st;
     cudaStream_t stream = nullptr;
-    DevBuf host_in, host_out;  // device staging of rr_chain_push
+    // rr_chain_push: two staging slots and two copy streams, so that the H2D copy of push k+1 runs while push k's
+    // kernels and D2H copy are still in flight (PCIe is full duplex; the chain edges are the only PCIe traffic)
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    DevBuf stage_in[2], stage_out[2];
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+    int slot = 0;
     std::string plan;
     uint64_t samples_lost = 0;  // SamplesLost events generated by Rechunker / Overlapper stages
+    bool push_mutated = false;  // the running push has passed its dry run and changed stage state
     bool allow_poly = true;  // rr_chain_set_fast_path
     bool allow_poly2 = true; // RR_DISABLE_POLY2=1: keep the generic polyphase kernel (k_poly) for f32 too
     size_t big_os_scratch_bytes = (size_t)2 << 30;  // RR_BIG_OS_SCRATCH_MB
@@ -268,6 +294,10 @@ struct rr_chain {
         ev_names[ev_used / 2 - 1] = name;
     }
 };
+
+namespace {
+void chain_restart(rr_chain* c);
+}
 
 #define RR_TIMED_LAUNCH(c, name, n_kernels, expr)                        \
     do {                                                                 \
@@ -435,6 +465,30 @@ int stage_event(const rr_stage_desc& d, StageHost& h, bool* interrupt) {
     return lost;
 }
 
+// chunk lengths the device Filter takes
+template <typename T> bool filter_len_supported(size_t n) {
+    if (n < 2 || n > ((size_t)1 << 24)) return false;
+    if ((n & (n - 1)) != 0) return false;
+    return rr::chain_os_supported<T>((int)n, 0, 0) || rr::big_os_supported<T>((int)n);
+}
+
+// what the device path cannot take is refused here, BEFORE a push changes any state (the dry run calls this)
+int stage_supported(const rr_chain* c, const rr_stage_desc& d, const Shape& in) {
+    if (in.n_chunks == 0 || in.chunk_len == 0) return RR_OK;
+    const bool f32 = c->dtype == RR_C32;
+    if (d.kind == RR_STAGE_FILTER) {
+        const size_t n = in.chunk_len;
+        if (!(f32 ? filter_len_supported<float>(n) : filter_len_supported<double>(n)))
+            return fail(RR_ERR_UNSUPPORTED, "Filter: chunk length not supported by the device path");
+    } else if (d.kind == RR_STAGE_FOURIER) {
+        const int n = (int)std::min<size_t>(in.chunk_len, (size_t)1 << 30);
+        const bool fft = f32 ? rr::fourier_fft_supported<float>(n) : rr::fourier_fft_supported<double>(n);
+        if (!fft && in.chunk_len > (size_t)rr::kFourierDirectMax)
+            return fail(RR_ERR_UNSUPPORTED, "Fourier: chunk lengths outside the FFT plans are limited to 4096 samples");
+    }
+    return RR_OK;
+}
+
 // output shape of a push without touching any state (capacity check, rr_chain_max_output)
 int dry_shape(const rr_chain* c, const Shape& in, Shape* out) {
     std::vector<StageHost> hs;
@@ -443,6 +497,7 @@ int dry_shape(const rr_chain* c, const Shape& in, Shape* out) {
     Shape sh = in;
     for (size_t i = 0; i < hs.size(); ++i) {
         StageAct a;
+        RR_TRY(stage_supported(c, c->st[i].d, sh));
         RR_TRY(advance_stage(c->st[i].d, hs[i], sh, &a));
         if (a.lost) {
             bool intr = true;
@@ -550,8 +605,8 @@ void nco_host_advance(Stage& s, long long len) {
 
 // ---- Filter design + upload (filters.rs:184-238) ----------------------------
 template <typename T> int filter_redesign(rr_chain* c, Stage& s, double sample_rate, size_t n) {
-    if (n < 2 || (n & (n - 1)) != 0)
-        return fail(RR_ERR_UNSUPPORTED, "Filter: the device path needs a power-of-two chunk length >= 2");
+    s.taps_valid = false;  // until this design is complete, nothing may be built from the previous taps
+    if (!filter_len_supported<T>(n)) return fail(RR_ERR_UNSUPPORTED, "Filter: chunk length not supported by the device path");
     const rr_stage_desc& d = s.d;
     if (!d.freq_resp) return fail(RR_ERR_INVALID, "Filter: freq_resp callback is null");
     rr_freq_resp_fn fn = d.freq_resp;
@@ -1271,6 +1326,7 @@ int run_push(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_chunks,
         if (sh.len() > out_stride && S > 1) return fail(RR_ERR_INVALID, "out_stride smaller than the produced samples");
     }
 
+    c->push_mutated = true;
     std::string plan;
     View cur;
     cur.p = dev_in;
@@ -1375,7 +1431,7 @@ int run_push(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_chunks,
             case RR_STAGE_FMMOD: {
                 Dest d;
                 RR_TRY(pick_dest<T>(c, s, last, dev_out, (long long)out_stride, (size_t)len, &d));
-                RR_TRY(s.fm_phase.ensure((size_t)S * sizeof(T), true));
+                RR_TRY(s.fm_phase.ensure((size_t)S * sizeof(T), true, st));
                 const double factor = s.d.deviation / cur.sh.rate * 6.283185307179586476925286766559;  // modulation.rs:44
                 RR_TIMED_LAUNCH(c, "k_fmmod", 1, rr::launch_fmmod<T>(cur.p, cur.stride, d.p, d.stride, len, S, s.fm_phase.p, factor, c->ctx->sm_count, st));
                 cur.p = d.p;
@@ -1451,8 +1507,8 @@ int run_push(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_chunks,
             case RR_STAGE_FMDEMOD: {
                 Dest d;
                 RR_TRY(pick_dest<T>(c, s, last, dev_out, (long long)out_stride, (size_t)len, &d));
-                RR_TRY(s.fm_prev.ensure((size_t)S * 2 * sizeof(T), true));
-                RR_TRY(s.fm_last.ensure((size_t)S * 2 * sizeof(T), true));
+                RR_TRY(s.fm_prev.ensure((size_t)S * 2 * sizeof(T), true, st));
+                RR_TRY(s.fm_last.ensure((size_t)S * 2 * sizeof(T), true, st));
                 const double factor = cur.sh.rate / s.d.deviation / 6.283185307179586476925286766559;  // modulation.rs:116
                 RR_TIMED_LAUNCH(c, "k_fmdemod", 2, rr::launch_fmdemod<T>(cur.p, cur.stride, d.p, d.stride, len, S, s.fm_prev.p, s.fm_last.p,
                                                    a.first_is_history ? 0 : 1, factor, st));
@@ -1571,6 +1627,27 @@ int run_push(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_chunks,
     return RR_OK;
 }
 
+// every block back to its state after construction; parameters (shifts, responses, deviations, gains) are kept
+void chain_restart(rr_chain* c) {
+    for (auto& s : c->st) {
+        s.h = StageHost{};
+        s.taps_valid = false;
+        s.poly_valid = s.poly_tried = s.poly2_valid = s.front_valid = false;
+        s.ztail_stale = false;
+        s.ucache_valid = false;
+        s.hist_fused_jlo = -1;
+        s.fwin_n = 0;
+        for (auto& h : s.nco_h) h = NcoHost{};
+        if (s.d.kind == RR_STAGE_FREQSHIFT) {
+            std::fill(s.shift_dirty.begin(), s.shift_dirty.end(), (uint8_t)1);
+            s.any_shift_dirty = true;
+        }
+        // FmMod's phase accumulator restarts at zero like a new block's
+        if (s.fm_phase.p) cudaMemsetAsync(s.fm_phase.p, 0, s.fm_phase.bytes, c->stream);
+        if (s.fm_last.p) cudaMemsetAsync(s.fm_last.p, 0, s.fm_last.bytes, c->stream);
+    }
+}
+
 }  // namespace
 
 // ===========================================================================
@@ -1599,8 +1676,8 @@ int rr_ctx_create(int device, rr_ctx** out) {
     RR_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
     RR_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10)
-        return fail(RR_ERR_UNSUPPORTED, "this library holds sm_100a code only; device compute capability is below 10.0");
+    if (prop.major != 10 || prop.minor != 0)  // sm_100a SASS is architecture specific and ships without PTX
+        return fail(RR_ERR_UNSUPPORTED, "this library holds sm_100a code only; the device's compute capability is not 10.0");
     rr_ctx* c = new rr_ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
@@ -1635,6 +1712,89 @@ int rr_host_unregister(rr_ctx* ctx, void* p) {
     RR_CUDA(cudaHostUnregister(p));
     return RR_OK;
 }
+// ---- pinned chunk pool (bufferpool.rs:187-222) -----------------------------------
+int rr_pool_create(rr_ctx* ctx, rr_pool** out) {
+    if (!ctx || !out) return fail(RR_ERR_INVALID, "rr_pool_create: null argument");
+    rr_pool* p = new rr_pool();
+    p->ctx = ctx;
+    *out = p;
+    return RR_OK;
+}
+int rr_pool_get(rr_pool* pool, size_t min_bytes, void** out, size_t* capacity) {
+    if (!pool || !out) return fail(RR_ERR_INVALID, "rr_pool_get: null argument");
+    *out = nullptr;
+    RR_CUDA(cudaSetDevice(pool->ctx->device));
+    const size_t need = min_bytes ? min_bytes : 1;
+    void* small = nullptr;
+    {
+        // ChunkBufPool::get_with_capacity takes the oldest recycled buffer (bufferpool.rs:213-216); a Vec that is too
+        // small grows when it is filled -- pinned memory cannot, so a too-small buffer is replaced here
+        std::lock_guard<std::mutex> lk(pool->mu);
+        if (!pool->idle.empty()) {
+            rr_pool::Buf b = pool->idle.front();
+            pool->idle.pop_front();
+            if (b.cap >= need) {
+                pool->live[b.p] = b.cap;
+                ++pool->n_reuse;
+                *out = b.p;
+                if (capacity) *capacity = b.cap;
+                return RR_OK;
+            }
+            small = b.p;
+        }
+    }
+    if (small) cudaFreeHost(small);
+    void* p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, need, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(e == cudaErrorMemoryAllocation ? RR_ERR_NOMEM : RR_ERR_CUDA, std::string("rr_pool_get: cudaHostAlloc: ") + cudaGetErrorString(e));
+    }
+    std::lock_guard<std::mutex> lk(pool->mu);
+    pool->live[p] = need;
+    ++pool->n_alloc;
+    *out = p;
+    if (capacity) *capacity = need;
+    return RR_OK;
+}
+int rr_pool_put(rr_pool* pool, void* p) {
+    if (!pool) return fail(RR_ERR_INVALID, "rr_pool_put: null pool");
+    if (!p) return RR_OK;
+    std::lock_guard<std::mutex> lk(pool->mu);
+    auto it = pool->live.find(p);
+    if (it == pool->live.end()) return fail(RR_ERR_INVALID, "rr_pool_put: the buffer is not on loan from this pool");
+    pool->idle.push_back(rr_pool::Buf{p, it->second});
+    pool->live.erase(it);
+    return RR_OK;
+}
+int rr_pool_stats(rr_pool* pool, uint64_t* allocated, uint64_t* reused, uint64_t* idle_buffers, uint64_t* live_buffers) {
+    if (!pool) return fail(RR_ERR_INVALID, "rr_pool_stats: null pool");
+    std::lock_guard<std::mutex> lk(pool->mu);
+    if (allocated) *allocated = pool->n_alloc;
+    if (reused) *reused = pool->n_reuse;
+    if (idle_buffers) *idle_buffers = pool->idle.size();
+    if (live_buffers) *live_buffers = pool->live.size();
+    return RR_OK;
+}
+int rr_pool_trim(rr_pool* pool) {
+    if (!pool) return fail(RR_ERR_INVALID, "rr_pool_trim: null pool");
+    std::deque<rr_pool::Buf> drop;
+    {
+        std::lock_guard<std::mutex> lk(pool->mu);
+        drop.swap(pool->idle);
+    }
+    for (auto& b : drop) cudaFreeHost(b.p);
+    return RR_OK;
+}
+int rr_pool_destroy(rr_pool* pool) {
+    if (!pool) return RR_OK;
+    rr_pool_trim(pool);
+    // buffers still on loan die with the pool, like Chunks that outlive their ChunkBufPool lose their recycler
+    // (bufferpool.rs:85-88: a closed channel makes the send fail and the Vec is dropped)
+    for (auto& kv : pool->live) cudaFreeHost(kv.first);
+    delete pool;
+    return RR_OK;
+}
 int rr_device_alloc(rr_ctx* ctx, size_t bytes, void** out) {
     if (!ctx || !out) return fail(RR_ERR_INVALID, "rr_device_alloc: null argument");
     RR_CUDA(cudaSetDevice(ctx->device));
@@ -1655,12 +1815,14 @@ int rr_device_free(rr_ctx* ctx, void* p) {
 int rr_memcpy_h2d(rr_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
     if (!ctx) return fail(RR_ERR_INVALID, "rr_memcpy_h2d: null context");
     RR_CUDA(cudaSetDevice(ctx->device));
+    RR_CUDA(cudaDeviceSynchronize());  // chains run on non-blocking streams: nothing may still be reading dst_dev
     RR_CUDA(cudaMemcpy(dst_dev, src_host, bytes, cudaMemcpyHostToDevice));
     return RR_OK;
 }
 int rr_memcpy_d2h(rr_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
     if (!ctx) return fail(RR_ERR_INVALID, "rr_memcpy_d2h: null context");
     RR_CUDA(cudaSetDevice(ctx->device));
+    RR_CUDA(cudaDeviceSynchronize());  // src_dev may still be written by a chain's (non-blocking) stream
     RR_CUDA(cudaMemcpy(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost));
     return RR_OK;
 }
@@ -1671,8 +1833,10 @@ int rr_metering_level(rr_ctx* ctx, int32_t dtype, const void* dev_in, size_t in_
     if (!ctx || !host_out || (!dev_in && n_chunks)) return fail(RR_ERR_INVALID, "rr_metering_level: null argument");
     if (dtype != RR_C32 && dtype != RR_C64) return fail(RR_ERR_INVALID, "rr_metering_level: bad dtype");
     if (n_streams < 1 || chunk_len == 0) return fail(RR_ERR_INVALID, "rr_metering_level: empty chunk (the reference divides by zero)");
+    if (n_streams > 65535) return fail(RR_ERR_INVALID, "rr_metering_level: at most 65535 streams per call");
     if (n_chunks == 0) return RR_OK;
     RR_CUDA(cudaSetDevice(ctx->device));
+    RR_CUDA(cudaDeviceSynchronize());  // dev_in may still be written by a chain's (non-blocking) stream
     DevBuf out;
     RR_TRY(out.ensure(sizeof(double) * n_chunks * (size_t)n_streams));
     cudaError_t e = dtype == RR_C32 ? rr::launch_level<float>(dev_in, (long long)in_stride, (long long)chunk_len, (long long)n_chunks, n_streams,
@@ -1695,6 +1859,7 @@ int rr_metering_bandwidth(rr_ctx* ctx, int32_t dtype, const void* dev_bins, size
     if (n_streams < 1 || n_streams > 65535 || chunk_len == 0) return fail(RR_ERR_INVALID, "rr_metering_bandwidth: empty chunk or bad stream count");
     if (n_chunks == 0) return RR_OK;
     RR_CUDA(cudaSetDevice(ctx->device));
+    RR_CUDA(cudaDeviceSynchronize());  // dev_bins may still be written by a chain's (non-blocking) stream
     DevBuf out;
     RR_TRY(out.ensure(sizeof(double) * n_chunks * (size_t)n_streams));
     cudaError_t e = dtype == RR_C32 ? rr::launch_bandwidth<float>(dev_bins, (long long)in_stride, (long long)chunk_len, (long long)n_chunks, n_streams,
@@ -1718,6 +1883,7 @@ int rr_metering_rescale_energy(rr_ctx* ctx, int32_t dtype, const void* dev_bins,
     if (n_streams < 1 || n_streams > 65535 || n_chunks > 65535) return fail(RR_ERR_INVALID, "rr_metering_rescale_energy: at most 65535 streams and chunks per call");
     if (n_chunks == 0 || resolution == 0) return RR_OK;
     RR_CUDA(cudaSetDevice(ctx->device));
+    RR_CUDA(cudaDeviceSynchronize());  // dev_bins may still be written by a chain's (non-blocking) stream
     const size_t fsz = dtype == RR_C32 ? sizeof(float) : sizeof(double);
     const size_t bytes = fsz * n_chunks * (size_t)n_streams * resolution;
     DevBuf out;
@@ -1855,6 +2021,7 @@ int rr_chain_create(rr_ctx* ctx, const rr_chain_desc* desc, rr_chain** out) {
     *out = nullptr;
     if (desc->dtype != RR_C32 && desc->dtype != RR_C64) return fail(RR_ERR_INVALID, "rr_chain_create: bad dtype");
     if (desc->n_streams < 1) return fail(RR_ERR_INVALID, "rr_chain_create: n_streams must be >= 1");
+    if (desc->n_streams > 65535) return fail(RR_ERR_INVALID, "rr_chain_create: at most 65535 streams per chain (streams map to a grid dimension)");
     if (desc->n_stages < 0 || (desc->n_stages > 0 && !desc->stages)) return fail(RR_ERR_INVALID, "rr_chain_create: bad stage list");
     for (int i = 0; i < desc->n_stages; ++i) {
         const rr_stage_desc& d = desc->stages[i];
@@ -1928,9 +2095,18 @@ int rr_chain_destroy(rr_chain* c) {
                           &s.gtab2, &s.twK2, &s.acoef, &s.gtab3, &s.ubuf[0], &s.ubuf[1], &s.fwin, &s.ftw, &s.fm_phase};
         for (DevBuf* b : bufs) b->release();
     }
-    c->host_in.release();
-    c->host_out.release();
+    if (c->d2h_stream) cudaStreamSynchronize(c->d2h_stream);
+    if (c->h2d_stream) cudaStreamSynchronize(c->h2d_stream);
+    for (int k = 0; k < 2; ++k) {
+        c->stage_in[k].release();
+        c->stage_out[k].release();
+        if (c->ev_h2d[k]) cudaEventDestroy(c->ev_h2d[k]);
+        if (c->ev_comp[k]) cudaEventDestroy(c->ev_comp[k]);
+        if (c->ev_d2h[k]) cudaEventDestroy(c->ev_d2h[k]);
+    }
     for (cudaEvent_t e : c->evs) cudaEventDestroy(e);
+    if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+    if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return RR_OK;
@@ -2047,6 +2223,7 @@ int rr_chain_push_device(rr_chain* c, double sample_rate, size_t chunk_len, size
     if (!dev_in) return fail(RR_ERR_INVALID, "rr_chain_push_device: dev_in is null");
     if (chunk_len > (size_t)1 << 30 || n_chunks > (size_t)1 << 30) return fail(RR_ERR_INVALID, "push too large");
     RR_CUDA(cudaSetDevice(c->ctx->device));
+    c->push_mutated = false;
     int r;
     if (c->dtype == RR_C32)
         r = run_push<float>(c, sample_rate, chunk_len, n_chunks, dev_in, in_stride, dev_out, out_capacity, out_stride, out_count,
@@ -2054,6 +2231,16 @@ int rr_chain_push_device(rr_chain* c, double sample_rate, size_t chunk_len, size
     else
         r = run_push<double>(c, sample_rate, chunk_len, n_chunks, dev_in, in_stride, dev_out, out_capacity, out_stride, out_count,
                              out_sample_rate);
+    if (r != RR_OK && c->push_mutated) {
+        // A failure behind the dry run (allocation, CUDA error) left some stages advanced and others not.  The stream
+        // cannot be continued consistently: every block restarts as after rr_chain_create (parameters kept; Filters
+        // redesign and prime again, resamplers restart their ring, the NCO re-derives its table at the next push).
+        const std::string msg = g_err;
+        chain_restart(c);
+        g_err = msg + " (the chain's streaming state was reset)";
+        if (out_count) *out_count = 0;
+    }
+    c->push_mutated = false;
     return r;
 }
 
@@ -2067,20 +2254,49 @@ int rr_chain_push(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_ch
     const size_t len = chunk_len * n_chunks;
     const size_t S = (size_t)c->S;
     if (S > 1 && in_stride < len) return fail(RR_ERR_INVALID, "in_stride smaller than the pushed samples");
-    const size_t max_out = rr_chain_max_output(c, sample_rate, chunk_len, n_chunks);
+    // everything that can be refused is refused before anything is enqueued or any state advances
+    Shape sh_in, sh_out;
+    sh_in.chunk_len = chunk_len;
+    sh_in.n_chunks = n_chunks;
+    sh_in.rate = sample_rate;
+    RR_TRY(dry_shape(c, sh_in, &sh_out));
+    const size_t max_out = sh_out.len();
     if (max_out > out_capacity) return fail(RR_ERR_CAPACITY, "output buffer too small for this push");
-    RR_TRY(c->host_in.ensure(S * len * c->esz));
-    RR_TRY(c->host_out.ensure(S * (max_out ? max_out : 1) * c->esz));
-    RR_CUDA(cudaMemcpy2DAsync(c->host_in.p, len * c->esz, host_in, in_stride * c->esz, len * c->esz, S, cudaMemcpyHostToDevice,
-                              c->stream));
-    size_t produced = 0;
-    RR_TRY(rr_chain_push_device(c, sample_rate, chunk_len, n_chunks, c->host_in.p, len, c->host_out.p, max_out, max_out ? max_out : 1,
-                                &produced, out_sample_rate));
-    if (produced > 0) {
-        if (!host_out) return fail(RR_ERR_INVALID, "rr_chain_push: host_out is null");
-        RR_CUDA(cudaMemcpy2DAsync(host_out, out_stride * c->esz, c->host_out.p, (max_out ? max_out : 1) * c->esz, produced * c->esz, S,
-                                  cudaMemcpyDeviceToHost, c->stream));
+    if (max_out > 0 && !host_out) return fail(RR_ERR_INVALID, "rr_chain_push: host_out is null");
+    if (max_out > out_stride && S > 1) return fail(RR_ERR_INVALID, "out_stride smaller than the produced samples");
+    if (!c->h2d_stream) {
+        RR_CUDA(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+        RR_CUDA(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            RR_CUDA(cudaEventCreateWithFlags(&c->ev_h2d[k], cudaEventDisableTiming));
+            RR_CUDA(cudaEventCreateWithFlags(&c->ev_comp[k], cudaEventDisableTiming));
+            RR_CUDA(cudaEventCreateWithFlags(&c->ev_d2h[k], cudaEventDisableTiming));
+        }
     }
+    const int b = c->slot;
+    const size_t ocap = max_out ? max_out : 1;
+    // (a staging buffer that has to grow is freed first: cudaFree waits for the work that still uses it)
+    RR_TRY(c->stage_in[b].ensure(S * len * c->esz));
+    RR_TRY(c->stage_out[b].ensure(S * ocap * c->esz));
+    // H2D of this push: behind the kernels of the push before last, which read the same slot
+    RR_CUDA(cudaStreamWaitEvent(c->h2d_stream, c->ev_comp[b], 0));
+    RR_CUDA(cudaMemcpy2DAsync(c->stage_in[b].p, len * c->esz, host_in, in_stride * c->esz, len * c->esz, S, cudaMemcpyHostToDevice,
+                              c->h2d_stream));
+    RR_CUDA(cudaEventRecord(c->ev_h2d[b], c->h2d_stream));
+    // kernels: behind that copy and behind the D2H copy that still reads this slot's output
+    RR_CUDA(cudaStreamWaitEvent(c->stream, c->ev_h2d[b], 0));
+    RR_CUDA(cudaStreamWaitEvent(c->stream, c->ev_d2h[b], 0));
+    size_t produced = 0;
+    RR_TRY(rr_chain_push_device(c, sample_rate, chunk_len, n_chunks, c->stage_in[b].p, len, c->stage_out[b].p, max_out, ocap, &produced,
+                                out_sample_rate));
+    RR_CUDA(cudaEventRecord(c->ev_comp[b], c->stream));
+    if (produced > 0) {
+        RR_CUDA(cudaStreamWaitEvent(c->d2h_stream, c->ev_comp[b], 0));
+        RR_CUDA(cudaMemcpy2DAsync(host_out, out_stride * c->esz, c->stage_out[b].p, ocap * c->esz, produced * c->esz, S,
+                                  cudaMemcpyDeviceToHost, c->d2h_stream));
+        RR_CUDA(cudaEventRecord(c->ev_d2h[b], c->d2h_stream));
+    }
+    c->slot ^= 1;
     if (out_count) *out_count = produced;
     return RR_OK;
 }
@@ -2089,6 +2305,8 @@ int rr_chain_sync(rr_chain* c) {
     if (!c) return fail(RR_ERR_INVALID, "null chain");
     RR_CUDA(cudaSetDevice(c->ctx->device));
     RR_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->d2h_stream) RR_CUDA(cudaStreamSynchronize(c->d2h_stream));
+    if (c->h2d_stream) RR_CUDA(cudaStreamSynchronize(c->h2d_stream));
     return RR_OK;
 }
 int rr_chain_set_fast_path(rr_chain* c, int enable) {

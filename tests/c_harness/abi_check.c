@@ -78,8 +78,25 @@ int main(int argc, char** argv) {
     float* in = NULL;
     float* out = NULL;
     const size_t cap = rr_chain_max_output(chain, 2400000.0, n, chunks);
-    if (rr_pinned_alloc(ctx, n * chunks * 8, (void**)&in) != RR_OK || rr_pinned_alloc(ctx, (cap + 1) * 8, (void**)&out) != RR_OK)
-        return fail("rr_pinned_alloc");
+    /* chain edges: chunks come from the pinned pool (ChunkBufPool::get_with_capacity, bufferpool.rs:210-222) and go
+     * back through the recycler when their last owner drops them (bufferpool.rs:82-90) */
+    rr_pool* pool = NULL;
+    if (rr_pool_create(ctx, &pool) != RR_OK) return fail("rr_pool_create");
+    {
+        void* a = NULL;
+        void* b = NULL;
+        size_t ca = 0, cb = 0;
+        uint64_t n_alloc = 0, n_reuse = 0, n_idle = 0, n_live = 0;
+        if (rr_pool_get(pool, 1000, &a, &ca) != RR_OK || ca < 1000) return fail("rr_pool_get");
+        if (rr_pool_put(pool, a) != RR_OK) return fail("rr_pool_put");
+        if (rr_pool_put(pool, a) == RR_OK) return fail("rr_pool_put accepted a buffer that is not on loan");
+        if (rr_pool_get(pool, 500, &b, &cb) != RR_OK || b != a || cb != ca) return fail("rr_pool_get did not recycle");
+        if (rr_pool_stats(pool, &n_alloc, &n_reuse, &n_idle, &n_live) != RR_OK || n_alloc != 1 || n_reuse != 1 || n_idle != 0 || n_live != 1)
+            return fail("rr_pool_stats");
+        if (rr_pool_put(pool, b) != RR_OK) return fail("rr_pool_put (2)");
+    }
+    if (rr_pool_get(pool, n * chunks * 8, (void**)&in, NULL) != RR_OK || rr_pool_get(pool, (cap + 1) * 8, (void**)&out, NULL) != RR_OK)
+        return fail("rr_pool_get (chunks)");
     /* a tone 1 kHz above the shift: after the chain it is a 1 kHz tone at 48 kS/s */
     for (size_t i = 0; i < n * chunks; ++i) {
         const double ph = 2.0 * 3.14159265358979323846 * (577000.0 + 1000.0) * (double)i / 2400000.0;
@@ -142,8 +159,8 @@ int main(int argc, char** argv) {
     }
     printf("abi_check ok: %zu output samples at %.0f S/s, plan %s, %llu kernel launches\n", total, rate, rr_chain_plan(chain),
            (unsigned long long)rr_kernel_launch_count());
-    rr_pinned_free(ctx, in);
-    rr_pinned_free(ctx, out);
+    if (rr_pool_put(pool, in) != RR_OK || rr_pool_put(pool, out) != RR_OK) return fail("rr_pool_put (chunks)");
+    rr_pool_destroy(pool);
     rr_chain_destroy(chain);
     rr_ctx_destroy(ctx);
     return 0;

@@ -31,7 +31,9 @@ def cases():
                              blocks=[("freqshift", 1.0, float((5 * 577) % 2_400_000 - 1_200_000)), ("filter_lowpass", 3000.0),
                                      ("downsample", 64, 48000.0, 6000.0, 3.0)]),
         # wide-band FM receive chain of config 4 at reduced rate/length
-        "c4_fm_f32": dict(flt="f32", sample_rate=1_000_000.0, chunk_len=4096, n_chunks=10, seed=20260000 + 400000,
+        # (input: FM-modulated band-limited noise + AWGN at -30 dB, SURVEY.md 8d -- a discriminator fed with
+        # filtered noise sits on its phase-wrap discontinuities and measures nothing but input rounding)
+        "c4_fm_f32": dict(flt="f32", sample_rate=1_000_000.0, chunk_len=4096, n_chunks=10, seed=20260000 + 400000, input="fm",
                           blocks=[("filter_lowpass", 100000.0), ("fmdemod", 75000.0), ("filter_deemph", 50e-6),
                                   ("downsample", 128, 50000.0, 40000.0, 3.0)]),
         # f64 precision case: filter + upsampler (config 5 at reduced size)
@@ -71,8 +73,15 @@ def oracle_blocks(case):
     return out
 
 
+def case_input(case):
+    total = case["chunk_len"] * case["n_chunks"]
+    if case.get("input") == "fm":
+        return orc.synth_fm_station(case["seed"], total, case["sample_rate"], 75000.0, 15000.0, -30.0, case["flt"])
+    return orc.synth_noise(case["seed"], total, case["flt"])
+
+
 def run_case(case):
-    x = orc.synth_noise(case["seed"], case["chunk_len"] * case["n_chunks"], case["flt"])
+    x = case_input(case)
     return orc.Chain(oracle_blocks(case)).run(case["sample_rate"], x, case["chunk_len"])
 
 

@@ -53,7 +53,7 @@ def test_against_golden(ctx, name, split):
     case = make_golden.cases()[name]
     want = np.load(os.path.join(HERE, "golden", name + ".npy"))
     n, k = case["chunk_len"], case["n_chunks"]
-    x = orc.synth_noise(case["seed"], n * k, case["flt"])
+    x = make_golden.case_input(case)
     ch = rr.Chain(ctx, rr_stages(case), case["flt"])
     parts = []
     pushes = [k] if split == "one_push" else [1] * k
@@ -65,8 +65,7 @@ def test_against_golden(ctx, name, split):
     ch.close()
     got = np.concatenate(parts)
     assert got.shape == want.shape
-    scale = 20.0 if "fm" in name else 1.0  # atan2 near +-pi amplifies input rounding (f32 chain of 4 blocks)
-    assert orc.rel_l2(got, want) <= TOL[case["flt"]] * scale
+    assert orc.rel_l2(got, want) <= TOL[case["flt"]]
 
 
 def test_empty_and_ragged_pushes(ctx):
