@@ -85,7 +85,28 @@ def run_case(case):
     return orc.Chain(oracle_blocks(case)).run(case["sample_rate"], x, case["chunk_len"])
 
 
+def emit_inputs(out_dir):
+    """Inputs, oracle outputs and the case list in the plain binary form rust/radiorust-b200/tests/emit_golden.rs
+    reads: with cargo, that test runs REAL radiorust on these inputs and compares (pins the oracle)."""
+    os.makedirs(out_dir, exist_ok=True)
+    lines = ["# name flt sample_rate chunk_len n_chunks blocks"]
+    for name, case in cases().items():
+        x = case_input(case)
+        x.tofile(os.path.join(out_dir, name + ".input.bin"))
+        run_case(case).tofile(os.path.join(out_dir, name + ".oracle.bin"))
+        blocks = ";".join(":".join(repr(float(v)) if isinstance(v, float) else str(v) for v in b) for b in case["blocks"])
+        lines.append(f"{name} {case['flt']} {case['sample_rate']!r} {case['chunk_len']} {case['n_chunks']} {blocks}")
+        if case.get("input") == "fm":
+            lines[-1] += ""
+    with open(os.path.join(out_dir, "cases.txt"), "w") as f:
+        f.write("\n".join(lines) + "\n")
+    print("wrote", out_dir)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "--emit-inputs":
+        emit_inputs(sys.argv[2])
+        sys.exit(0)
     for name, case in cases().items():
         y = run_case(case)
         np.save(os.path.join(HERE, name + ".npy"), y)
