@@ -225,6 +225,14 @@ struct Stage {
     int ubuf_cur = 0;
     bool ucache_valid = false;
     long long ucache_rows = 0;  // rows of the previous push
+    // where the last Lmax rows of u of the previous front-end push live (either path leaves them behind)
+    const void* ucache_ptr = nullptr;
+    long long ucache_stride = 0;
+    // k_fused (front end + low-rate part in one kernel): its kept rows (ping-pong) and its constant-memory slot
+    DevBuf ukeep[2];
+    int ukeep_cur = 0;
+    int fused_slot = -1;
+    bool fused_valid = false;
     bool front_valid = false;
     int front_rank = 0;
     double front_discarded = 0.0;
@@ -270,6 +278,8 @@ struct rr_chain {
     bool allow_sab = true;    // RR_DISABLE_SAB=1: short pushes keep one low-rate block (and inverse round) per stream
     bool allow_ucache = true; // RR_DISABLE_UCACHE=1: recompute the history rows of u from hist2 in every push
     bool allow_front = true; // RR_DISABLE_FRONT=1: k_poly2 on all P branches instead of the rank-reduced front end
+    bool allow_fused = true; // RR_DISABLE_FUSED=1: k_front + k_poly2 (u through HBM) instead of k_fused
+    int fused_min_streams = -1;  // streams from which k_fused is used (default: two per SM; RR_FUSED_MIN_STREAMS)
     // optional CUDA-event timing of the dominant kernel of a push (bench.py's roofline)
     bool timing = false;
     std::vector<cudaEvent_t> evs;  // pairs (start, stop), one per timed launch since rr_chain_set_timing
@@ -892,6 +902,29 @@ template <typename T> int regen_ztail(rr_chain* c, Stage& f, Stage& ds) {
     return RR_OK;
 }
 
+// k_fused reads its coefficient table from constant memory: a few slots per device, owned by Downsampler stages
+std::mutex g_slot_mu;
+const void* g_slot_owner[16][8] = {};
+int fused_slot_acquire(int device, const void* owner) {
+    if (device < 0 || device >= 16) return -1;
+    std::lock_guard<std::mutex> lk(g_slot_mu);
+    const int n = std::min(8, rr::fused_coef_slots());
+    for (int i = 0; i < n; ++i)
+        if (g_slot_owner[device][i] == owner) return i;
+    for (int i = 0; i < n; ++i)
+        if (!g_slot_owner[device][i]) {
+            g_slot_owner[device][i] = owner;
+            return i;
+        }
+    return -1;
+}
+void fused_slot_release(int device, const void* owner) {
+    if (device < 0 || device >= 16) return;
+    std::lock_guard<std::mutex> lk(g_slot_mu);
+    for (int i = 0; i < 8; ++i)
+        if (g_slot_owner[device][i] == owner) g_slot_owner[device][i] = nullptr;
+}
+
 // (re)build the polyphase tables for the pair (filter f, downsampler ds)
 template <typename T> int poly_prepare(rr_chain* c, Stage& f, Stage& ds) {
     if (ds.poly_tried) return RR_OK;
@@ -899,6 +932,7 @@ template <typename T> int poly_prepare(rr_chain* c, Stage& f, Stage& ds) {
     ds.poly_valid = false;
     ds.poly2_valid = false;
     ds.front_valid = false;
+    ds.fused_valid = false;
     if (!f.taps_valid) return RR_OK;
     const long long P = ds.h.P, Q = ds.h.Q;
     const long long n = (long long)f.h.f_n, L = ds.h.r_L;
@@ -994,6 +1028,16 @@ template <typename T> int poly_prepare(rr_chain* c, Stage& f, Stage& ds) {
                 ds.front_rank = rank;
                 ds.front_discarded = disc;
                 ds.front_valid = true;
+                // the fused kernel takes the same coefficients through constant memory
+                if (c->allow_fused && rr::fused_supported(RK, P, (int)Lmax)) {
+                    const int slot = fused_slot_acquire(c->ctx->device, &ds);
+                    if (slot >= 0) {
+                        RR_CUDA(rr::fused_upload_coef(slot, ac.data(), (int)P, c->stream));
+                        RR_CUDA(cudaStreamSynchronize(c->stream));  // `ac` is pageable and dies here
+                        ds.fused_slot = slot;
+                        ds.fused_valid = true;
+                    }
+                }
             }
         }
     }
@@ -1090,7 +1134,7 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
         // outputs m (1-based, counted with the reduced counters) firing inside this part
         const long long m_lo = m0 + 1;
         const long long m_hi = floordiv128(j0 + zlen, Qq, Pq);
-        bool used_poly2 = false, used_front = false;
+        bool used_poly2 = false, used_front = false, used_fused = false;
         if (m_hi >= m_lo) {
             rr::PolyArgs<T> a{};
             // filter output k aligns with push sample k; the part starts at push sample ca*n, and the
@@ -1115,7 +1159,71 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
             bool done = false;
             if constexpr (std::is_same<T, float>::value) {
                 const bool tma_ok = ((uintptr_t)a.in % 16 == 0) && (S == 1 || a.in_stride % 2 == 0) && a.len < (1LL << 31);
-                if (ds.poly2_valid && ds.front_valid && tma_ok) {
+                // ---- k_fused: front end + low-rate part in one persistent kernel (u stays in shared memory).  Steady
+                // state only: the whole push is polyphase, the previous push left its last Lmax rows of u behind, and
+                // there are enough streams to give every SM whole streams; everything else takes k_front + k_poly2.
+                if (ds.poly2_valid && ds.front_valid && ds.fused_valid && c->allow_fused && tma_ok && ca == 0 && was_ucache_valid &&
+                    c->allow_ucache && ds.ucache_ptr && Qq == 1 && m0 == 0 && a.J0 >= 0 && a.J0 < Pq && S >= c->fused_min_streams &&
+                    m_hi - m_lo + 1 >= std::max<long long>(ds.poly_Lmax, 2 * ds.poly2_V)) {
+                    constexpr int RK = 10;
+                    const long long n_out = m_hi - m_lo + 1;
+                    const long long Lh = ds.poly_Lmax;
+                    const size_t kbytes = (size_t)S * (size_t)Lh * RK * 2 * sizeof(float);
+                    DevBuf& kb = ds.ukeep[ds.ukeep_cur];
+                    RR_TRY(kb.ensure(kbytes));
+                    rr::FusedArgs fu{};
+                    fu.in = a.in;
+                    fu.in_stride = a.in_stride;
+                    fu.len = a.len;
+                    fu.hist2 = f.hist2[f.hist_cur].p;
+                    fu.n = a.n;
+                    fu.nco = a.nco;
+                    fu.P = (int)Pq;
+                    fu.coef_slot = ds.fused_slot;
+                    fu.J0 = a.J0;
+                    fu.n_out = (int)n_out;
+                    fu.Lmax = (int)Lh;
+                    fu.V = ds.poly2_V;
+                    fu.ukeep_in = ds.ucache_ptr;
+                    fu.ukeep_in_stride = ds.ucache_stride;
+                    fu.ukeep_out = kb.p;
+                    fu.ukeep_out_stride = Lh * RK;
+                    fu.gtab = ds.gtab3.p;
+                    fu.twK = ds.poly2_tw_own ? ds.twK2.p : ds.twK.p;
+                    fu.out = obase;
+                    fu.out_stride = ostride;
+                    const long long emit = (long long)da.out.len();
+                    if (direct && direct->user_out && emit >= (long long)da.pending_before && emit > 0) {
+                        fu.out = (char*)direct->user_out + da.pending_before * 2 * sizeof(T);
+                        fu.out_stride = direct->user_stride;
+                        fu.out2 = ds.obuf[ds.obuf_cur ^ 1].p;
+                        fu.out2_stride = ostride;
+                        fu.out_split = emit - (long long)da.pending_before;
+                        direct->done = true;
+                    }
+                    // the rows cover push offsets [-J0, m_hi*P - J0): the kernel also writes the Filter's next history
+                    // from len - 2n up to its last row (the rest is k_hist2_update's)
+                    const long long cover_hi = m_hi * Pq - a.J0;
+                    f.hist_fused_jlo = -1;
+                    f.hist_fused_jfirst = 0;
+                    const long long hfrom = a.len - 2 * a.n, hstart = std::max<long long>(hfrom, 0);
+                    if (cover_hi > hstart) {
+                        fu.hist_out = f.hist2[f.hist_cur ^ 1].p;
+                        fu.hist_from = hfrom;
+                        fu.hist_stride = 2 * a.n;
+                        f.hist_fused_jlo = cover_hi - hfrom;
+                        f.hist_fused_jfirst = hstart - hfrom;
+                    }
+                    RR_TIMED_LAUNCH(c, "k_fused", 1, rr::launch_fused(S, fu, c->ctx->sm_count, st));
+                    ds.ucache_valid = true;
+                    ds.ucache_rows = n_out + Lh;
+                    ds.ucache_ptr = kb.p;
+                    ds.ucache_stride = Lh * RK;
+                    ds.ukeep_cur ^= 1;
+                    done = true;
+                    used_fused = true;
+                }
+                if (!done && ds.poly2_valid && ds.front_valid && tma_ok) {
                     // u rows [m_lo-1-Lmax, m_hi-1] of every stream, then the low-rate part on u as a stream of
                     // RK branches whose first output (virtual index Lmax+1) is output m_lo
                     constexpr int RK = 10;
@@ -1150,9 +1258,8 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
                         const bool cached = was_ucache_valid && c->allow_ucache && ca == 0 && ds.ucache_rows >= Lh && n_out > 0;
                         rr::FrontArgs fa{};
                         if (cached) {  // k_front moves them over itself
-                            const int pv = ds.ubuf_cur ^ 1;
-                            fa.kept_src = (const char*)ds.ubuf[pv].p + (size_t)(ds.ucache_rows - Lh) * RK * 2 * sizeof(float);
-                            fa.kept_stride = ds.ubuf_stride[pv];
+                            fa.kept_src = ds.ucache_ptr;
+                            fa.kept_stride = ds.ucache_stride;
                             fa.kept_rows = (int)Lh;
                         }
                         fa.in = a.in;
@@ -1251,6 +1358,9 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
                         RR_TIMED_LAUNCH(c, "k_poly2", 1, rr::launch_poly2(G2, S2, b, st));
                         ds.ucache_valid = true;
                         ds.ucache_rows = n_rows;
+                        // the last Lmax rows of [history rows | new rows] of this push
+                        ds.ucache_ptr = (const char*)ub.p + (size_t)(n_rows - Lh) * RK * 2 * sizeof(float);
+                        ds.ucache_stride = u_stride;
                         ds.ubuf_cur ^= 1;
                         done = true;
                         used_front = true;
@@ -1301,7 +1411,7 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
         }
         ds.ztail_stale = true;
         if (!plan->empty() && plan->back() != '+' && plan->back() != '|' && ca > 0) *plan += "|";
-        *plan += used_front ? "front+poly2[filter+down]" : (used_poly2 ? "poly2[filter+down]" : "poly[filter+down]");
+        *plan += used_fused ? "fused[filter+down]" : (used_front ? "front+poly2[filter+down]" : (used_poly2 ? "poly2[filter+down]" : "poly[filter+down]"));
     }
     return RR_OK;
 }
@@ -2077,6 +2187,9 @@ int rr_chain_create(rr_ctx* ctx, const rr_chain_desc* desc, rr_chain** out) {
     if (const char* e = std::getenv("RR_DISABLE_POLY")) c->allow_poly = !(e[0] == '1');
     if (const char* e = std::getenv("RR_DISABLE_POLY2")) c->allow_poly2 = !(e[0] == '1');
     if (const char* e = std::getenv("RR_DISABLE_FRONT")) c->allow_front = !(e[0] == '1');
+    if (const char* e = std::getenv("RR_DISABLE_FUSED")) c->allow_fused = !(e[0] == '1');
+    c->fused_min_streams = 2 * ctx->sm_count;
+    if (const char* e = std::getenv("RR_FUSED_MIN_STREAMS")) c->fused_min_streams = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("RR_DISABLE_UCACHE")) c->allow_ucache = !(e[0] == '1');
     if (const char* e = std::getenv("RR_DISABLE_SAB")) c->allow_sab = !(e[0] == '1');
     if (const char* e = std::getenv("RR_BIG_OS_SCRATCH_MB")) c->big_os_scratch_bytes = (size_t)std::max(1, std::atoi(e)) << 20;
@@ -2092,8 +2205,9 @@ int rr_chain_destroy(rr_chain* c) {
     for (auto& s : c->st) {
         DevBuf* bufs[] = {&s.nco_d, &s.hperm, &s.tw, &s.hist2[0], &s.hist2[1], &s.ztmp, &s.gtab, &s.twK, &s.big_h, &s.big_twA, &s.big_twB, &s.big_scratch,
                           &s.ir, &s.tail[0], &s.tail[1], &s.obuf[0], &s.obuf[1], &s.fm_prev, &s.fm_last, &s.out,
-                          &s.gtab2, &s.twK2, &s.acoef, &s.gtab3, &s.ubuf[0], &s.ubuf[1], &s.fwin, &s.ftw, &s.fm_phase};
+                          &s.gtab2, &s.twK2, &s.acoef, &s.gtab3, &s.ubuf[0], &s.ubuf[1], &s.fwin, &s.ftw, &s.fm_phase, &s.ukeep[0], &s.ukeep[1]};
         for (DevBuf* b : bufs) b->release();
+        if (s.fused_slot >= 0) fused_slot_release(c->ctx->device, &s);
     }
     if (c->d2h_stream) cudaStreamSynchronize(c->d2h_stream);
     if (c->h2d_stream) cudaStreamSynchronize(c->h2d_stream);

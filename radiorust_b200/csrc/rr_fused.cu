@@ -1,0 +1,672 @@
+// k_fused: FreqShifter -> Filter -> Downsampler (integer decimation P, complex f32) in ONE persistent kernel.
+//
+// Same algebra as k_front + k_poly2 (rr_front.cu, rr_poly2.cu: the fused filter's P x (Lmax+1) matrix is
+// sum_c a_c b_c^T to below f32 rounding), but the intermediate u never travels through HBM:
+//
+//   front-end warps (F):  u_c[i] = rowph(i) * sum_p a_c[p] * colph(p) * x[iP + p]   -> rows of a shared-memory tile
+//   transform warps (T):  y = sum_c (b_c * u_c)  by 512-point overlap-save transforms on that tile -> HBM
+//
+// so a step reads every input sample once (8 B) and writes every output once (8 B / P): the algorithmic bytes of
+// SURVEY.md 8d.  One CTA per SM walks through whole streams; per stream the two roles meet at two tile stages
+// guarded by full/empty mbarriers, a block of V = 511 - Lmax new rows each.
+//
+// F warp: one lane per row of P samples (32 rows = one tile), so the RK x P coefficients are warp-uniform and come
+// from constant memory through the uniform datapath (LDCU -> FFMA2 with a uniform-register operand): no
+// shared-memory traffic for them (k_front's coefficient reads took 20 of its 28 wavefronts per step and made it
+// LSU bound).  Samples arrive by TMA, half a row per box (two boxes of `hp` columns per tile), into a per-warp
+// ring of slots with its own mbarriers; a warp runs ahead over stream boundaries.
+//
+// T warps: k_poly2's SINGLE path (two columns per warp end to end, one exchange, products summed through the
+// stage, spectra parked, inverse transforms in groups), fed from the stage instead of a TMA tile.  The Lmax rows a
+// block shares with its predecessor are carried in each warp's own 16-byte strip (a small keep buffer); the first
+// block of a stream takes them from the rows the previous push kept in HBM.
+//
+// Reference semantics: transform.rs:333-348 (NCO), filters.rs:240-253 (overlap-save Filter),
+// resampling.rs:103-121 (decimating FIR).  sm_100a only.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <mutex>
+
+#include "rr_kernels.h"
+#include "rr_poly.cuh"
+#include "rr_pk.cuh"
+
+namespace rr {
+
+namespace {
+
+constexpr int FK = 512;          // points per transform
+constexpr int FRK = 10;          // columns of u (rank of the factorisation, padded)
+constexpr int T_WARPS = FRK / 2;  // transform warps: two columns each
+constexpr int T_THREADS = 32 * T_WARPS;
+constexpr int F_ROWS = 32;       // rows per front-end tile: one lane per row
+constexpr int PITCH = FRK * 8;   // bytes per stage row
+constexpr int STAGE_ROWS = 528;  // 512 + spare rows of the exchange layout (element (t, k1) at row 33 t + k1)
+constexpr int STAGE_BYTES = STAGE_ROWS * PITCH;
+constexpr int TW_UNITS = 17;
+constexpr int TW_BYTES = 16 * TW_UNITS * 16;
+constexpr int YS_STRIDE = FK + 1;
+
+// coefficient tables in constant memory: kFusedSlots tables of up to kFusedSlotFloats floats ([P/2][2][FRK])
+constexpr int kFusedSlots = 6;
+constexpr int kFusedSlotFloats = 2560;  // P <= 256
+__constant__ float4 c_fcoef[kFusedSlots * kFusedSlotFloats / 4];
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mb_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mb_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "FWAIT_%=:\n"
+        "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra FDONE_%=;\n"
+        "bra FWAIT_%=;\n"
+        "FDONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ pc f_lds(uint32_t addr) {
+    pc r;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ void f_lds2(uint32_t addr, pc& a, pc& b) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(b.x), "=f"(b.y) : "r"(addr));
+}
+__device__ __forceinline__ void f_sts(uint32_t addr, pc a) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a.x), "f"(a.y) : "memory");
+}
+__device__ __forceinline__ void f_sts2(uint32_t addr, pc a, pc b) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y) : "memory");
+}
+__device__ __forceinline__ void f_ldg2(const float4* p, pc& a, pc& b) {
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(b.x), "=f"(b.y) : "l"(p));
+}
+
+// pass 1 of the 512-point transform of this thread's 32 inputs (rows t + 16*i1), as in rr_poly2.cu
+__device__ __forceinline__ void f_pass1_store(pc (&v)[32], uint32_t tw_row, uint32_t xch_wr) {
+    pdft_regs<32, +1>(v);
+    pc w[3][2];
+    f_lds2(tw_row, w[0][0], w[0][1]);
+    f_lds2(tw_row + 16, w[1][0], w[1][1]);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        if (m + 2 < 16) f_lds2(tw_row + (m + 2) * 16, w[(m + 2) % 3][0], w[(m + 2) % 3][1]);
+        f_sts(xch_wr + (2 * m) * PITCH, pcmul(v[2 * m], w[m % 3][0]));
+        f_sts(xch_wr + (2 * m + 1) * PITCH, pcmul(v[2 * m + 1], w[m % 3][1]));
+    }
+}
+
+struct FusedGeom {
+    int steps, S0, hp, slot_bytes, slot_stride;  // column pairs per row, pairs in half 0, box columns, ring slot size
+};
+__host__ __device__ inline FusedGeom fused_geom(int P) {
+    FusedGeom g;
+    g.steps = P / 2;
+    g.S0 = (g.steps + 1) / 2;
+    g.hp = 2 * g.S0 + ((g.S0 & 1) ? 0 : 2);  // an odd number of 16-byte units per slot row: conflict-free 16-byte row loads
+    if (g.hp > P) g.hp = P;
+    g.slot_bytes = F_ROWS * g.hp * 8;
+    g.slot_stride = (g.slot_bytes + 127) / 128 * 128;
+    return g;
+}
+
+}  // namespace
+
+// FW front-end warps, ring depth D per warp, NB parked spectra per inverse round
+template <int FW, int D, int NB, bool HAS_NCO>
+__global__ void __launch_bounds__(T_THREADS + 32 * FW, 1)
+k_fused(const __grid_constant__ CUtensorMap tmap, const FusedArgs a, const int n_streams) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int P = a.P;
+    const FusedGeom geo = fused_geom(P);
+    const int Lmax = a.Lmax, V = a.V, n_out = a.n_out;
+    const int B = (n_out + V - 1) / V;                       // blocks per stream
+    const int n_tiles = (B * V + F_ROWS - 1) / F_ROWS;       // tiles per stream (rows >= n_out are written as zeros)
+
+    // ---- shared-memory map ------------------------------------------------------------------------------
+    const int keep_bytes = ((Lmax * PITCH) + 127) / 128 * 128;
+    unsigned char* const p_stage = smem;
+    unsigned char* const p_tw = p_stage + 2 * STAGE_BYTES;
+    unsigned char* const p_keep = p_tw + TW_BYTES;
+    unsigned char* const p_ys = p_keep + keep_bytes;
+    unsigned char* const p_ring = p_ys + (((size_t)NB * YS_STRIDE * 8 + 127) / 128 * 128);
+    unsigned char* const p_colph = p_ring + (size_t)FW * D * geo.slot_stride;
+    unsigned char* const p_bar = p_colph + (((size_t)FW * P * 8 + 127) / 128 * 128);
+    const uint32_t bar_full = s_u32(p_bar), bar_empty = bar_full + 16, bar_ring = bar_full + 32;
+
+    // ---- one-time set-up: zero the stages (stale rows must be finite), twiddles, barriers ----------------------
+    for (int e = threadIdx.x; e < 2 * STAGE_BYTES / 16; e += blockDim.x) reinterpret_cast<float4*>(p_stage)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    {
+        const float2* __restrict__ twK = reinterpret_cast<const float2*>(a.twK);
+        for (int e = threadIdx.x; e < FK; e += blockDim.x) {
+            const int tr = e >> 5, k1 = e & 31;
+            const float2 w = twK[(tr * k1) & (FK - 1)];
+            const int off = (tr * TW_UNITS + (k1 >> 1)) * 16 + (k1 & 1) * 8;
+            *reinterpret_cast<float2*>(p_tw + off) = w;
+        }
+    }
+    if (threadIdx.x == 0) {
+        mb_init(bar_full, FW);
+        mb_init(bar_full + 8, FW);
+        mb_init(bar_empty, T_WARPS);
+        mb_init(bar_empty + 8, T_WARPS);
+        for (int q = 0; q < FW * D; ++q) mb_init(bar_ring + q * 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int n_my = (n_streams - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // streams of this CTA
+    if (n_my <= 0) return;
+
+    if (warp >= T_WARPS) {
+        // =====================================================================================================
+        // front-end warps
+        // =====================================================================================================
+        const int fw = warp - T_WARPS;
+        const uint32_t ring_s = s_u32(p_ring) + fw * (D * geo.slot_stride);
+        const uint32_t rbar = bar_ring + fw * (D * 8);
+        float2* const colph = reinterpret_cast<float2*>(p_colph) + fw * P;
+        const uint32_t col_s = s_u32(colph);
+        const int steps = geo.steps, S0 = geo.S0, hp = geo.hp;
+        const int half1_col0 = P - hp;  // half 1's box covers columns [P - hp, P): it never reaches past the row
+        const int len32 = (int)a.len;
+        const long long hist_len = 2 * a.n;
+        const int tiles_w = fw < n_tiles ? (n_tiles - fw + FW - 1) / FW : 0;  // tiles of this warp per stream
+        const int items_w = 2 * tiles_w;                                       // (tile, half) items per stream
+        const long long n_items = (long long)items_w * n_my;
+
+        // item -> (stream ordinal, tile, half); tiles with no valid row have no TMA copy ("zero tiles")
+        auto item_tile = [&](long long it, int* so, int* j, int* half) {
+            *so = (int)(it / items_w);
+            const int r = (int)(it - (long long)*so * items_w);
+            *j = fw + (r >> 1) * FW;
+            *half = r & 1;
+        };
+        auto tile_pos0 = [&](int j) -> int { return (int)((long long)j * F_ROWS * P - a.J0); };
+        long long q_issue = 0;  // TMA copies issued so far (ring position)
+        long long it_issue = 0;
+        auto issue_next = [&]() {
+            // advance to the next item that has a copy and start it (lane 0 issues; bookkeeping is warp-uniform)
+            while (it_issue < n_items) {
+                int so, j, half;
+                item_tile(it_issue, &so, &j, &half);
+                ++it_issue;
+                const int rows_ok = min(F_ROWS, n_out - j * F_ROWS);
+                if (rows_ok <= 0) continue;
+                const int s = (int)blockIdx.x + so * (int)gridDim.x;
+                const int pos0 = tile_pos0(j);
+                const int coff = half ? half1_col0 : 0;
+                // coordinates (c, i): address = c + i*P.  Rows that must not be read get a row coordinate outside
+                // [0, F_ROWS) and are zero-filled: the rows behind the last valid one (tail), and row 0 of a tile
+                // that starts before the pushed samples (head; patched by hand when the tile is consumed)
+                int sh = 0;
+                if (pos0 < 0) sh = -1;
+                else if (rows_ok < F_ROWS || pos0 + (F_ROWS - 1) * P + coff + hp > len32) sh = F_ROWS - rows_ok;
+                const int c = pos0 + coff - sh * P;
+                const int slot = (int)(q_issue % D);
+                if (lane == 0) {
+                    mb_expect_tx(rbar + slot * 8, (uint32_t)geo.slot_bytes);
+                    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                                     ring_s + slot * geo.slot_stride),
+                                 "l"(&tmap), "r"(rbar + slot * 8), "r"(c), "r"(sh), "r"(s)
+                                 : "memory");
+                }
+                ++q_issue;
+                return;
+            }
+        };
+#pragma unroll 1
+        for (int q = 0; q < D; ++q) issue_next();
+
+        long long q_cons = 0;       // copies consumed so far
+        long long gb_acq = -1;      // highest global block whose stage this warp has acquired
+        long long gb_arr = -1;      // highest global block this warp has arrived on (full)
+        // arrive on `full` for every block up to gb_done: a block is only arrived on once its stage has been acquired
+        // (i.e. the block two before is consumed), so that arrivals never pile up within one barrier phase
+        auto arrive_upto = [&](long long gb_done) {
+            for (long long g2 = gb_arr + 1; g2 <= gb_done; ++g2) {
+                while (gb_acq < g2) {
+                    ++gb_acq;
+                    mb_wait(bar_empty + (uint32_t)(gb_acq & 1) * 8, (uint32_t)(((gb_acq >> 1) & 1) ^ 1));
+                }
+                __syncwarp();
+                if (lane == 0) mb_arrive(bar_full + (uint32_t)(g2 & 1) * 8);
+            }
+            if (gb_done > gb_arr) gb_arr = gb_done;
+        };
+
+#pragma unroll 1
+        for (int so = 0; so < n_my; ++so) {
+            const int s = (int)blockIdx.x + so * (int)gridDim.x;
+            const long long gb0 = (long long)so * B;  // global index of this stream's block 0
+            // ---- per-stream NCO constants -------------------------------------------------------------
+            uint32_t denom = 1, numer_abs = 0, idx0 = 0;
+            int sign = 0;
+            float start = 0.f;
+            pc rot_tile(1.f, 0.f);
+            if (HAS_NCO) {
+                const NcoStream ns = a.nco[s];
+                denom = ns.denom;
+                numer_abs = ns.numer_abs;
+                sign = ns.sign;
+                idx0 = ns.idx;
+                start = (float)ns.start_phase;
+                const cx<float> r = nco_rotation<float>((long long)F_ROWS * P * FW, numer_abs, denom, sign);
+                rot_tile = pc(r.x, r.y);
+                __syncwarp();  // the previous stream's column phasors are no longer read
+                for (int p = lane; p < P; p += 32) {
+                    const cx<float> c = nco_rotation<float>(p, numer_abs, denom, sign);
+                    colph[p] = make_float2(c.x, c.y);
+                }
+                __syncwarp();
+            }
+            const float2* __restrict__ in = reinterpret_cast<const float2*>(a.in) + (long long)s * a.in_stride;
+            const float2* __restrict__ hist_end = reinterpret_cast<const float2*>(a.hist2) + ((long long)s + 1) * hist_len;
+            float2* __restrict__ hist_o = a.hist_out ? reinterpret_cast<float2*>(a.hist_out) + (long long)s * a.hist_stride : nullptr;
+            float4* __restrict__ keep_o = reinterpret_cast<float4*>(reinterpret_cast<float2*>(a.ukeep_out) + (long long)s * a.ukeep_out_stride);
+            const float4* cf_base = c_fcoef + a.coef_off4;
+
+            pc rowph(1.f, 0.f);
+#pragma unroll 1
+            for (int k = 0; k < tiles_w; ++k) {
+                const int j = fw + k * FW;
+                const int r0 = j * F_ROWS;           // first row of the tile
+                const int row = r0 + lane;           // this lane's row
+                const int rows_ok = min(F_ROWS, n_out - r0);
+                const int pos0 = tile_pos0(j);
+                pc acc[FRK];
+#pragma unroll
+                for (int c = 0; c < FRK; ++c) acc[c] = pc(0.f, 0.f);
+                if (rows_ok > 0) {
+                    if (HAS_NCO) {
+                        if ((k & 15) == 0) {
+                            long long kk = ((long long)idx0 + pos0 + (long long)lane * P) % (long long)denom;
+                            if (kk < 0) kk += denom;
+                            const cx<float> c = nco_phasor<float>(mulmod_u32(numer_abs, (uint32_t)kk, denom), denom, sign, start);
+                            rowph = pc(c.x, c.y);
+                        } else {
+                            rowph = pcmul(rowph, rot_tile);
+                        }
+                    }
+                    const long long prow = (long long)pos0 + (long long)lane * P;  // push offset of this lane's row
+                    const bool to_hist = hist_o != nullptr && (long long)pos0 + (long long)F_ROWS * P > a.hist_from;
+#pragma unroll 1
+                    for (int half = 0; half < 2; ++half) {
+                        const int slot = (int)(q_cons % D);
+                        const uint32_t slot_s = ring_s + slot * geo.slot_stride;
+                        mb_wait(rbar + slot * 8, (uint32_t)((q_cons / D) & 1));
+                        const int col0 = half ? half1_col0 : 0;
+                        if (pos0 < 0) {
+                            // head tile: row 0 arrived as zeros; fill it from the history (already mixed: un-mix) and the push
+                            float2* dst = reinterpret_cast<float2*>(smem + (slot_s - s_u32(smem)));
+                            const float r0x = __shfl_sync(0xffffffffu, rowph.x, 0), r0y = __shfl_sync(0xffffffffu, rowph.y, 0);
+                            for (int cc = lane; cc < hp; cc += 32) {
+                                const int p = col0 + cc;
+                                const long long pos = (long long)pos0 + p;
+                                float2 q = make_float2(0.f, 0.f);
+                                if (pos >= 0) {
+                                    if (pos < a.len) q = __ldg(in + pos);
+                                } else if (pos >= -hist_len) {
+                                    q = __ldg(hist_end + pos);
+                                    if (HAS_NCO) {
+                                        const float2 cph = colph[p];
+                                        const pc y = pcmulc(pc(q.x, q.y), pcmul(pc(r0x, r0y), pc(cph.x, cph.y)));
+                                        q = make_float2(y.x, y.y);
+                                    }
+                                }
+                                dst[cc] = q;
+                            }
+                            __syncwarp();
+                        }
+                        const int st_lo = half ? S0 : 0, st_hi = half ? steps : S0;
+                        // slot column of sample column 2*st: 2*st - col0
+                        const uint32_t row_s = slot_s + lane * (hp * 8) - col0 * 8;
+                        auto run = [&](auto write_hist) {
+#pragma unroll 4
+                            for (int st = st_lo; st < st_hi; ++st) {
+                                pc x0, x1;
+                                f_lds2(row_s + st * 16, x0, x1);
+                                if (HAS_NCO) {
+                                    pc c0, c1;
+                                    f_lds2(col_s + st * 16, c0, c1);
+                                    x0 = pcmul(x0, c0);
+                                    x1 = pcmul(x1, c1);
+                                }
+                                if (decltype(write_hist)::value) {
+                                    // the Filter's next history = the fully mixed samples (filters.rs:260 keeps the input chunk)
+                                    const pc y0 = HAS_NCO ? pcmul(x0, rowph) : x0, y1 = HAS_NCO ? pcmul(x1, rowph) : x1;
+                                    const long long jh = prow + 2 * st - a.hist_from;
+                                    if (row < n_out && jh >= -1) {
+                                        if (jh >= 0) hist_o[jh] = make_float2(y0.x, y0.y);
+                                        hist_o[jh + 1] = make_float2(y1.x, y1.y);
+                                    }
+                                }
+                                const float4* cf = cf_base + st * 5;
+                                const float4 a0 = cf[0], a1 = cf[1], a2 = cf[2], a3 = cf[3], a4 = cf[4];
+                                const float k0[FRK] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y};
+                                const float k1[FRK] = {a2.z, a2.w, a3.x, a3.y, a3.z, a3.w, a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+                                for (int c = 0; c < FRK; ++c) {
+                                    acc[c] = pfma_s(x0, k0[c], acc[c]);
+                                    acc[c] = pfma_s(x1, k1[c], acc[c]);
+                                }
+                            }
+                        };
+                        if (to_hist) run(std::true_type{});
+                        else run(std::false_type{});
+                        // every lane is done with the slot: refill it (generic-proxy reads ordered before the async copy)
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        ++q_cons;
+                        issue_next();
+                    }
+                }
+                // ---- the tile's rows go to the stage(s) of their block(s) -------------------------------------
+                const int r_last = min(r0 + F_ROWS, B * V) - 1;
+                const long long gb_hi = gb0 + r_last / V;
+                while (gb_acq < gb_hi) {
+                    ++gb_acq;
+                    // free when the transform warps have released the block two before (passes at once for the first two)
+                    mb_wait(bar_empty + (uint32_t)(gb_acq & 1) * 8, (uint32_t)(((gb_acq >> 1) & 1) ^ 1));
+                }
+                if (row < B * V) {
+                    const int b = row / V, i = Lmax + (row - b * V);
+                    const uint32_t dst = s_u32(p_stage) + (uint32_t)((gb0 + b) & 1) * STAGE_BYTES + i * PITCH;
+                    const bool live = row < n_out;
+#pragma unroll
+                    for (int c = 0; c < FRK; c += 2) {
+                        pc y0 = acc[c], y1 = acc[c + 1];
+                        if (HAS_NCO) {
+                            y0 = pcmul(y0, rowph);
+                            y1 = pcmul(y1, rowph);
+                        }
+                        if (!live) {
+                            y0 = pc(0.f, 0.f);
+                            y1 = pc(0.f, 0.f);
+                        }
+                        f_sts2(dst + c * 8, y0, y1);
+                        // the last Lmax rows of the push are the history rows of the next one
+                        if (live && row >= n_out - Lmax) keep_o[((long long)(row - (n_out - Lmax)) * FRK + c) / 2] = make_float4(y0.x, y0.y, y1.x, y1.y);
+                    }
+                }
+                __syncwarp();
+                // blocks this warp has no more rows for are complete on its part
+                const int j_next = j + FW;
+                const long long gb_done = (k + 1 < tiles_w) ? gb0 + min((j_next * F_ROWS) / V, B) - 1 : gb0 + B - 1;
+                arrive_upto(gb_done);
+            }
+            if (tiles_w == 0) arrive_upto(gb0 + B - 1);  // a warp without tiles (fewer tiles than warps) still owes its arrivals
+        }
+        return;
+    }
+
+    // =========================================================================================================
+    // transform warps
+    // =========================================================================================================
+    const int tid = threadIdx.x;  // 0 .. T_THREADS-1
+    const int t = lane >> 1, gg = lane & 1;
+    const int g = 2 * warp + gg;  // column of u
+    auto sync_t = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(T_THREADS) : "memory"); };
+    const uint32_t stage0 = s_u32(p_stage);
+    const uint32_t tw_row = s_u32(p_tw) + t * (TW_UNITS * 16);
+    const uint32_t tile_rd = t * PITCH + g * 8;
+    const uint32_t xch_wr = 33 * t * PITCH + g * 8;
+    const uint32_t xch_rd = t * PITCH + g * 8;
+    const uint32_t keep_s = s_u32(p_keep) + warp * 16;
+    float2* const ysave = reinterpret_cast<float2*>(p_ys);
+    const float4* __restrict__ gtab = reinterpret_cast<const float4*>(a.gtab);
+    const int hist_rows_per_lane = (Lmax + 31) / 32;  // <= 12 (Lmax <= 383)
+
+    const long long n_blocks_total = (long long)n_my * B;
+    int parked = 0;            // spectra waiting for their inverse transform
+    long long gb_first = 0;    // global block of parked job 0
+
+#pragma unroll 1
+    for (long long gb = 0; gb < n_blocks_total; ++gb) {
+        const int so = (int)(gb / B), b = (int)(gb - (long long)so * B);
+        const int s = (int)blockIdx.x + so * (int)gridDim.x;
+        const uint32_t stg = stage0 + (uint32_t)(gb & 1) * STAGE_BYTES;
+
+        // history rows of the stream's first block: kept by the previous push (loads in flight during the wait)
+        float4 hreg[12];
+        if (b == 0) {
+            const float4* __restrict__ kin = reinterpret_cast<const float4*>(reinterpret_cast<const float2*>(a.ukeep_in) + (long long)s * a.ukeep_in_stride);
+#pragma unroll
+            for (int q = 0; q < 12; ++q) {
+                const int r = lane + 32 * q;
+                if (q < hist_rows_per_lane && r < Lmax) hreg[q] = __ldg(kin + ((long long)r * FRK) / 2 + warp);
+            }
+        }
+        mb_wait(bar_full + (uint32_t)(gb & 1) * 8, (uint32_t)((gb >> 1) & 1));
+        // rows [0, Lmax) of this warp's strip: from the previous push (b == 0) or from the previous block (keep buffer);
+        // rows [V, V + Lmax) of the strip are the next block's
+#pragma unroll
+        for (int q = 0; q < 12; ++q) {
+            const int r = lane + 32 * q;
+            if (q < hist_rows_per_lane && r < Lmax) {
+                float4 h;
+                if (b == 0) h = hreg[q];
+                else asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(h.x), "=f"(h.y), "=f"(h.z), "=f"(h.w) : "r"(keep_s + r * PITCH));
+                float4 nx;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(nx.x), "=f"(nx.y), "=f"(nx.z), "=f"(nx.w) : "r"(stg + (V + r) * PITCH + warp * 16));
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + r * PITCH + warp * 16), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(keep_s + r * PITCH), "f"(nx.x), "f"(nx.y), "f"(nx.z), "f"(nx.w) : "memory");
+            }
+        }
+        __syncwarp();
+
+        // ---- forward transforms of this warp's two columns, products with FFT(b_c) ----------------------------------
+        pc acc[32];
+        {
+            pc v[32];
+            const uint32_t src = stg + tile_rd;
+#pragma unroll
+            for (int m = 0; m < 32; ++m) v[m] = f_lds(src + m * (16 * PITCH));
+            __syncwarp();  // the strip's rows are consumed by every lane before any lane overwrites them
+            f_pass1_store(v, tw_row, stg + xch_wr);
+        }
+        {
+            const float4* gp = gtab + tid;
+            pc h[16];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) f_ldg2(gp + jj * T_THREADS, h[2 * jj], h[2 * jj + 1]);
+            __syncwarp();
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {
+                pc x[16];
+#pragma unroll
+                for (int tr = 0; tr < 16; ++tr) x[tr] = f_lds(stg + xch_rd + (33 * tr + 16 * which) * PITCH);
+                pdft_regs<16, +1>(x);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) acc[which * 16 + k] = pcmul(x[k], h[k]);
+                if (which == 0) {
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) f_ldg2(gp + (8 + jj) * T_THREADS, h[2 * jj], h[2 * jj + 1]);
+                }
+            }
+        }
+        // ---- sum the ten partial spectra through the stage, park the block's spectrum ------------------------------
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f_sts(stg + xch_rd + (16 * j) * PITCH, acc[j]);
+        sync_t();
+        if (parked == 0) gb_first = gb;
+        {
+            float2* ys = ysave + parked * YS_STRIDE;
+            for (int o = tid; o < FK; o += T_THREADS) {
+                const uint32_t src = stg + o * PITCH;
+                pc sum(0.f, 0.f);
+#pragma unroll
+                for (int w = 0; w < T_WARPS; ++w) {
+                    pc u0, u1;
+                    f_lds2(src + w * 16, u0, u1);
+                    sum = sum + u0;
+                    sum = sum + u1;
+                }
+                const int j = o >> 4, tt = o & 15;
+                ys[tt + 16 * (j >> 4) + 32 * (j & 15)] = make_float2(sum.x, sum.y);
+            }
+        }
+        ++parked;
+
+        // ---- inverse transforms of the parked spectra (column g takes job g), through the stage this block still holds
+        if (parked == NB || gb + 1 == n_blocks_total) {
+            sync_t();  // all sums are parked, nobody reads the stage's rows any more
+#pragma unroll 1
+            for (int j0 = 0; j0 < parked; j0 += FRK) {
+                if (j0 + 2 * warp >= parked) continue;
+                const int job = j0 + g;
+                const bool active = job < parked;
+                pc v[32];
+                const float2* ys = ysave + (active ? job : 0) * YS_STRIDE;
+#pragma unroll
+                for (int i1 = 0; i1 < 32; ++i1) {
+                    const float2 q = ys[t + 16 * i1];
+                    v[i1] = active ? pc(q.x, -q.y) : pc(0.f, 0.f);  // conj in, conj out = inverse transform
+                }
+                f_pass1_store(v, tw_row, stg + xch_wr);
+                __syncwarp();
+                const long long gj = gb_first + (active ? job : 0);
+                const int so_j = (int)(gj / B), b_j = (int)(gj - (long long)so_j * B);
+                const int s_j = (int)blockIdx.x + so_j * (int)gridDim.x;
+                float2* __restrict__ out = reinterpret_cast<float2*>(a.out) + (long long)s_j * a.out_stride;
+                float2* __restrict__ out2 = a.out2 ? reinterpret_cast<float2*>(a.out2) + (long long)s_j * a.out2_stride : nullptr;
+#pragma unroll
+                for (int which = 0; which < 2; ++which) {
+                    pc x[16];
+#pragma unroll
+                    for (int tr = 0; tr < 16; ++tr) x[tr] = f_lds(stg + xch_rd + (33 * tr + 16 * which) * PITCH);
+                    pdft_regs<16, +1>(x);
+                    if (active) {
+#pragma unroll
+                        for (int k2 = 0; k2 < 16; ++k2) {
+                            const int i = t + 16 * which + 32 * k2;
+                            if (i >= Lmax && i < Lmax + V) {
+                                const long long o = (long long)b_j * V + (i - Lmax);  // output index within the push
+                                if (o < n_out) {
+                                    float2* dst = (out2 != nullptr && o >= a.out_split) ? out2 + (o - a.out_split) : out + o;
+                                    *dst = make_float2(x[k2].x, -x[k2].y);
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            parked = 0;
+            sync_t();  // the parked spectra may be overwritten
+        }
+        // ---- hand the stage back to the front-end warps ---------------------------------------------------------------
+        __syncwarp();
+        if (lane == 0) mb_arrive(bar_empty + (uint32_t)(gb & 1) * 8);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+namespace {
+
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                              const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn fused_encode_fn() {
+    static EncodeFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeFn>(p);
+    });
+    return fn;
+}
+
+template <int FW, int D, int NB> size_t fused_smem(int P, int Lmax) {
+    const FusedGeom geo = fused_geom(P);
+    size_t b = 2 * (size_t)STAGE_BYTES + TW_BYTES;
+    b += ((size_t)Lmax * PITCH + 127) / 128 * 128;
+    b += ((size_t)NB * YS_STRIDE * 8 + 127) / 128 * 128;
+    b += (size_t)FW * D * geo.slot_stride;
+    b += ((size_t)FW * P * 8 + 127) / 128 * 128;
+    b += 32 + (size_t)FW * D * 8 + 64;
+    return b;
+}
+
+template <int FW, int D, int NB>
+cudaError_t launch_cfg(int n_streams, const FusedArgs& a, const CUtensorMap& tm, int sm_count, cudaStream_t st) {
+    const size_t smem = fused_smem<FW, D, NB>(a.P, a.Lmax);
+    if (smem > (size_t)227 * 1024) return cudaErrorInvalidConfiguration;
+    const int grid = std::min(n_streams, sm_count);
+    void (*kern)(const CUtensorMap, const FusedArgs, const int) = a.nco ? k_fused<FW, D, NB, true> : k_fused<FW, D, NB, false>;
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, T_THREADS + 32 * FW, smem, st>>>(tm, a, n_streams);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+int fused_coef_slots() { return kFusedSlots; }
+
+bool fused_supported(int rank_pad, long long P, int Lmax) {
+    if (rank_pad != FRK || P < 4 || P > 254 || (P % 2) != 0 || fused_encode_fn() == nullptr) return false;
+    if (Lmax < 1 || FK - 1 - Lmax < 128 || Lmax > 383) return false;
+    if ((P / 2) * 2 * FRK > kFusedSlotFloats) return false;
+    return fused_smem<4, 3, 10>((int)P, Lmax) <= (size_t)227 * 1024;
+}
+
+cudaError_t fused_upload_coef(int slot, const float* acoef, int P, cudaStream_t st) {
+    if (slot < 0 || slot >= kFusedSlots) return cudaErrorInvalidValue;
+    const size_t n = (size_t)(P / 2) * 2 * FRK;
+    if (n > (size_t)kFusedSlotFloats) return cudaErrorInvalidValue;
+    return cudaMemcpyToSymbolAsync(c_fcoef, acoef, n * sizeof(float), (size_t)slot * kFusedSlotFloats * sizeof(float), cudaMemcpyHostToDevice, st);
+}
+
+cudaError_t launch_fused(int n_streams, const FusedArgs& a0, int sm_count, cudaStream_t st) {
+    EncodeFn enc = fused_encode_fn();
+    if (!enc) return cudaErrorNotSupported;
+    FusedArgs a = a0;
+    a.coef_off4 = a.coef_slot * (kFusedSlotFloats / 4);
+    const FusedGeom geo = fused_geom(a.P);
+    // the stream as overlapping rows of P samples: element (c0, i, s) = in[s*in_stride + c0 + i*P]; a box is half a
+    // row wide and F_ROWS rows tall
+    CUtensorMap tm;
+    const cuuint64_t dims[3] = {(cuuint64_t)a.len, (cuuint64_t)F_ROWS, (cuuint64_t)n_streams};
+    const cuuint64_t sstride = n_streams > 1 ? (cuuint64_t)a.in_stride * 8 : (((cuuint64_t)a.len * 8 + 15) / 16) * 16;
+    const cuuint64_t strides[2] = {(cuuint64_t)a.P * 8, sstride};
+    const cuuint32_t box[3] = {(cuuint32_t)geo.hp, (cuuint32_t)F_ROWS, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void*>(a.in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    // configuration: front-end warps, ring depth, parked spectra (RR_FUSED_CFG=fw,d,nb picks another instantiated one)
+    static int cfg = -1;
+    if (cfg < 0) {
+        cfg = 0;
+        if (const char* e = std::getenv("RR_FUSED_CFG")) cfg = std::atoi(e);
+    }
+    switch (cfg) {
+        case 1: return launch_cfg<4, 4, 5>(n_streams, a, tm, sm_count, st);
+        case 2: return launch_cfg<5, 3, 5>(n_streams, a, tm, sm_count, st);
+        case 3: return launch_cfg<6, 2, 8>(n_streams, a, tm, sm_count, st);
+        case 4: return launch_cfg<3, 4, 10>(n_streams, a, tm, sm_count, st);
+        default: return launch_cfg<4, 3, 10>(n_streams, a, tm, sm_count, st);
+    }
+}
+
+}  // namespace rr

@@ -228,6 +228,40 @@ struct FrontArgs {
 bool front_supported(int rank_pad, long long P);
 cudaError_t launch_front(int rank_pad, int n_streams, const FrontArgs& a, cudaStream_t st);
 
+// ---- k_fused (rr_fused.cu): front end + low-rate part in one persistent kernel; u stays in shared memory.
+// Rows are numbered from the push's first new row: row r, column p is push sample r*P + p - J0, output r = row r's.
+struct FusedArgs {
+    const void* in;        // [S][in_stride] complex<float>: the pushed samples (pre-NCO)
+    long long in_stride;
+    long long len;
+    const void* hist2;     // [S][2n]: the 2n post-NCO samples preceding `in` (row 0 may reach into them)
+    long long n;
+    const NcoStream* nco;  // [S] or nullptr
+    int P;
+    int coef_slot;         // constant-memory slot holding acoef ([P/2][2][10], as FrontArgs::acoef)
+    int coef_off4;         // set by the launcher
+    long long J0;          // 0 <= J0 < P
+    int n_out;             // new rows (= outputs) per stream, >= Lmax
+    int Lmax, V;           // reach of the low-rate filter, new rows per block (511 - Lmax)
+    const void* ukeep_in;  // [S][ukeep_in_stride] complex: the Lmax rows of u preceding row 0, rows of 10
+    long long ukeep_in_stride;
+    void* ukeep_out;       // [S][ukeep_out_stride]: the last Lmax rows of this push
+    long long ukeep_out_stride;
+    const void* gtab;      // FFT_512(b_c) in poly2_table_index(10, 0, c, k) order
+    const void* twK;       // [512] exp(-j*2*pi*e/512)
+    void* out;             // [S][out_stride]; output o to out[o], or to out2[o - out_split] when o >= out_split
+    long long out_stride;
+    void* out2;
+    long long out2_stride, out_split;
+    // optional: the mixed samples at push offsets >= hist_from also go to hist_out[s][offset - hist_from]
+    void* hist_out;
+    long long hist_from, hist_stride;
+};
+bool fused_supported(int rank_pad, long long P, int Lmax);
+int fused_coef_slots();
+cudaError_t fused_upload_coef(int slot, const float* acoef, int P, cudaStream_t st);
+cudaError_t launch_fused(int n_streams, const FusedArgs& a, int sm_count, cudaStream_t st);
+
 // new hist2 = last 2n post-NCO samples of [hist2_in | in]; only entries [j_lo, j_hi) (j_hi < 0: 2n) -- the
 // others were written by k_front
 template <typename T>

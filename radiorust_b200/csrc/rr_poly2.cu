@@ -53,6 +53,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "rr_kernels.h"
@@ -601,10 +602,15 @@ EncodeFn encode_fn() {
     return fn;
 }
 
-template <int G> cudaError_t launch_g(int n_streams, const PolyArgs<float>& a, const CUtensorMap& tm, cudaStream_t st) {
+template <int G> cudaError_t launch_g(int n_streams, const PolyArgs<float>& a0, const CUtensorMap& tm, cudaStream_t st) {
     using C = P2Cfg<G>;
+    PolyArgs<float> a = a0;
+    // EXPERIMENT (RR_P2_ONE_HALF_PER_SM=1): one half per CTA and one CTA per SM -- how fast is a lone half?
+    static const bool exp_one = std::getenv("RR_P2_ONE_HALF_PER_SM") != nullptr;
+    if (exp_one) a.halves = 1;
     const int halves = a.halves == 1 ? 1 : 2;
-    const size_t smem = C::half_bytes(a.nbpc) * halves;
+    size_t smem = C::half_bytes(a.nbpc) * halves;
+    if (exp_one) smem = std::max(smem, (size_t)120 * 1024);
     const int per_cta = a.nbpc * (a.ngrp > 0 ? a.ngrp : 1);
     // one CTA per SM; a half walks through several streams when there are more stream pairs than SMs
     static int sm_count = 0;
@@ -616,7 +622,7 @@ template <int G> cudaError_t launch_g(int n_streams, const PolyArgs<float>& a, c
     }
     const unsigned gx = (unsigned)((a.n_blocks + per_cta - 1) / per_cta);
     unsigned gy = (unsigned)((n_streams + halves - 1) / halves);
-    const int slots = sm_count * (halves == 1 ? 2 : 1);  // CTAs that can be resident at once
+    const int slots = sm_count * ((halves == 1 && !exp_one) ? 2 : 1);  // CTAs that can be resident at once
     if ((long long)gx * gy > slots) gy = (unsigned)std::max(1, std::min((int)gy, (slots + (int)gx - 1) / (int)gx));
     const dim3 grid(gx, gy);
     void (*kern)(const CUtensorMap, const PolyArgs<float>, const int);
