@@ -27,6 +27,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
 
@@ -110,6 +111,14 @@ __device__ __forceinline__ void f_pass1_store(pc (&v)[32], uint32_t tw_row, uint
     }
 }
 
+// RR_FUSED_PROF: per-phase cycle counters of front-end warp 0 / transform warp 0 of every CTA (development builds only)
+#ifdef RR_FUSED_PROF
+#define PROF(...) __VA_ARGS__
+__device__ long long g_fused_prof[256 * 16];
+#else
+#define PROF(...)
+#endif
+
 struct FusedGeom {
     int steps, S0, hp, slot_bytes, slot_stride;  // column pairs per row, pairs in half 0, box columns, ring slot size
 };
@@ -124,15 +133,43 @@ __host__ __device__ inline FusedGeom fused_geom(int P) {
     return g;
 }
 
+// steps [S_LO, S_HI) of a row, fully unrolled: the coefficient addresses are kernel parameter + immediate, so the
+// loads are LDCU (uniform datapath) and the compiler pipelines them and the shared-memory loads freely
+template <int S_LO, int S_HI, bool HAS_NCO>
+__device__ __forceinline__ void f_steps(pc (&acc)[FRK], const float4* __restrict__ xrow, const float4* __restrict__ crow, const float4* cf_base) {
+#pragma unroll
+    for (int st = S_LO; st < S_HI; ++st) {
+        const float4 xv = xrow[st];
+        pc x0(xv.x, xv.y), x1(xv.z, xv.w);
+        if (HAS_NCO) {
+            const float4 cv = crow[st];
+            x0 = pcmul(x0, pc(cv.x, cv.y));
+            x1 = pcmul(x1, pc(cv.z, cv.w));
+        }
+        const float4* cf = cf_base + st * 5;
+        const float4 a0 = cf[0], a1 = cf[1], a2 = cf[2], a3 = cf[3], a4 = cf[4];
+        const float k0[FRK] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y};
+        const float k1[FRK] = {a2.z, a2.w, a3.x, a3.y, a3.z, a3.w, a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+        for (int c = 0; c < FRK; ++c) {
+            acc[c] = pfma_s(x0, k0[c], acc[c]);
+            acc[c] = pfma_s(x1, k1[c], acc[c]);
+        }
+    }
+}
+
 }  // namespace
 
-// FW front-end warps, ring depth D per warp, NB parked spectra per inverse round
-template <int FW, int D, int NB, bool HAS_NCO>
+// FW front-end warps, ring depth D per warp, NB parked spectra per inverse round; PT: decimation factor known at
+// compile time (the front end's step loop is unrolled completely) or 0 (any even P)
+template <int FW, int D, int NB, bool HAS_NCO, int PT>
 __global__ void __launch_bounds__(T_THREADS + 32 * FW, 1)
 k_fused(const __grid_constant__ CUtensorMap tmap, const FusedArgs a, const int n_streams) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int P = a.P;
+    // the warp index through a warp broadcast: the compiler then knows that role dispatch and everything derived from
+    // it is warp-uniform (uniform registers, LDCU for the coefficient table)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const int P = PT > 0 ? PT : a.P;
     const FusedGeom geo = fused_geom(P);
     const int Lmax = a.Lmax, V = a.V, n_out = a.n_out;
     const int B = (n_out + V - 1) / V;                       // blocks per stream
@@ -161,6 +198,7 @@ k_fused(const __grid_constant__ CUtensorMap tmap, const FusedArgs a, const int n
         }
     }
     if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
         mb_init(bar_full, FW);
         mb_init(bar_full + 8, FW);
         mb_init(bar_empty, T_WARPS);
@@ -175,71 +213,68 @@ k_fused(const __grid_constant__ CUtensorMap tmap, const FusedArgs a, const int n
 
     if (warp >= T_WARPS) {
         // =====================================================================================================
-        // front-end warps
+        // front-end warps.  All bookkeeping is 32-bit and incremental (no divisions in the tile loop): the tile loop's
+        // overhead competes with 25 steps of ~65 cycles.
         // =====================================================================================================
         const int fw = warp - T_WARPS;
         const uint32_t ring_s = s_u32(p_ring) + fw * (D * geo.slot_stride);
         const uint32_t rbar = bar_ring + fw * (D * 8);
         float2* const colph = reinterpret_cast<float2*>(p_colph) + fw * P;
-        const uint32_t col_s = s_u32(colph);
         const int steps = geo.steps, S0 = geo.S0, hp = geo.hp;
         const int half1_col0 = P - hp;  // half 1's box covers columns [P - hp, P): it never reaches past the row
-        const int len32 = (int)a.len;
-        const long long hist_len = 2 * a.n;
+        const int J0 = (int)a.J0;
+        const int hist_len = (int)(2 * a.n);
+        const int hist_from = (int)a.hist_from;
         const int tiles_w = fw < n_tiles ? (n_tiles - fw + FW - 1) / FW : 0;  // tiles of this warp per stream
-        const int items_w = 2 * tiles_w;                                       // (tile, half) items per stream
-        const long long n_items = (long long)items_w * n_my;
+        const int BV = B * V;
+        const int tile_step = FW * F_ROWS;  // rows between consecutive tiles of this warp
 
-        // item -> (stream ordinal, tile, half); tiles with no valid row have no TMA copy ("zero tiles")
-        auto item_tile = [&](long long it, int* so, int* j, int* half) {
-            *so = (int)(it / items_w);
-            const int r = (int)(it - (long long)*so * items_w);
-            *j = fw + (r >> 1) * FW;
-            *half = r & 1;
-        };
-        auto tile_pos0 = [&](int j) -> int { return (int)((long long)j * F_ROWS * P - a.J0); };
-        long long q_issue = 0;  // TMA copies issued so far (ring position)
-        long long it_issue = 0;
+        // ---- issue side: (stream ordinal, tile, half) of the next copy, its ring slot ------------------------------
+        int i_so = 0, i_k = 0, i_half = 0, i_slot = 0;
         auto issue_next = [&]() {
-            // advance to the next item that has a copy and start it (lane 0 issues; bookkeeping is warp-uniform)
-            while (it_issue < n_items) {
-                int so, j, half;
-                item_tile(it_issue, &so, &j, &half);
-                ++it_issue;
+            // advance to the next item that has a copy (tiles with no valid row have none) and start it
+            while (i_so < n_my) {
+                if (i_k >= tiles_w) {  // (only when tiles_w == 0)
+                    i_so = n_my;
+                    break;
+                }
+                const int j = fw + i_k * FW, half = i_half, so = i_so;
+                i_half ^= 1;
+                if (i_half == 0 && ++i_k == tiles_w) {
+                    i_k = 0;
+                    ++i_so;
+                }
                 const int rows_ok = min(F_ROWS, n_out - j * F_ROWS);
                 if (rows_ok <= 0) continue;
-                const int s = (int)blockIdx.x + so * (int)gridDim.x;
-                const int pos0 = tile_pos0(j);
+                const int pos0 = j * (F_ROWS * P) - J0;
                 const int coff = half ? half1_col0 : 0;
                 // coordinates (c, i): address = c + i*P.  Rows that must not be read get a row coordinate outside
                 // [0, F_ROWS) and are zero-filled: the rows behind the last valid one (tail), and row 0 of a tile
                 // that starts before the pushed samples (head; patched by hand when the tile is consumed)
-                int sh = 0;
-                if (pos0 < 0) sh = -1;
-                else if (rows_ok < F_ROWS || pos0 + (F_ROWS - 1) * P + coff + hp > len32) sh = F_ROWS - rows_ok;
-                const int c = pos0 + coff - sh * P;
-                const int slot = (int)(q_issue % D);
+                const int sh = pos0 < 0 ? -1 : F_ROWS - rows_ok;
                 if (lane == 0) {
-                    mb_expect_tx(rbar + slot * 8, (uint32_t)geo.slot_bytes);
+                    mb_expect_tx(rbar + i_slot * 8, (uint32_t)geo.slot_bytes);
                     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-                                     ring_s + slot * geo.slot_stride),
-                                 "l"(&tmap), "r"(rbar + slot * 8), "r"(c), "r"(sh), "r"(s)
+                                     ring_s + i_slot * geo.slot_stride),
+                                 "l"(&tmap), "r"(rbar + i_slot * 8), "r"(pos0 + coff - sh * P), "r"(sh), "r"((int)blockIdx.x + so * (int)gridDim.x)
                                  : "memory");
                 }
-                ++q_issue;
+                i_slot = (i_slot + 1 == D) ? 0 : i_slot + 1;
                 return;
             }
         };
 #pragma unroll 1
         for (int q = 0; q < D; ++q) issue_next();
 
-        long long q_cons = 0;       // copies consumed so far
-        long long gb_acq = -1;      // highest global block whose stage this warp has acquired
-        long long gb_arr = -1;      // highest global block this warp has arrived on (full)
+        PROF(long long pr[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long pr_t0 = clock64();)
+        int c_slot = 0;
+        uint32_t c_phase = 0;  // parity of the consume slot's next completion (flips when the ring wraps)
+        int gb_acq = -1;       // highest global block whose stage this warp has acquired
+        int gb_arr = -1;       // highest global block this warp has arrived on (full)
         // arrive on `full` for every block up to gb_done: a block is only arrived on once its stage has been acquired
         // (i.e. the block two before is consumed), so that arrivals never pile up within one barrier phase
-        auto arrive_upto = [&](long long gb_done) {
-            for (long long g2 = gb_arr + 1; g2 <= gb_done; ++g2) {
+        auto arrive_upto = [&](int gb_done) {
+            for (int g2 = gb_arr + 1; g2 <= gb_done; ++g2) {
                 while (gb_acq < g2) {
                     ++gb_acq;
                     mb_wait(bar_empty + (uint32_t)(gb_acq & 1) * 8, (uint32_t)(((gb_acq >> 1) & 1) ^ 1));
@@ -253,7 +288,7 @@ k_fused(const __grid_constant__ CUtensorMap tmap, const FusedArgs a, const int n
 #pragma unroll 1
         for (int so = 0; so < n_my; ++so) {
             const int s = (int)blockIdx.x + so * (int)gridDim.x;
-            const long long gb0 = (long long)so * B;  // global index of this stream's block 0
+            const int gb0 = so * B;  // global index of this stream's block 0
             // ---- per-stream NCO constants -------------------------------------------------------------
             uint32_t denom = 1, numer_abs = 0, idx0 = 0;
             int sign = 0;
@@ -266,7 +301,7 @@ k_fused(const __grid_constant__ CUtensorMap tmap, const FusedArgs a, const int n
                 sign = ns.sign;
                 idx0 = ns.idx;
                 start = (float)ns.start_phase;
-                const cx<float> r = nco_rotation<float>((long long)F_ROWS * P * FW, numer_abs, denom, sign);
+                const cx<float> r = nco_rotation<float>((long long)tile_step * P, numer_abs, denom, sign);
                 rot_tile = pc(r.x, r.y);
                 __syncwarp();  // the previous stream's column phasors are no longer read
                 for (int p = lane; p < P; p += 32) {
@@ -280,19 +315,21 @@ k_fused(const __grid_constant__ CUtensorMap tmap, const FusedArgs a, const int n
             float2* __restrict__ hist_o = a.hist_out ? reinterpret_cast<float2*>(a.hist_out) + (long long)s * a.hist_stride : nullptr;
             float4* __restrict__ keep_o = reinterpret_cast<float4*>(reinterpret_cast<float2*>(a.ukeep_out) + (long long)s * a.ukeep_out_stride);
             const float4* cf_base = c_fcoef + a.coef_off4;
+            const float4* __restrict__ crow = reinterpret_cast<const float4*>(colph);
 
+            // block and offset within the block of the tile's first row
+            int blk = (fw * F_ROWS) / V, off = (fw * F_ROWS) - blk * V;
             pc rowph(1.f, 0.f);
 #pragma unroll 1
             for (int k = 0; k < tiles_w; ++k) {
-                const int j = fw + k * FW;
-                const int r0 = j * F_ROWS;           // first row of the tile
-                const int row = r0 + lane;           // this lane's row
-                const int rows_ok = min(F_ROWS, n_out - r0);
-                const int pos0 = tile_pos0(j);
+                const int r0 = (fw + k * FW) * F_ROWS;  // first row of the tile
+                const int row = r0 + lane;              // this lane's row
+                const int pos0 = r0 * P - J0;
                 pc acc[FRK];
 #pragma unroll
                 for (int c = 0; c < FRK; ++c) acc[c] = pc(0.f, 0.f);
-                if (rows_ok > 0) {
+                PROF(long long pc0 = clock64();)
+                if (r0 < n_out) {
                     if (HAS_NCO) {
                         if ((k & 15) == 0) {
                             long long kk = ((long long)idx0 + pos0 + (long long)lane * P) % (long long)denom;
@@ -303,13 +340,14 @@ k_fused(const __grid_constant__ CUtensorMap tmap, const FusedArgs a, const int n
                             rowph = pcmul(rowph, rot_tile);
                         }
                     }
-                    const long long prow = (long long)pos0 + (long long)lane * P;  // push offset of this lane's row
-                    const bool to_hist = hist_o != nullptr && (long long)pos0 + (long long)F_ROWS * P > a.hist_from;
+                    const int prow = pos0 + lane * P;  // push offset of this lane's row
+                    const bool to_hist = hist_o != nullptr && pos0 + F_ROWS * P > hist_from;
 #pragma unroll 1
                     for (int half = 0; half < 2; ++half) {
-                        const int slot = (int)(q_cons % D);
-                        const uint32_t slot_s = ring_s + slot * geo.slot_stride;
-                        mb_wait(rbar + slot * 8, (uint32_t)((q_cons / D) & 1));
+                        const uint32_t slot_s = ring_s + c_slot * geo.slot_stride;
+                        PROF(long long pw0 = clock64(); pr[0] += pw0 - pc0;)
+                        mb_wait(rbar + c_slot * 8, c_phase);
+                        PROF(long long pw1 = clock64(); pr[1] += pw1 - pw0;)
                         const int col0 = half ? half1_col0 : 0;
                         if (pos0 < 0) {
                             // head tile: row 0 arrived as zeros; fill it from the history (already mixed: un-mix) and the push
@@ -317,10 +355,10 @@ k_fused(const __grid_constant__ CUtensorMap tmap, const FusedArgs a, const int n
                             const float r0x = __shfl_sync(0xffffffffu, rowph.x, 0), r0y = __shfl_sync(0xffffffffu, rowph.y, 0);
                             for (int cc = lane; cc < hp; cc += 32) {
                                 const int p = col0 + cc;
-                                const long long pos = (long long)pos0 + p;
+                                const int pos = pos0 + p;
                                 float2 q = make_float2(0.f, 0.f);
                                 if (pos >= 0) {
-                                    if (pos < a.len) q = __ldg(in + pos);
+                                    if (pos < (int)a.len) q = __ldg(in + pos);
                                 } else if (pos >= -hist_len) {
                                     q = __ldg(hist_end + pos);
                                     if (HAS_NCO) {
@@ -333,28 +371,28 @@ k_fused(const __grid_constant__ CUtensorMap tmap, const FusedArgs a, const int n
                             }
                             __syncwarp();
                         }
-                        const int st_lo = half ? S0 : 0, st_hi = half ? steps : S0;
+                        // plain (non-volatile) shared-memory loads: the compiler pipelines them and the constant-bank loads
+                        // over the unrolled steps; the mbarrier wait above (memory clobber) keeps them behind the copy.
                         // slot column of sample column 2*st: 2*st - col0
-                        const uint32_t row_s = slot_s + lane * (hp * 8) - col0 * 8;
-                        auto run = [&](auto write_hist) {
-#pragma unroll 4
+                        const float4* __restrict__ xrow = reinterpret_cast<const float4*>(smem + (slot_s - s_u32(smem)) + lane * (hp * 8) - col0 * 8);
+                        if (to_hist) {
+                            // tiles inside the last 2n samples: the Filter's next history = the fully mixed samples
+                            // (filters.rs:260 keeps the input chunk); a few tiles per stream, run-time loop
+                            const int st_lo = half ? S0 : 0, st_hi = half ? steps : S0;
+#pragma unroll 2
                             for (int st = st_lo; st < st_hi; ++st) {
-                                pc x0, x1;
-                                f_lds2(row_s + st * 16, x0, x1);
+                                const float4 xv = xrow[st];
+                                pc x0(xv.x, xv.y), x1(xv.z, xv.w);
                                 if (HAS_NCO) {
-                                    pc c0, c1;
-                                    f_lds2(col_s + st * 16, c0, c1);
-                                    x0 = pcmul(x0, c0);
-                                    x1 = pcmul(x1, c1);
+                                    const float4 cv = crow[st];
+                                    x0 = pcmul(x0, pc(cv.x, cv.y));
+                                    x1 = pcmul(x1, pc(cv.z, cv.w));
                                 }
-                                if (decltype(write_hist)::value) {
-                                    // the Filter's next history = the fully mixed samples (filters.rs:260 keeps the input chunk)
-                                    const pc y0 = HAS_NCO ? pcmul(x0, rowph) : x0, y1 = HAS_NCO ? pcmul(x1, rowph) : x1;
-                                    const long long jh = prow + 2 * st - a.hist_from;
-                                    if (row < n_out && jh >= -1) {
-                                        if (jh >= 0) hist_o[jh] = make_float2(y0.x, y0.y);
-                                        hist_o[jh + 1] = make_float2(y1.x, y1.y);
-                                    }
+                                const pc y0 = HAS_NCO ? pcmul(x0, rowph) : x0, y1 = HAS_NCO ? pcmul(x1, rowph) : x1;
+                                const int jh = prow + 2 * st - hist_from;
+                                if (row < n_out && jh >= -1) {
+                                    if (jh >= 0) hist_o[jh] = make_float2(y0.x, y0.y);
+                                    hist_o[jh + 1] = make_float2(y1.x, y1.y);
                                 }
                                 const float4* cf = cf_base + st * 5;
                                 const float4 a0 = cf[0], a1 = cf[1], a2 = cf[2], a3 = cf[3], a4 = cf[4];
@@ -366,28 +404,66 @@ k_fused(const __grid_constant__ CUtensorMap tmap, const FusedArgs a, const int n
                                     acc[c] = pfma_s(x1, k1[c], acc[c]);
                                 }
                             }
-                        };
-                        if (to_hist) run(std::true_type{});
-                        else run(std::false_type{});
+                        } else if constexpr (PT > 0) {
+                            constexpr int STEPS_C = PT / 2, S0_C = (STEPS_C + 1) / 2;
+                            if (half == 0) f_steps<0, S0_C, HAS_NCO>(acc, xrow, crow, cf_base);
+                            else f_steps<S0_C, STEPS_C, HAS_NCO>(acc, xrow, crow, cf_base);
+                        } else {
+                            const int st_lo = half ? S0 : 0, st_hi = half ? steps : S0;
+#pragma unroll 4
+                            for (int st = st_lo; st < st_hi; ++st) {
+                                const float4 xv = xrow[st];
+                                pc x0(xv.x, xv.y), x1(xv.z, xv.w);
+                                if (HAS_NCO) {
+                                    const float4 cv = crow[st];
+                                    x0 = pcmul(x0, pc(cv.x, cv.y));
+                                    x1 = pcmul(x1, pc(cv.z, cv.w));
+                                }
+                                const float4* cf = cf_base + st * 5;
+                                const float4 a0 = cf[0], a1 = cf[1], a2 = cf[2], a3 = cf[3], a4 = cf[4];
+                                const float k0[FRK] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y};
+                                const float k1[FRK] = {a2.z, a2.w, a3.x, a3.y, a3.z, a3.w, a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+                                for (int c = 0; c < FRK; ++c) {
+                                    acc[c] = pfma_s(x0, k0[c], acc[c]);
+                                    acc[c] = pfma_s(x1, k1[c], acc[c]);
+                                }
+                            }
+                        }
                         // every lane is done with the slot: refill it (generic-proxy reads ordered before the async copy)
+                        PROF(long long ps1 = clock64(); pr[2] += ps1 - pw1;)
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         __syncwarp();
-                        ++q_cons;
+                        PROF(long long ps2 = clock64(); pr[3] += ps2 - ps1;)
+                        if (++c_slot == D) {
+                            c_slot = 0;
+                            c_phase ^= 1u;
+                        }
                         issue_next();
+                        PROF(pc0 = clock64(); pr[4] += pc0 - ps2;)
                     }
                 }
                 // ---- the tile's rows go to the stage(s) of their block(s) -------------------------------------
-                const int r_last = min(r0 + F_ROWS, B * V) - 1;
-                const long long gb_hi = gb0 + r_last / V;
-                while (gb_acq < gb_hi) {
-                    ++gb_acq;
-                    // free when the transform warps have released the block two before (passes at once for the first two)
-                    mb_wait(bar_empty + (uint32_t)(gb_acq & 1) * 8, (uint32_t)(((gb_acq >> 1) & 1) ^ 1));
+                {
+                    const int last_off = min(off + F_ROWS, BV - blk * V) - 1;  // offset (from block blk's first row) of the tile's last row below B*V
+                    const int gb_hi = gb0 + blk + (last_off >= V ? 1 : 0);
+                    PROF(long long pe0 = clock64(); pr[0] += pe0 - pc0;)
+                    while (gb_acq < gb_hi) {
+                        ++gb_acq;
+                        // free when the transform warps have released the block two before (passes at once for the first two)
+                        mb_wait(bar_empty + (uint32_t)(gb_acq & 1) * 8, (uint32_t)(((gb_acq >> 1) & 1) ^ 1));
+                    }
+                    PROF(pc0 = clock64(); pr[5] += pc0 - pe0;)
                 }
-                if (row < B * V) {
-                    const int b = row / V, i = Lmax + (row - b * V);
-                    const uint32_t dst = s_u32(p_stage) + (uint32_t)((gb0 + b) & 1) * STAGE_BYTES + i * PITCH;
+                if (row < BV) {
+                    int b = blk, o = off + lane;
+                    if (o >= V) {
+                        o -= V;
+                        ++b;
+                    }
+                    const uint32_t dst = s_u32(p_stage) + (uint32_t)((gb0 + b) & 1) * STAGE_BYTES + (Lmax + o) * PITCH;
                     const bool live = row < n_out;
+                    const bool keep = live && row >= n_out - Lmax;  // the last Lmax rows of the push are the next push's history rows
 #pragma unroll
                     for (int c = 0; c < FRK; c += 2) {
                         pc y0 = acc[c], y1 = acc[c + 1];
@@ -400,18 +476,25 @@ k_fused(const __grid_constant__ CUtensorMap tmap, const FusedArgs a, const int n
                             y1 = pc(0.f, 0.f);
                         }
                         f_sts2(dst + c * 8, y0, y1);
-                        // the last Lmax rows of the push are the history rows of the next one
-                        if (live && row >= n_out - Lmax) keep_o[((long long)(row - (n_out - Lmax)) * FRK + c) / 2] = make_float4(y0.x, y0.y, y1.x, y1.y);
+                        if (keep) keep_o[((row - (n_out - Lmax)) * FRK + c) / 2] = make_float4(y0.x, y0.y, y1.x, y1.y);
                     }
                 }
                 __syncwarp();
-                // blocks this warp has no more rows for are complete on its part
-                const int j_next = j + FW;
-                const long long gb_done = (k + 1 < tiles_w) ? gb0 + min((j_next * F_ROWS) / V, B) - 1 : gb0 + B - 1;
-                arrive_upto(gb_done);
+                // next tile of this warp; the blocks it no longer has rows for are complete on this warp's part
+                off += tile_step;
+                while (off >= V) {
+                    off -= V;
+                    ++blk;
+                }
+                arrive_upto((k + 1 < tiles_w) ? gb0 + min(blk, B) - 1 : gb0 + B - 1);
+                PROF(pr[6] += clock64() - pc0;)
             }
             if (tiles_w == 0) arrive_upto(gb0 + B - 1);  // a warp without tiles (fewer tiles than warps) still owes its arrivals
         }
+        PROF(if (fw == 0 && lane == 0) {
+            for (int q = 0; q < 7; ++q) g_fused_prof[blockIdx.x * 16 + q] = pr[q];
+            g_fused_prof[blockIdx.x * 16 + 7] = clock64() - pr_t0;
+        })
         return;
     }
 
@@ -432,13 +515,17 @@ k_fused(const __grid_constant__ CUtensorMap tmap, const FusedArgs a, const int n
     const float4* __restrict__ gtab = reinterpret_cast<const float4*>(a.gtab);
     const int hist_rows_per_lane = (Lmax + 31) / 32;  // <= 12 (Lmax <= 383)
 
-    const long long n_blocks_total = (long long)n_my * B;
-    int parked = 0;            // spectra waiting for their inverse transform
-    long long gb_first = 0;    // global block of parked job 0
+    const int n_blocks_total = n_my * B;
+    int parked = 0;      // spectra waiting for their inverse transform
+    int gb_first = 0;    // global block of parked job 0
+    int so = 0, b = -1;  // stream ordinal and block of the current global block
 
 #pragma unroll 1
-    for (long long gb = 0; gb < n_blocks_total; ++gb) {
-        const int so = (int)(gb / B), b = (int)(gb - (long long)so * B);
+    for (int gb = 0; gb < n_blocks_total; ++gb) {
+        if (++b == B) {
+            b = 0;
+            ++so;
+        }
         const int s = (int)blockIdx.x + so * (int)gridDim.x;
         const uint32_t stg = stage0 + (uint32_t)(gb & 1) * STAGE_BYTES;
 
@@ -541,8 +628,8 @@ k_fused(const __grid_constant__ CUtensorMap tmap, const FusedArgs a, const int n
                 }
                 f_pass1_store(v, tw_row, stg + xch_wr);
                 __syncwarp();
-                const long long gj = gb_first + (active ? job : 0);
-                const int so_j = (int)(gj / B), b_j = (int)(gj - (long long)so_j * B);
+                const int gj = gb_first + (active ? job : 0);
+                const int so_j = gj / B, b_j = gj - so_j * B;
                 const int s_j = (int)blockIdx.x + so_j * (int)gridDim.x;
                 float2* __restrict__ out = reinterpret_cast<float2*>(a.out) + (long long)s_j * a.out_stride;
                 float2* __restrict__ out2 = a.out2 ? reinterpret_cast<float2*>(a.out2) + (long long)s_j * a.out2_stride : nullptr;
@@ -612,10 +699,27 @@ cudaError_t launch_cfg(int n_streams, const FusedArgs& a, const CUtensorMap& tm,
     const size_t smem = fused_smem<FW, D, NB>(a.P, a.Lmax);
     if (smem > (size_t)227 * 1024) return cudaErrorInvalidConfiguration;
     const int grid = std::min(n_streams, sm_count);
-    void (*kern)(const CUtensorMap, const FusedArgs, const int) = a.nco ? k_fused<FW, D, NB, true> : k_fused<FW, D, NB, false>;
+    void (*kern)(const CUtensorMap, const FusedArgs, const int);
+    // decimation factors with an unrolled front end (2.4 MS/s -> 48 kS/s and other common SDR ratios); any other even P
+    // takes the run-time loop
+    switch (a.P) {
+        case 50: kern = a.nco ? k_fused<FW, D, NB, true, 50> : k_fused<FW, D, NB, false, 50>; break;
+        default: kern = a.nco ? k_fused<FW, D, NB, true, 0> : k_fused<FW, D, NB, false, 0>; break;
+    }
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, T_THREADS + 32 * FW, smem, st>>>(tm, a, n_streams);
+#ifdef RR_FUSED_PROF
+    static int calls = 0;
+    if (++calls == 12) {
+        cudaDeviceSynchronize();
+        long long h[256 * 16];
+        cudaMemcpyFromSymbol(h, g_fused_prof, sizeof h);
+        for (int c : {0, 100})
+            fprintf(stderr, "cta %d F0: tile-head %lld ring-wait %lld steps %lld fence+sync %lld issue %lld empty-wait %lld finalize %lld | total %lld\n", c, h[c * 16],
+                    h[c * 16 + 1], h[c * 16 + 2], h[c * 16 + 3], h[c * 16 + 4], h[c * 16 + 5], h[c * 16 + 6], h[c * 16 + 7]);
+    }
+#endif
     return cudaGetLastError();
 }
 
@@ -627,7 +731,7 @@ bool fused_supported(int rank_pad, long long P, int Lmax) {
     if (rank_pad != FRK || P < 4 || P > 254 || (P % 2) != 0 || fused_encode_fn() == nullptr) return false;
     if (Lmax < 1 || FK - 1 - Lmax < 128 || Lmax > 383) return false;
     if ((P / 2) * 2 * FRK > kFusedSlotFloats) return false;
-    return fused_smem<4, 3, 10>((int)P, Lmax) <= (size_t)227 * 1024;
+    return fused_smem<7, 2, 5>((int)P, Lmax) <= (size_t)227 * 1024;
 }
 
 cudaError_t fused_upload_coef(int slot, const float* acoef, int P, cudaStream_t st) {
@@ -654,18 +758,17 @@ cudaError_t launch_fused(int n_streams, const FusedArgs& a0, int sm_count, cudaS
     const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void*>(a.in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
-    // configuration: front-end warps, ring depth, parked spectra (RR_FUSED_CFG=fw,d,nb picks another instantiated one)
+    // configuration <front-end warps, ring depth, parked spectra>: seven front-end warps fill the register file next to the five
+    // transform warps (12 warps x 168 registers) and were the fastest measured (RR_FUSED_CFG=1|2 picks the others)
     static int cfg = -1;
     if (cfg < 0) {
         cfg = 0;
         if (const char* e = std::getenv("RR_FUSED_CFG")) cfg = std::atoi(e);
     }
     switch (cfg) {
-        case 1: return launch_cfg<4, 4, 5>(n_streams, a, tm, sm_count, st);
-        case 2: return launch_cfg<5, 3, 5>(n_streams, a, tm, sm_count, st);
-        case 3: return launch_cfg<6, 2, 8>(n_streams, a, tm, sm_count, st);
-        case 4: return launch_cfg<3, 4, 10>(n_streams, a, tm, sm_count, st);
-        default: return launch_cfg<4, 3, 10>(n_streams, a, tm, sm_count, st);
+        case 1: return launch_cfg<4, 3, 10>(n_streams, a, tm, sm_count, st);
+        case 2: return launch_cfg<6, 2, 8>(n_streams, a, tm, sm_count, st);
+        default: return launch_cfg<7, 2, 5>(n_streams, a, tm, sm_count, st);
     }
 }
 
