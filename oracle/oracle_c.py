@@ -22,17 +22,25 @@ def lib():
             fn = getattr(_lib, name)
             fn.restype = C.c_int
             fn.argtypes = [C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
-                           C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_double, C.c_double, C.c_int]
+                           C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_double, C.c_double, C.c_int,
+                           C.c_void_p]
+        for name in ("oracle_phase_table_f32", "oracle_phase_table_f64"):
+            fn = getattr(_lib, name)
+            fn.restype = None
+            fn.argtypes = [C.c_int64, C.c_int64, C.c_void_p]
     return _lib
 
 
 def chain(x: np.ndarray, flt: str, sample_rate: float, chunk_len: int, shifts=None, precision: float = 1.0,
-          freq_resp=None, window=None, down=None, n_threads: int = 1, timing: dict | None = None) -> list:
+          freq_resp=None, window=None, down=None, n_threads: int = 1, timing: dict | None = None,
+          prebuilt_phase_tables: bool = False) -> list:
     """Runs [FreqShifter ->] [Filter ->] [Downsampler] over the rows of ``x`` from a fresh start.
 
     ``shifts``: per-stream shift in hertz or None; ``freq_resp``: Filter closure or None;
     ``down``: (output_rate, bandwidth, quality) or None.  Returns one output array per stream
-    (Downsampler output framing is not applied: all produced samples).
+    (Downsampler output framing is not applied: all produced samples).  ``prebuilt_phase_tables``: FreqShifter's
+    phase tables (transform.rs:321-340, built once per retune by the reference) are built before the timed call
+    (``timing["table_seconds"]``) instead of inside it.
     """
     x = np.ascontiguousarray(np.atleast_2d(x), dtype=orc.complex_dtype(flt))
     S, total = x.shape
@@ -65,11 +73,22 @@ def chain(x: np.ndarray, flt: str, sample_rate: float, chunk_len: int, shifts=No
     fn = lib().oracle_chain_f32 if flt == "f32" else lib().oracle_chain_f64
     import time
 
+    tabs_p = None
+    if prebuilt_phase_tables and numer is not None:
+        tfn = lib().oracle_phase_table_f32 if flt == "f32" else lib().oracle_phase_table_f64
+        tt = time.perf_counter()
+        tabs = [np.empty(int(d), dtype=x.dtype) for d in denom]
+        for s in range(S):
+            tfn(int(numer[s]), int(denom[s]), tabs[s].ctypes.data)
+        tabs_p = (C.c_void_p * S)(*[t.ctypes.data for t in tabs])
+        if timing is not None:
+            timing["table_seconds"] = time.perf_counter() - tt
+
     t0 = time.perf_counter()
     rc = fn(S, chunk_len, n_chunks, xp, yp, n_out, 1 if shifts is not None else 0,
             numer.ctypes.data if numer is not None else None, denom.ctypes.data if denom is not None else None,
             1 if hext is not None else 0, hext.ctypes.data if hext is not None else None,
-            1 if down is not None else 0, ir.ctypes.data if ir is not None else None, L, in_rate, out_rate, n_threads)
+            1 if down is not None else 0, ir.ctypes.data if ir is not None else None, L, in_rate, out_rate, n_threads, tabs_p)
     if timing is not None:
         timing["seconds"] = time.perf_counter() - t0  # the C hot loops only (design excluded)
     if rc != 0:

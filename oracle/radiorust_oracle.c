@@ -11,9 +11,10 @@
  *   Downsampler  src/blocks/resampling.rs:103-133  (ring buffer + L-tap dot product)
  * The cold design paths (H(f), taps) are NOT here: callers pass the tables that
  * oracle/radiorust_oracle.py designed (filters.rs:184-238, resampling.rs:82-101).
- * rustfft (Cargo.toml:19, absent from /root/reference) is replaced by the plain
- * iterative radix-2 FFT below: both are unnormalised DFTs, so results agree to
- * rounding.  Parity status: validated against the numpy oracle in
+ * rustfft (Cargo.toml:19, absent from /root/reference) is replaced by the
+ * radix-4 Stockham (autosort) FFT below, compiled in AVX-512 / AVX2 / baseline
+ * clones that the loader picks at run time (rustfft picks AVX/SSE butterflies the
+ * same way): both are unnormalised DFTs, so results agree to rounding.  Parity status: validated against the numpy oracle in
  * tests/test_oracle_c.py; end-to-end outputs of these blocks are "parity
  * unpinned" upstream (the reference ships no tests for them).
  *
@@ -30,29 +31,59 @@
 #define M_PI 3.14159265358979323846
 #endif
 
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+#define CLONES __attribute__((target_clones("avx512f", "avx2", "default")))
+#else
+#define CLONES
+#endif
+
 #define DEFINE_ORACLE(T, SUF, SIN, COS, TAU_CONST)                                                          \
     typedef struct { T re, im; } cx_##SUF;                                                                  \
                                                                                                             \
-    /* in-place radix-2 DIT FFT, unnormalised; tw[k] = exp(-+ j 2 pi k / n), k < n/2 */                      \
-    static void fft_##SUF(cx_##SUF* a, size_t n, const cx_##SUF* tw) {                                      \
-        for (size_t i = 1, j = 0; i < n; ++i) {                                                             \
-            size_t bit = n >> 1;                                                                            \
-            for (; j & bit; bit >>= 1) j ^= bit;                                                            \
-            j ^= bit;                                                                                       \
-            if (i < j) { cx_##SUF t = a[i]; a[i] = a[j]; a[j] = t; }                                        \
-        }                                                                                                   \
-        for (size_t len = 2; len <= n; len <<= 1) {                                                         \
-            const size_t half = len >> 1, step = n / len;                                                   \
-            for (size_t i = 0; i < n; i += len) {                                                           \
-                for (size_t k = 0; k < half; ++k) {                                                         \
-                    const cx_##SUF w = tw[k * step];                                                        \
-                    const cx_##SUF u = a[i + k], x = a[i + k + half];                                       \
-                    const T vr = x.re * w.re - x.im * w.im, vi = x.re * w.im + x.im * w.re;                 \
-                    a[i + k].re = u.re + vr; a[i + k].im = u.im + vi;                                       \
-                    a[i + k + half].re = u.re - vr; a[i + k + half].im = u.im - vi;                         \
+    /* radix-4 Stockham autosort FFT (a closing radix-2 pass when log2 n is odd), unnormalised, result in `a`;  */   \
+    /* tw[k] = exp(-+ j 2 pi k / n) for k < n, `b` is scratch of n elements; INV selects the sign of j           */   \
+    CLONES static void fft_##SUF(cx_##SUF* a, cx_##SUF* b, size_t n, const cx_##SUF* tw, int inv) {                   \
+        cx_##SUF *x = a, *y = b;                                                                            \
+        size_t m = n, s = 1;                                                                                \
+        for (; m >= 4; m >>= 2, s <<= 2) {                                                                  \
+            const size_t m1 = m >> 2, tstep = n / m;                                                        \
+            for (size_t p = 0; p < m1; ++p) {                                                               \
+                const cx_##SUF w1 = tw[p * tstep], w2 = tw[2 * p * tstep], w3 = tw[3 * p * tstep];          \
+                const cx_##SUF* xa = x + s * p;                                                             \
+                const cx_##SUF* xb = x + s * (p + m1);                                                      \
+                const cx_##SUF* xc = x + s * (p + 2 * m1);                                                  \
+                const cx_##SUF* xd = x + s * (p + 3 * m1);                                                  \
+                cx_##SUF* y0 = y + s * (4 * p);                                                             \
+                cx_##SUF* y1 = y0 + s;                                                                      \
+                cx_##SUF* y2 = y1 + s;                                                                      \
+                cx_##SUF* y3 = y2 + s;                                                                      \
+                for (size_t q = 0; q < s; ++q) {                                                            \
+                    const T apc_r = xa[q].re + xc[q].re, apc_i = xa[q].im + xc[q].im;                       \
+                    const T amc_r = xa[q].re - xc[q].re, amc_i = xa[q].im - xc[q].im;                       \
+                    const T bpd_r = xb[q].re + xd[q].re, bpd_i = xb[q].im + xd[q].im;                       \
+                    const T bmd_r = xb[q].re - xd[q].re, bmd_i = xb[q].im - xd[q].im;                       \
+                    /* j*(b-d) forward: (-im, re); inverse: (im, -re) */                                    \
+                    const T jr = inv ? bmd_i : -bmd_i, ji = inv ? -bmd_r : bmd_r;                           \
+                    const T t1r = amc_r - jr, t1i = amc_i - ji;                                             \
+                    const T t2r = apc_r - bpd_r, t2i = apc_i - bpd_i;                                       \
+                    const T t3r = amc_r + jr, t3i = amc_i + ji;                                             \
+                    y0[q].re = apc_r + bpd_r; y0[q].im = apc_i + bpd_i;                                     \
+                    y1[q].re = t1r * w1.re - t1i * w1.im; y1[q].im = t1r * w1.im + t1i * w1.re;             \
+                    y2[q].re = t2r * w2.re - t2i * w2.im; y2[q].im = t2r * w2.im + t2i * w2.re;             \
+                    y3[q].re = t3r * w3.re - t3i * w3.im; y3[q].im = t3r * w3.im + t3i * w3.re;             \
                 }                                                                                           \
             }                                                                                               \
+            cx_##SUF* t = x; x = y; y = t;                                                                  \
         }                                                                                                   \
+        if (m == 2) {                                                                                       \
+            for (size_t q = 0; q < s; ++q) {                                                                \
+                const cx_##SUF u = x[q], v = x[q + s];                                                      \
+                y[q].re = u.re + v.re; y[q].im = u.im + v.im;                                               \
+                y[q + s].re = u.re - v.re; y[q + s].im = u.im - v.im;                                       \
+            }                                                                                               \
+            cx_##SUF* t = x; x = y; y = t;                                                                  \
+        }                                                                                                   \
+        if (x != a) memcpy(a, x, sizeof(cx_##SUF) * n);                                                     \
     }                                                                                                       \
                                                                                                             \
     typedef struct {                                                                                        \
@@ -68,21 +99,44 @@
         size_t* n_out;            /* [n_streams] */                                                         \
         const int64_t* numer;     /* reduced ratio per stream (transform.rs:298-302) */                     \
         const int64_t* denom;                                                                               \
+        const cx_##SUF* const* phase_tabs; /* optional: prebuilt phase tables (the reference builds its table  */ \
+                                           /* once per retune, transform.rs:321-340, outside the steady state) */ \
         size_t s_begin, s_end;                                                                              \
         int status;                                                                                         \
     } job_##SUF;                                                                                            \
+                                                                                                            \
+    /* FreqShifter's phase table of `denom` entries (transform.rs:321-340) */                               \
+    void oracle_phase_table_##SUF(int64_t numer, int64_t denom, T* out) {                                   \
+        cx_##SUF* phase = (cx_##SUF*)out;                                                                   \
+        int64_t i = 0;                                                                                      \
+        for (int64_t k = 0; k < denom; ++k) {                                                               \
+            const T ph = (T)0 + (T)i / (T)denom * (T)TAU_CONST; /* transform.rs:335 */                      \
+            phase[k].re = COS(ph); phase[k].im = SIN(ph);                                                   \
+            i = (i + numer) % denom; /* C '%' truncates like Rust's */                                      \
+        }                                                                                                   \
+    }                                                                                                       \
+                                                                                                            \
+    CLONES static void fir_##SUF(const cx_##SUF* ring, size_t ring_pos, size_t L, const T* ir, cx_##SUF* out) { \
+        /* resampling.rs:112-120: L-tap dot product over the ring, oldest sample first */                    \
+        T sr = 0, si = 0;                                                                                   \
+        size_t q = 0;                                                                                       \
+        for (size_t i = ring_pos; i < L; ++i, ++q) { sr += ring[i].re * ir[q]; si += ring[i].im * ir[q]; } \
+        for (size_t i = 0; i < ring_pos; ++i, ++q) { sr += ring[i].re * ir[q]; si += ring[i].im * ir[q]; } \
+        out->re = sr; out->im = si;                                                                         \
+    }                                                                                                       \
                                                                                                             \
     static void* worker_##SUF(void* arg) {                                                                  \
         job_##SUF* jb = (job_##SUF*)arg;                                                                    \
         const size_t n = jb->n, N = 2 * n, L = jb->L;                                                       \
         cx_##SUF* buf = (cx_##SUF*)malloc(sizeof(cx_##SUF) * N);                                            \
-        cx_##SUF* twf = (cx_##SUF*)malloc(sizeof(cx_##SUF) * (N / 2 + 1));                                  \
-        cx_##SUF* twi = (cx_##SUF*)malloc(sizeof(cx_##SUF) * (N / 2 + 1));                                  \
+        cx_##SUF* scr = (cx_##SUF*)malloc(sizeof(cx_##SUF) * N);                                            \
+        cx_##SUF* twf = (cx_##SUF*)malloc(sizeof(cx_##SUF) * (N + 1));                                      \
+        cx_##SUF* twi = (cx_##SUF*)malloc(sizeof(cx_##SUF) * (N + 1));                                      \
         cx_##SUF* mixed = (cx_##SUF*)malloc(sizeof(cx_##SUF) * n);                                          \
         cx_##SUF* prev = (cx_##SUF*)malloc(sizeof(cx_##SUF) * n);                                           \
         cx_##SUF* ring = (cx_##SUF*)calloc(L ? L : 1, sizeof(cx_##SUF));                                    \
-        if (!buf || !twf || !twi || !mixed || !prev || !ring) { jb->status = -1; return NULL; }             \
-        for (size_t k = 0; k < N / 2; ++k) {                                                                \
+        if (!buf || !scr || !twf || !twi || !mixed || !prev || !ring) { jb->status = -1; return NULL; }     \
+        for (size_t k = 0; k < N; ++k) {                                                                \
             const double a = -2.0 * M_PI * (double)k / (double)N;                                           \
             twf[k].re = (T)cos(a); twf[k].im = (T)sin(a);                                                   \
             twi[k].re = (T)cos(a); twi[k].im = (T)(-sin(a));                                                \
@@ -92,18 +146,18 @@
             cx_##SUF* y = jb->y[s];                                                                         \
             size_t produced = 0;                                                                            \
             /* FreqShifter: phase table of `denom` entries (transform.rs:321-340) */                        \
-            cx_##SUF* phase = NULL;                                                                         \
+            const cx_##SUF* phase = NULL;                                                                   \
+            cx_##SUF* phase_own = NULL;                                                                     \
             size_t plen = 0, pidx = 0;                                                                      \
             if (jb->with_nco) {                                                                             \
-                const int64_t numer = jb->numer[s], denom = jb->denom[s];                                   \
-                plen = (size_t)denom;                                                                       \
-                phase = (cx_##SUF*)malloc(sizeof(cx_##SUF) * plen);                                         \
-                if (!phase) { jb->status = -1; break; }                                                     \
-                int64_t i = 0;                                                                              \
-                for (size_t k = 0; k < plen; ++k) {                                                         \
-                    const T ph = (T)0 + (T)i / (T)denom * (T)TAU_CONST; /* transform.rs:335 */              \
-                    phase[k].re = COS(ph); phase[k].im = SIN(ph);                                           \
-                    i = (i + numer) % denom; /* C '%' truncates like Rust's */                              \
+                plen = (size_t)jb->denom[s];                                                                \
+                if (jb->phase_tabs) {                                                                       \
+                    phase = jb->phase_tabs[s];                                                              \
+                } else {                                                                                    \
+                    phase_own = (cx_##SUF*)malloc(sizeof(cx_##SUF) * plen);                                 \
+                    if (!phase_own) { jb->status = -1; break; }                                             \
+                    oracle_phase_table_##SUF(jb->numer[s], jb->denom[s], (T*)phase_own);                    \
+                    phase = phase_own;                                                                      \
                 }                                                                                           \
             }                                                                                               \
             int have_prev = 0;                                                                              \
@@ -133,13 +187,13 @@
                     memcpy(buf, prev, sizeof(cx_##SUF) * n);       /* filters.rs:241-243 */                 \
                     memcpy(buf + n, in, sizeof(cx_##SUF) * n);                                              \
                     memcpy(prev, in, sizeof(cx_##SUF) * n);        /* filters.rs:260 */                     \
-                    fft_##SUF(buf, N, twf);                        /* filters.rs:244-246 */                 \
+                    fft_##SUF(buf, scr, N, twf, 0);                /* filters.rs:244-246 */                 \
                     for (size_t k = 0; k < N; ++k) {               /* filters.rs:247-249 */                 \
                         const cx_##SUF h = jb->hext[k], v = buf[k];                                         \
                         buf[k].re = v.re * h.re - v.im * h.im;                                              \
                         buf[k].im = v.re * h.im + v.im * h.re;                                              \
                     }                                                                                       \
-                    fft_##SUF(buf, N, twi);                        /* filters.rs:250-252 */                 \
+                    fft_##SUF(buf, scr, N, twi, 1);                /* filters.rs:250-252 */                 \
                     z = buf;                                       /* truncate(n), filters.rs:253 */        \
                 }                                                                                           \
                 if (jb->with_down) {                                                                        \
@@ -150,11 +204,7 @@
                         pos += jb->out_rate;                                                                \
                         if (pos >= jb->in_rate) {                                                           \
                             pos -= jb->in_rate;                                                             \
-                            T sr = 0, si = 0;                                                               \
-                            size_t q = 0;                                                                   \
-                            for (size_t i = ring_pos; i < L; ++i, ++q) { sr += ring[i].re * jb->ir[q]; si += ring[i].im * jb->ir[q]; } \
-                            for (size_t i = 0; i < ring_pos; ++i, ++q) { sr += ring[i].re * jb->ir[q]; si += ring[i].im * jb->ir[q]; } \
-                            y[produced].re = sr; y[produced].im = si;                                       \
+                            fir_##SUF(ring, ring_pos, L, jb->ir, &y[produced]);                             \
                             ++produced;                                                                     \
                         }                                                                                   \
                     }                                                                                       \
@@ -164,9 +214,9 @@
                 }                                                                                           \
             }                                                                                               \
             jb->n_out[s] = produced;                                                                        \
-            free(phase);                                                                                    \
+            free(phase_own);                                                                                \
         }                                                                                                   \
-        free(buf); free(twf); free(twi); free(mixed); free(prev); free(ring);                               \
+        free(buf); free(scr); free(twf); free(twi); free(mixed); free(prev); free(ring);                               \
         return NULL;                                                                                        \
     }                                                                                                       \
                                                                                                             \
@@ -175,7 +225,8 @@
     /* samples are returned concatenated).  Returns 0 on success.                                    */   \
     int oracle_chain_##SUF(size_t n_streams, size_t n, size_t n_chunks, const T* const* x, T* const* y, size_t* n_out, \
                            int with_nco, const int64_t* numer, const int64_t* denom, int with_filter, const T* hext,    \
-                           int with_down, const T* ir, size_t L, double in_rate, double out_rate, int n_threads) {      \
+                           int with_down, const T* ir, size_t L, double in_rate, double out_rate, int n_threads,        \
+                           const T* const* phase_tabs) {                                                                \
         if (n_threads < 1) n_threads = 1;                                                                   \
         if ((size_t)n_threads > n_streams) n_threads = (int)(n_streams ? n_streams : 1);                    \
         if (with_filter && (n < 2 || (n & (n - 1)))) return -2;                                             \
@@ -189,7 +240,7 @@
             jb->in_rate = in_rate; jb->out_rate = out_rate;                                                 \
             jb->with_nco = with_nco; jb->with_filter = with_filter; jb->with_down = with_down;              \
             jb->x = (const cx_##SUF* const*)x; jb->y = (cx_##SUF* const*)y; jb->n_out = n_out;              \
-            jb->numer = numer; jb->denom = denom;                                                           \
+            jb->numer = numer; jb->denom = denom; jb->phase_tabs = (const cx_##SUF* const*)phase_tabs;      \
             jb->s_begin = n_streams * (size_t)i / (size_t)n_threads;                                        \
             jb->s_end = n_streams * (size_t)(i + 1) / (size_t)n_threads;                                    \
             jb->status = 0;                                                                                 \

@@ -1946,6 +1946,7 @@ int rr_metering_level(rr_ctx* ctx, int32_t dtype, const void* dev_in, size_t in_
     if (n_streams > 65535) return fail(RR_ERR_INVALID, "rr_metering_level: at most 65535 streams per call");
     if (n_chunks == 0) return RR_OK;
     RR_CUDA(cudaSetDevice(ctx->device));
+    (void)cudaGetLastError();  // a stale error of an unrelated earlier call is not ours
     RR_CUDA(cudaDeviceSynchronize());  // dev_in may still be written by a chain's (non-blocking) stream
     DevBuf out;
     RR_TRY(out.ensure(sizeof(double) * n_chunks * (size_t)n_streams));
@@ -1969,6 +1970,7 @@ int rr_metering_bandwidth(rr_ctx* ctx, int32_t dtype, const void* dev_bins, size
     if (n_streams < 1 || n_streams > 65535 || chunk_len == 0) return fail(RR_ERR_INVALID, "rr_metering_bandwidth: empty chunk or bad stream count");
     if (n_chunks == 0) return RR_OK;
     RR_CUDA(cudaSetDevice(ctx->device));
+    (void)cudaGetLastError();  // a stale error of an unrelated earlier call is not ours
     RR_CUDA(cudaDeviceSynchronize());  // dev_bins may still be written by a chain's (non-blocking) stream
     DevBuf out;
     RR_TRY(out.ensure(sizeof(double) * n_chunks * (size_t)n_streams));
@@ -1993,6 +1995,7 @@ int rr_metering_rescale_energy(rr_ctx* ctx, int32_t dtype, const void* dev_bins,
     if (n_streams < 1 || n_streams > 65535 || n_chunks > 65535) return fail(RR_ERR_INVALID, "rr_metering_rescale_energy: at most 65535 streams and chunks per call");
     if (n_chunks == 0 || resolution == 0) return RR_OK;
     RR_CUDA(cudaSetDevice(ctx->device));
+    (void)cudaGetLastError();  // a stale error of an unrelated earlier call is not ours
     RR_CUDA(cudaDeviceSynchronize());  // dev_bins may still be written by a chain's (non-blocking) stream
     const size_t fsz = dtype == RR_C32 ? sizeof(float) : sizeof(double);
     const size_t bytes = fsz * n_chunks * (size_t)n_streams * resolution;
@@ -2337,6 +2340,7 @@ int rr_chain_push_device(rr_chain* c, double sample_rate, size_t chunk_len, size
     if (!dev_in) return fail(RR_ERR_INVALID, "rr_chain_push_device: dev_in is null");
     if (chunk_len > (size_t)1 << 30 || n_chunks > (size_t)1 << 30) return fail(RR_ERR_INVALID, "push too large");
     RR_CUDA(cudaSetDevice(c->ctx->device));
+    (void)cudaGetLastError();  // a stale error of an unrelated earlier call (another library in the process) is not ours
     c->push_mutated = false;
     int r;
     if (c->dtype == RR_C32)

@@ -555,6 +555,10 @@ k_fused(const __grid_constant__ CUtensorMap tmap, const FusedArgs a, const int n
                 asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(keep_s + r * PITCH), "f"(nx.x), "f"(nx.y), "f"(nx.z), "f"(nx.w) : "memory");
             }
         }
+        // row 511 takes part in the transform but in no stored output (the l = -1 slot of the low-rate filter is empty for
+        // Q == 1): it must not hold what the previous block's exchange left there -- stale values of spectrum magnitude
+        // would add their rounding noise to every output
+        if (lane == 0) asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(stg + (FK - 1) * PITCH + warp * 16), "f"(0.f) : "memory");
         __syncwarp();
 
         // ---- forward transforms of this warp's two columns, products with FFT(b_c) ----------------------------------

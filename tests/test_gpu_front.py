@@ -201,7 +201,7 @@ def test_front_full_baseline_size_on_device(ctx):
     """BASELINE.json config C3 at its full single-GPU size -- 4096 streams x 50 chunks x 4096 samples per push,
     device resident (6.7 GB of input) -- through properties that need no oracle run at that size:
     streams s and s + 2048 get identical samples and shifts and must come out bit-identical (independence,
-    determinism, no cross-stream leakage in the persistent kernels), two pushes, and three streams are checked
+    determinism, no cross-stream leakage in the persistent kernels), three pushes, and three streams are checked
     against the oracle sample by sample."""
     import torch
 
@@ -222,12 +222,13 @@ def test_front_full_baseline_size_on_device(ctx):
     cap = chain.max_output(sr, n, C + 1) + 2048
     y = torch.zeros((S, cap, 2), device="cuda", dtype=torch.float32)
     outs = []
-    for push in range(2):
+    for push in range(3):
         cnt, rate = chain.push_device(sr, n, C, x.data_ptr(), length, y.data_ptr(), cap, cap)
         chain.sync()
         torch.cuda.synchronize()
         assert rate == 48000.0 and cnt > 0 and cnt % 2048 == 0
-        assert "front+poly2" in chain.plan, chain.plan
+        # push 0: start-up chunks + k_front + k_poly2; push 1 (steady state): k_fused
+        assert ("front+poly2" if push == 0 else "fused[") in chain.plan, chain.plan
         got = y[:, :cnt].clone()
         assert torch.equal(got[:half], got[half:])
         assert bool(torch.isfinite(got).all())
@@ -237,8 +238,8 @@ def test_front_full_baseline_size_on_device(ctx):
         xs = x[s].cpu().numpy().view(np.complex64).reshape(-1)
         oc = orc.Chain([orc.FreqShifter("f32", 1.0, shifts[s]), orc.Filter.new("f32", orc.lowpass(3000.0)),
                         orc.Downsampler("f32", 2048, 48000.0, 6000.0)])
-        want = oc.run(sr, np.concatenate([xs, xs]), n)
-        g = torch.cat([outs[0][s], outs[1][s]]).cpu().numpy().view(np.complex64).reshape(-1)
+        want = oc.run(sr, np.concatenate([xs, xs, xs]), n)
+        g = torch.cat([outs[0][s], outs[1][s], outs[2][s]]).cpu().numpy().view(np.complex64).reshape(-1)
         assert g.shape == want.shape
         assert orc.rel_l2(g, want) <= TOL
     del x, y
