@@ -152,6 +152,14 @@ int rr_host_register(rr_ctx* ctx, void* p, size_t bytes);
 int rr_host_unregister(rr_ctx* ctx, void* p);
 int rr_device_alloc(rr_ctx* ctx, size_t bytes, void** out);
 int rr_device_free(rr_ctx* ctx, void* p);
+/* A device buffer of ANOTHER process's GPU (one process per GPU) as a local pointer: the owner exports a 64-byte
+ * handle of a buffer it got from rr_device_alloc, the others open it (peer access over NVLink is enabled on
+ * opening).  Passed as `dev_out` of rr_chain_push_device it makes the chain's last kernel store its outputs
+ * straight into the owner's memory -- the gather of a channelizer's outputs without a collective
+ * kernel.  The owner keeps the buffer allocated until every opener has closed it. */
+int rr_ipc_export(rr_ctx* ctx, void* dev_ptr, void* handle_out_64_bytes);
+int rr_ipc_open(rr_ctx* ctx, const void* handle_64_bytes, void** dev_ptr);
+int rr_ipc_close(rr_ctx* ctx, void* dev_ptr);
 /* synchronous copies; both first wait for ALL work queued on the device (chains run on their own non-blocking
  * streams), so they are safe right behind rr_chain_push_device without an rr_chain_sync */
 int rr_memcpy_h2d(rr_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);

@@ -83,6 +83,9 @@ SIGNATURES = {
     "rr_host_unregister": (_I, [_P, _P]),
     "rr_device_alloc": (_I, [_P, _SZ, C.POINTER(_P)]),
     "rr_device_free": (_I, [_P, _P]),
+    "rr_ipc_export": (_I, [_P, _P, _P]),
+    "rr_ipc_open": (_I, [_P, _P, C.POINTER(_P)]),
+    "rr_ipc_close": (_I, [_P, _P]),
     "rr_memcpy_h2d": (_I, [_P, _P, _P, _SZ]),
     "rr_memcpy_d2h": (_I, [_P, _P, _P, _SZ]),
     "rr_metering_level": (_I, [_P, C.c_int32, _P, _SZ, _SZ, _SZ, _I, C.POINTER(_D)]),

@@ -1922,6 +1922,31 @@ int rr_device_free(rr_ctx* ctx, void* p) {
     if (p) RR_CUDA(cudaFree(p));
     return RR_OK;
 }
+// ---- device buffers shared between processes (one process per GPU): the gather of the channelizer outputs -------
+int rr_ipc_export(rr_ctx* ctx, void* dev_ptr, void* handle_out_64_bytes) {
+    if (!ctx || !dev_ptr || !handle_out_64_bytes) return fail(RR_ERR_INVALID, "rr_ipc_export: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the header promises a 64-byte handle");
+    RR_CUDA(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    RR_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
+    std::memcpy(handle_out_64_bytes, &h, sizeof h);
+    return RR_OK;
+}
+int rr_ipc_open(rr_ctx* ctx, const void* handle_64_bytes, void** dev_ptr) {
+    if (!ctx || !handle_64_bytes || !dev_ptr) return fail(RR_ERR_INVALID, "rr_ipc_open: null argument");
+    *dev_ptr = nullptr;
+    RR_CUDA(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle_64_bytes, sizeof h);
+    RR_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return RR_OK;
+}
+int rr_ipc_close(rr_ctx* ctx, void* dev_ptr) {
+    if (!ctx) return fail(RR_ERR_INVALID, "rr_ipc_close: null context");
+    RR_CUDA(cudaSetDevice(ctx->device));
+    if (dev_ptr) RR_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    return RR_OK;
+}
 int rr_memcpy_h2d(rr_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
     if (!ctx) return fail(RR_ERR_INVALID, "rr_memcpy_h2d: null context");
     RR_CUDA(cudaSetDevice(ctx->device));
