@@ -130,6 +130,10 @@ struct StageHost {
     int r_L = 0;
     long long P = 1, Q = 1, j0 = 0, m0 = 0;
     size_t r_pending = 0;
+    // rates that are not integer valued: the firing pattern follows the reference's f64 `pos` recurrence
+    // (resampling.rs:67,109-111 / :197,247-266) step by step instead of the exact rational form
+    bool r_indexed = false;
+    double r_pos = 0.0;
     // FMDEMOD
     bool fm_has_prev = false;
     // FREQSHIFT
@@ -149,6 +153,7 @@ struct StageAct {
     size_t n_new = 0;          // resampler: samples produced by this push
     size_t pending_before = 0;
     long long j0 = 0, m0 = 0;  // resampler counters before the push
+    double pos0 = 0.0;         // indexed resampler: `pos` before the push
     bool nco_recalc = false;
     int seg_before = 0;        // filter: chunks of the current segment seen before this push
     bool lost = false;         // Rechunker: the partial chunk was dropped (SamplesLost goes downstream first)
@@ -201,6 +206,12 @@ struct Stage {
     // >= 0: this push's k_front already wrote entries [hist_fused_jfirst, hist_fused_jlo) of the new hist2
     long long hist_fused_jlo = -1, hist_fused_jfirst = 0;
     DevBuf ztmp;      // filter-output scratch of the unfused stateful path
+    // chunk lengths that are not a power of two run on the kernels of the next power of two f_np (taps zero padded):
+    // [history chunk | pushed chunks] is staged contiguously, transformed in chunks of f_np, and the wanted slice copied out
+    size_t f_np = 0;
+    DevBuf stg_in, stg_out, zero_chunk;
+    // indexed resamplers: firing / position tables of the current push
+    DevBuf idx_a, idx_b;
     std::vector<std::complex<double>> taps;  // windowed impulse response (Flt-rounded), for the polyphase tables
     bool taps_valid = false;
     // big overlap-save tables
@@ -407,12 +418,17 @@ int advance_stage(const rr_stage_desc& d, StageHost& h, const Shape& in, StageAc
                 const double margin = down ? (out_rate - d.bandwidth) / 2.0 : (in_rate - d.bandwidth) / 2.0;
                 const double lf = std::ceil((down ? in_rate : out_rate) / margin * d.quality);
                 if (!(lf > 0.0) || lf > 1.0e8) return fail(RR_ERR_INVALID, "resampler impulse response length out of range");
-                if (!integer_valued(in_rate) || !integer_valued(out_rate) || in_rate == 0.0 || out_rate == 0.0)
-                    return fail(RR_ERR_UNSUPPORTED, "device resamplers need integer-valued, non-zero sample rates");
-                long long Pn = (long long)in_rate, Qn = (long long)out_rate;
-                const long long g = std::gcd(Pn, Qn);
-                h.P = Pn / g;
-                h.Q = Qn / g;
+                if (in_rate == 0.0 || out_rate == 0.0) return fail(RR_ERR_INVALID, "resampler sample rates must be non-zero");
+                h.r_indexed = !integer_valued(in_rate) || !integer_valued(out_rate);
+                h.r_pos = 0.0;
+                if (!h.r_indexed) {
+                    long long Pn = (long long)in_rate, Qn = (long long)out_rate;
+                    const long long g = std::gcd(Pn, Qn);
+                    h.P = Pn / g;
+                    h.Q = Qn / g;
+                } else {
+                    h.P = h.Q = 1;
+                }
                 h.j0 = 0;
                 h.m0 = 0;
                 h.r_L = (int)lf;
@@ -423,13 +439,40 @@ int advance_stage(const rr_stage_desc& d, StageHost& h, const Shape& in, StageAc
             const long long len = (long long)in.len();
             a.j0 = h.j0;
             a.m0 = h.m0;
-            long long total_after;
-            if (down) total_after = floordiv128(h.j0 + len, h.Q, h.P);  // outputs m with ceil(m*P/Q) <= J
-            else total_after = ceildiv128(h.j0 + len, h.Q, h.P);        // q_p = ceil(p*Q/P), resampling.rs:249-266
-            a.n_new = (size_t)(total_after - h.m0);
-            const long long j1 = (h.j0 + len) % h.P;
-            h.j0 = j1;
-            h.m0 = down ? floordiv128(j1, h.Q, h.P) : ceildiv128(j1, h.Q, h.P);
+            a.pos0 = h.r_pos;
+            if (h.r_indexed) {
+                // the reference's recurrence, literally (f64 `pos`): count the outputs of this push
+                const double in_rate = in.rate, out_rate = d.output_rate;
+                double pos = h.r_pos;
+                size_t cnt = 0;
+                if (down) {
+                    for (long long j = 0; j < len; ++j) {  // resampling.rs:109-111
+                        pos += out_rate;
+                        if (pos >= in_rate) {
+                            pos -= in_rate;
+                            ++cnt;
+                        }
+                    }
+                } else {
+                    for (long long p = 0; p < len; ++p) {  // resampling.rs:247-266
+                        while (pos < out_rate) {
+                            ++cnt;
+                            pos += in_rate;
+                        }
+                        pos -= out_rate;
+                    }
+                }
+                h.r_pos = pos;
+                a.n_new = cnt;
+            } else {
+                long long total_after;
+                if (down) total_after = floordiv128(h.j0 + len, h.Q, h.P);  // outputs m with ceil(m*P/Q) <= J
+                else total_after = ceildiv128(h.j0 + len, h.Q, h.P);        // q_p = ceil(p*Q/P), resampling.rs:249-266
+                a.n_new = (size_t)(total_after - h.m0);
+                const long long j1 = (h.j0 + len) % h.P;
+                h.j0 = j1;
+                h.m0 = down ? floordiv128(j1, h.Q, h.P) : ceildiv128(j1, h.Q, h.P);
+            }
             a.pending_before = h.r_pending;
             const size_t ocl = d.output_chunk_len ? (size_t)d.output_chunk_len : 1;
             const size_t total = h.r_pending + a.n_new;
@@ -476,11 +519,18 @@ int stage_event(const rr_stage_desc& d, StageHost& h, bool* interrupt) {
 }
 
 // chunk lengths the device Filter takes
-template <typename T> bool filter_len_supported(size_t n) {
-    if (n < 2 || n > ((size_t)1 << 24)) return false;
-    if ((n & (n - 1)) != 0) return false;
-    return rr::chain_os_supported<T>((int)n, 0, 0) || rr::big_os_supported<T>((int)n);
+// the power-of-two chunk length the device kernels run a Filter of chunk length n with (n itself when it is one)
+inline size_t filter_padded_len(size_t n) {
+    size_t np = 32;
+    while (np < n) np <<= 1;
+    return np;
 }
+template <typename T> bool filter_len_supported(size_t n) {
+    if (n < 1 || n > ((size_t)1 << 23)) return false;
+    const size_t np = filter_padded_len(n);
+    return rr::chain_os_supported<T>((int)np, 0, 0) || rr::big_os_supported<T>((int)np);
+}
+inline bool is_pow2(size_t n) { return n >= 2 && (n & (n - 1)) == 0; }
 
 // what the device path cannot take is refused here, BEFORE a push changes any state (the dry run calls this)
 int stage_supported(const rr_chain* c, const rr_stage_desc& d, const Shape& in) {
@@ -630,6 +680,20 @@ template <typename T> int filter_redesign(rr_chain* c, Stage& s, double sample_r
     std::vector<std::complex<double>> H;
     if (!rr::design_filter_response(f, w, sample_rate, n, sizeof(T) == 4, &H, &s.taps))
         return fail(RR_ERR_UNSUPPORTED, "Filter: design failed");
+    const size_t n_orig = n;
+    s.f_np = filter_padded_len(n);
+    if (s.f_np != n) {
+        // z[k] = sum_{m<n} taps[m] x[k-m] on the kernels of chunk length f_np: the same taps, zero padded, in the second
+        // half of a 2*f_np buffer (filters.rs:220-226 with n -> f_np)
+        n = s.f_np;
+        H.assign(2 * n, std::complex<double>(0.0, 0.0));
+        for (size_t i = 0; i < n_orig; ++i) H[n + i] = s.taps[i];
+        rr::fft_pow2(H, false);
+        // ... and the reference's 1/(2 n^2) (filters.rs:186) goes with ITS inverse of 2n points; this one has 2*f_np
+        const double fix = (double)n_orig / (double)n;
+        for (auto& v : H) v *= fix;
+        RR_TRY(s.zero_chunk.ensure(n * 2 * sizeof(T), true, c->stream));
+    }
     const size_t N = 2 * n;
     if (rr::chain_os_supported<T>((int)n, 0, 0)) {
         std::vector<std::complex<double>> hp(N), tw;
@@ -652,7 +716,7 @@ template <typename T> int filter_redesign(rr_chain* c, Stage& s, double sample_r
     } else {
         return fail(RR_ERR_UNSUPPORTED, "Filter: chunk length not supported by the device path");
     }
-    const size_t hb = (size_t)c->S * 2 * n * 2 * sizeof(T);
+    const size_t hb = (size_t)c->S * 2 * n_orig * 2 * sizeof(T);
     RR_TRY(s.hist2[0].ensure(hb));
     RR_TRY(s.hist2[1].ensure(hb));
     s.taps_valid = true;
@@ -805,11 +869,58 @@ template <typename T> int materialize_nco(rr_chain* c, Stage& nco, const FilterI
 // hist2's newer half; `fih`: chunk 0 only primes the filter (filters.rs:240,260).
 // Writes (k - fih) * n filter outputs to dst.
 template <typename T>
-int run_os(rr_chain* c, Stage& s, const FilterIo& io, size_t k, bool fih, void* dst, long long dst_stride) {
+int run_os(rr_chain* c, Stage& s, const FilterIo& io, size_t k, bool fih, void* dst, long long dst_stride, const void* hist_override = nullptr,
+           long long hist_stride_override = 0);
+
+// Chunk lengths that are not a power of two (filters.rs:227-228 plans any length): the filter is
+// z[t] = sum_{m<n} taps[m] x[t-m], so it can run on the kernels of the next power of two f_np with the taps zero
+// padded.  [history chunk | pushed chunks] is staged contiguously (mixed, when an NCO is folded in), cut into chunks of
+// f_np behind a zero chunk, transformed, and the outputs of the pushed samples are copied out.
+template <typename T>
+int run_os_padded(rr_chain* c, Stage& s, const FilterIo& io, size_t k, bool fih, void* dst, long long dst_stride) {
+    const size_t n = io.n, np = s.f_np, esz = 2 * sizeof(T);
+    const int S = c->S;
+    const size_t n_hist = fih ? 0 : n;
+    const size_t Ls = n_hist + k * n;            // staged samples per stream
+    if (Ls <= n) return RR_OK;                    // nothing to emit
+    const size_t nch = (Ls + np - 1) / np;        // chunks of f_np
+    const size_t stride = nch * np;
+    RR_TRY(s.stg_in.ensure((size_t)S * stride * esz));
+    RR_TRY(s.stg_out.ensure((size_t)S * stride * esz));
+    char* stg = (char*)s.stg_in.p;
+    if (n_hist) {
+        const char* hist_newer = (const char*)s.hist2[s.hist_cur].p + n * esz;
+        RR_LAUNCH(1, rr::launch_copy2d<T>(hist_newer, (long long)(2 * n), stg, (long long)stride, (long long)n, S, c->stream));
+    }
+    if (io.nco) {
+        RR_LAUNCH(1, rr::launch_freqshift<T>(io.in, io.in_stride, stg + n_hist * esz, (long long)stride, (long long)(k * n), S,
+                                             (const rr::NcoStream*)io.nco->nco_d.p, 0, c->stream));
+    } else {
+        RR_LAUNCH(1, rr::launch_copy2d<T>(io.in, io.in_stride, stg + n_hist * esz, (long long)stride, (long long)(k * n), S, c->stream));
+    }
+    if (stride > Ls)
+        RR_CUDA(cudaMemset2DAsync(stg + Ls * esz, stride * esz, 0, (stride - Ls) * esz, (size_t)S, c->stream));
+    FilterIo pio;
+    pio.in = stg;
+    pio.in_stride = (long long)stride;
+    pio.n = np;
+    pio.n_chunks = nch;
+    pio.nco = nullptr;
+    RR_TRY(run_os<T>(c, s, pio, nch, false, s.stg_out.p, (long long)stride, s.zero_chunk.p, 0));
+    // staged index t holds the filter output of staged sample t: the pushed samples' outputs start at index n
+    RR_LAUNCH(1, rr::launch_copy2d<T>((const char*)s.stg_out.p + n * esz, (long long)stride, dst, dst_stride, (long long)(Ls - n), S, c->stream));
+    return RR_OK;
+}
+
+template <typename T>
+int run_os(rr_chain* c, Stage& s, const FilterIo& io, size_t k, bool fih, void* dst, long long dst_stride, const void* hist_override,
+           long long hist_stride_override) {
     const size_t n = io.n;
     const int S = c->S;
     if (k == 0) return RR_OK;
-    const char* hist_newer = (const char*)s.hist2[s.hist_cur].p + n * 2 * sizeof(T);
+    if (!hist_override && s.f_np != 0 && s.f_np != n) return run_os_padded<T>(c, s, io, k, fih, dst, dst_stride);
+    const char* hist_newer = hist_override ? (const char*)hist_override : (const char*)s.hist2[s.hist_cur].p + n * 2 * sizeof(T);
+    const long long hist_stride = hist_override ? hist_stride_override : (long long)(2 * n);
     if (rr::chain_os_supported<T>((int)n, 0, 0)) {
         rr::ChainOsArgs<T> a{};
         a.in = io.in;
@@ -818,7 +929,7 @@ int run_os(rr_chain* c, Stage& s, const FilterIo& io, size_t k, bool fih, void* 
         a.first_is_history = fih ? 1 : 0;
         a.emit = 1;
         a.hist_in = hist_newer;
-        a.hist_stride = (long long)(2 * n);
+        a.hist_stride = hist_stride;
         a.hist_out = nullptr;
         a.hperm = s.hperm.p;
         a.twN = s.tw.p;
@@ -863,8 +974,8 @@ int run_os(rr_chain* c, Stage& s, const FilterIo& io, size_t k, bool fih, void* 
             rr::BigOsArgs<T> a{};
             a.in = (const char*)src + s0 * (size_t)src_stride * esz;
             a.in_stride = src_stride;
-            a.hist = hist_newer + s0 * 2 * n * esz;
-            a.hist_stride = (long long)(2 * n);
+            a.hist = hist_newer + s0 * (size_t)hist_stride * esz;
+            a.hist_stride = hist_stride;
             a.first_chunk = (int)(first + b0);
             a.n_blocks = (int)nb;
             a.scratch = s.big_scratch.p;
@@ -1044,6 +1155,69 @@ template <typename T> int poly_prepare(rr_chain* c, Stage& f, Stage& ds) {
     return RR_OK;
 }
 
+// ---- resamplers at rates that are not integer valued ---------------------------------------------------------
+// The firing instants come from the reference's own f64 `pos` recurrence, replayed on the host for this push
+// (StageAct::pos0 = pos before the push), and are uploaded as index tables.
+template <typename T>
+int downsample_indexed(rr_chain* c, Stage& ds, const StageAct& a, const void* in, long long in_stride, long long len, void* out,
+                       long long out_stride) {
+    const double in_rate = ds.h.r_in_rate, out_rate = ds.d.output_rate;
+    std::vector<int> fire;
+    fire.reserve(a.n_new);
+    double pos = a.pos0;
+    for (long long j = 0; j < len; ++j) {  // resampling.rs:109-111
+        pos += out_rate;
+        if (pos >= in_rate) {
+            pos -= in_rate;
+            fire.push_back((int)j);
+        }
+    }
+    if (fire.size() != a.n_new) return fail(RR_ERR_INVALID, "internal: indexed downsampler count mismatch");
+    RR_TRY(ds.idx_a.ensure(std::max<size_t>(fire.size(), 1) * sizeof(int)));
+    if (!fire.empty()) RR_CUDA(cudaMemcpyAsync(ds.idx_a.p, fire.data(), fire.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    RR_CUDA(cudaStreamSynchronize(c->stream));  // `fire` is pageable and dies here
+    RR_LAUNCH(2, rr::launch_downsample_indexed<T>(in, in_stride, len, ds.tail[ds.tail_cur].p, ds.tail[ds.tail_cur ^ 1].p, (const T*)ds.ir.p,
+                                                  ds.h.r_L, (const int*)ds.idx_a.p, (long long)fire.size(), out, out_stride, c->S, c->stream));
+    ds.tail_cur ^= 1;
+    return RR_OK;
+}
+template <typename T>
+int upsample_indexed(rr_chain* c, Stage& us, const StageAct& a, const void* in, long long in_stride, long long len, void* out,
+                     long long out_stride) {
+    const double in_rate = us.h.r_in_rate, out_rate = us.d.output_rate;
+    const int L = us.h.r_L;
+    std::vector<int> qpos((size_t)len);
+    double pos = a.pos0;
+    long long q = 0;
+    for (long long p = 0; p < len; ++p) {  // resampling.rs:239-266: input p lands at the next cell to be emitted
+        qpos[(size_t)p] = (int)q;
+        while (pos < out_rate) {
+            ++q;
+            pos += in_rate;
+        }
+        pos -= out_rate;
+    }
+    if ((size_t)q != a.n_new) return fail(RR_ERR_INVALID, "internal: indexed upsampler count mismatch");
+    // cnt[i] = number of inputs with qpos <= i, i < n_new + L
+    std::vector<int> cnt((size_t)q + (size_t)L);
+    {
+        size_t p = 0;
+        for (size_t i = 0; i < cnt.size(); ++i) {
+            while (p < qpos.size() && (size_t)qpos[p] <= i) ++p;
+            cnt[i] = (int)p;
+        }
+    }
+    RR_TRY(us.idx_a.ensure(std::max<size_t>(qpos.size(), 1) * sizeof(int)));
+    RR_TRY(us.idx_b.ensure(std::max<size_t>(cnt.size(), 1) * sizeof(int)));
+    if (!qpos.empty()) RR_CUDA(cudaMemcpyAsync(us.idx_a.p, qpos.data(), qpos.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    if (!cnt.empty()) RR_CUDA(cudaMemcpyAsync(us.idx_b.p, cnt.data(), cnt.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    RR_CUDA(cudaStreamSynchronize(c->stream));
+    RR_LAUNCH(1, rr::launch_upsample_indexed<T>(in, in_stride, len, us.tail[us.tail_cur].p, us.tail[us.tail_cur ^ 1].p, (const T*)us.ir.p, L,
+                                                (const int*)us.idx_a.p, (const int*)us.idx_b.p, q, out, out_stride, c->S, c->stream));
+    us.tail_cur ^= 1;
+    return RR_OK;
+}
+
 // Filter stage `f` (with optional folded NCO) followed by Downsampler `ds`:
 // consumes the whole push, leaves new outputs behind ds's pending samples.
 // `direct` (optional): the Downsampler is the chain's last stage -- when the whole push goes through k_poly2, its
@@ -1064,13 +1238,14 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
     void* obase = (char*)ds.obuf[ds.obuf_cur].p + da.pending_before * 2 * sizeof(T);
     const long long ostride = (long long)ds.obuf_cap;
 
-    if (c->allow_poly) RR_TRY(poly_prepare<T>(c, f, ds));
+    const bool rational = !ds.h.r_indexed && is_pow2(n);  // the fused polyphase / overlap-save+FIR kernels need in/out = P/Q and a power-of-two chunk
+    if (c->allow_poly && rational) RR_TRY(poly_prepare<T>(c, f, ds));
     // the kept u rows stay usable only from one front-end push to the very next one
     const bool was_ucache_valid = ds.ucache_valid;
     ds.ucache_valid = false;
     // chunks the stateful path must take: those whose outputs still depend on pre-segment state
     size_t ca = io.n_chunks;
-    if (c->allow_poly && ds.poly_valid) {
+    if (c->allow_poly && rational && ds.poly_valid) {
         const size_t need = (size_t)(2 - std::min(2, fa.seg_before));
         ca = std::min(need, io.n_chunks);
     }
@@ -1080,9 +1255,18 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
     long long j0 = da.j0, m0 = da.m0;  // decimator counters at the start of the part being processed
     if (ca > fih) {
         const long long zlen = (long long)((ca - fih) * n);
+        if (ds.h.r_indexed) {
+            // rates that are not integer valued: Filter output to scratch, then the FIR at the firing instants of the
+            // reference's f64 recurrence
+            RR_TRY(f.ztmp.ensure((size_t)S * (size_t)zlen * 2 * sizeof(T)));
+            RR_TRY(run_os<T>(c, f, io, ca, fih != 0, f.ztmp.p, zlen));
+            RR_TRY(downsample_indexed<T>(c, ds, da, f.ztmp.p, zlen, zlen, obase, ostride));
+            *plan += "os|downsample(indexed)";
+            return RR_OK;
+        }
         const long long tot = floordiv128(j0 + zlen, ds.h.Q, ds.h.P);
         const long long n_out = tot - m0;
-        if (rr::chain_os_supported<T>((int)n, 1, L)) {
+        if (rational && rr::chain_os_supported<T>((int)n, 1, L)) {
             rr::ChainOsArgs<T> a{};
             a.in = io.in;
             a.in_stride = io.in_stride;
@@ -1120,7 +1304,7 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
             RR_LAUNCH(2, rr::launch_downsample<T>(f.ztmp.p, zlen, zlen, ds.tail[ds.tail_cur].p, ds.tail[ds.tail_cur ^ 1].p, (const T*)ds.ir.p,
                                                   L, rs, n_out, obase, ostride, S, st));
             ds.tail_cur ^= 1;
-            *plan += rr::chain_os_supported<T>((int)n, 0, 0) ? "fused_os[filter]|downsample" : "big_os|downsample";
+            *plan += !is_pow2(n) ? "padded_os[filter]|downsample" : (rr::chain_os_supported<T>((int)n, 0, 0) ? "fused_os[filter]|downsample" : "big_os|downsample");
         }
         obase = (char*)obase + (size_t)n_out * 2 * sizeof(T);
         j0 = (j0 + zlen) % ds.h.P;
@@ -1671,7 +1855,7 @@ int run_push(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_chunks,
                     cur.p = d.p;
                     cur.stride = d.stride;
                     cur.sh = a.out;
-                    plan += rr::chain_os_supported<T>((int)n, 0, 0) ? "fused_os[filter]" : "big_os";
+                    plan += !is_pow2(n) ? "padded_os[filter]" : (rr::chain_os_supported<T>((int)n, 0, 0) ? "fused_os[filter]" : "big_os");
                 }
                 // new history: the last two mixed chunks (filters.rs:260 keeps one; the polyphase path needs two)
                 {
@@ -1709,6 +1893,13 @@ int run_push(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_chunks,
                 rs.Q = s.h.Q;
                 rs.j0 = a.j0;
                 rs.m0 = a.m0;
+                if (s.h.r_indexed) {
+                    if (down) RR_TRY(downsample_indexed<T>(c, s, a, cur.p, cur.stride, len, o, (long long)s.obuf_cap));
+                    else RR_TRY(upsample_indexed<T>(c, s, a, cur.p, cur.stride, len, o, (long long)s.obuf_cap));
+                    plan += down ? "downsample(indexed)" : "upsample(indexed)";
+                    RR_TRY(resampler_emit<T>(c, s, a, last, dev_out, (long long)out_stride, &cur));
+                    break;
+                }
                 if (down) {
                     RR_TIMED_LAUNCH(c, "k_downsample", 2, rr::launch_downsample<T>(cur.p, cur.stride, len, s.tail[s.tail_cur].p, s.tail[s.tail_cur ^ 1].p,
                                                           (const T*)s.ir.p, s.h.r_L, rs, (long long)a.n_new, o, (long long)s.obuf_cap, S, st));
@@ -2067,7 +2258,7 @@ int rr_design_filter_response(rr_freq_resp_fn f, void* f_user, int32_t window_ki
     };
     std::vector<std::complex<double>> H;
     if (!rr::design_filter_response(fr, make_window(window_kind, window_beta, w, w_user), sample_rate, n, dtype == RR_C32, &H))
-        return fail(RR_ERR_UNSUPPORTED, "rr_design_filter_response: n must be a power of two >= 2");
+        return fail(RR_ERR_INVALID, "rr_design_filter_response: n must be >= 1");
     for (size_t i = 0; i < H.size(); ++i) {
         out_2n_complex[2 * i] = H[i].real();
         out_2n_complex[2 * i + 1] = H[i].imag();
@@ -2233,7 +2424,8 @@ int rr_chain_destroy(rr_chain* c) {
     for (auto& s : c->st) {
         DevBuf* bufs[] = {&s.nco_d, &s.hperm, &s.tw, &s.hist2[0], &s.hist2[1], &s.ztmp, &s.gtab, &s.twK, &s.big_h, &s.big_twA, &s.big_twB, &s.big_scratch,
                           &s.ir, &s.tail[0], &s.tail[1], &s.obuf[0], &s.obuf[1], &s.fm_prev, &s.fm_last, &s.out,
-                          &s.gtab2, &s.twK2, &s.acoef, &s.gtab3, &s.ubuf[0], &s.ubuf[1], &s.fwin, &s.ftw, &s.fm_phase, &s.ukeep[0], &s.ukeep[1]};
+                          &s.gtab2, &s.twK2, &s.acoef, &s.gtab3, &s.ubuf[0], &s.ubuf[1], &s.fwin, &s.ftw, &s.fm_phase, &s.ukeep[0], &s.ukeep[1],
+                          &s.stg_in, &s.stg_out, &s.zero_chunk, &s.idx_a, &s.idx_b};
         for (DevBuf* b : bufs) b->release();
         if (s.fused_slot >= 0) fused_slot_release(c->ctx->device, &s);
     }

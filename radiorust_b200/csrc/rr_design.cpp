@@ -94,10 +94,40 @@ void fft_pow2(std::vector<std::complex<double>>& a, bool inverse) {
     }
 }
 
+// Any length: powers of two directly, everything else by Bluestein's chirp-z identity on a power-of-two transform
+// (rustfft plans every length too, filters.rs:200,227-228).  The chirp angle is reduced exactly (k*k mod 2n in
+// integers) and evaluated in long double, so the result is as accurate as the power-of-two transform itself.
+void fft_any(std::vector<std::complex<double>>& a, bool inverse) {
+    const size_t n = a.size();
+    if (n <= 1) return;
+    if ((n & (n - 1)) == 0) {
+        fft_pow2(a, inverse);
+        return;
+    }
+    size_t m = 1;
+    while (m < 2 * n - 1) m <<= 1;
+    std::vector<std::complex<double>> chirp(n), A(m, std::complex<double>(0.0, 0.0)), B(m, std::complex<double>(0.0, 0.0));
+    const long double pi = 3.14159265358979323846264338327950288L;
+    for (size_t k = 0; k < n; ++k) {
+        const unsigned long long kk = (unsigned long long)(((unsigned __int128)k * k) % (2ULL * n));
+        const long double ang = (inverse ? 1.0L : -1.0L) * pi * (long double)kk / (long double)n;
+        chirp[k] = std::complex<double>((double)cosl(ang), (double)sinl(ang));  // exp(-+ j pi k^2 / n)
+    }
+    for (size_t k = 0; k < n; ++k) A[k] = a[k] * chirp[k];
+    B[0] = std::conj(chirp[0]);
+    for (size_t k = 1; k < n; ++k) B[k] = B[m - k] = std::conj(chirp[k]);
+    fft_pow2(A, false);
+    fft_pow2(B, false);
+    for (size_t k = 0; k < m; ++k) A[k] *= B[k];
+    fft_pow2(A, true);
+    const double inv_m = 1.0 / (double)m;
+    for (size_t k = 0; k < n; ++k) a[k] = A[k] * inv_m * chirp[k];
+}
+
 // src/blocks/filters.rs:184-238
 bool design_filter_response(const FreqResp& f, const WindowFn& w, double sample_rate, size_t n, bool as_f32,
                             std::vector<std::complex<double>>* out, std::vector<std::complex<double>>* taps) {
-    if (n < 2 || (n & (n - 1)) != 0) return false;
+    if (n < 1) return false;
     const double n_flt = (double)n;
     const double scale = 2.0 * n_flt * n_flt;  // :186
     std::vector<std::complex<double>> response(n, std::complex<double>(0.0, 0.0));
@@ -108,7 +138,7 @@ bool design_filter_response(const FreqResp& f, const WindowFn& w, double sample_
         response[i] = f((int64_t)i, freq) / scale;
         if (i > 0) response[n - i] = f(-(int64_t)i, -freq) / scale;
     }
-    fft_pow2(response, true);                                               // :200 (unnormalised inverse)
+    fft_any(response, true);                                                // :200 (unnormalised inverse)
     for (size_t i = 0; i < n / 2; ++i) std::swap(response[i], response[i + n / 2]);  // :201-203
     double energy_pre = 0.0, energy_post = 0.0;
     for (size_t i = 0; i < n; ++i) {  // :204-214
@@ -124,7 +154,7 @@ bool design_filter_response(const FreqResp& f, const WindowFn& w, double sample_
         else (*out)[n + i] = response[i];
     }
     if (taps) taps->assign(out->begin() + (long)n, out->end());
-    fft_pow2(*out, false);  // :227-238 (the reference runs this one in Flt; f64 here, rounded once by the caller)
+    fft_any(*out, false);  // :227-238 (the reference runs this one in Flt; f64 here, rounded once by the caller)
     return true;
 }
 

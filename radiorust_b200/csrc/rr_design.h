@@ -24,10 +24,12 @@ using WindowFn = std::function<double(double x)>;
 
 // In-place power-of-two complex FFT, unnormalised; inverse = conjugate kernel.
 void fft_pow2(std::vector<std::complex<double>>& a, bool inverse);
+// The same for any length (Bluestein on fft_pow2 when the length is not a power of two).
+void fft_any(std::vector<std::complex<double>>& a, bool inverse);
 
 // extended_response (2n bins).  `as_f32`: round the zero-padded impulse
 // response to f32 before the last FFT like the reference does for Flt = f32.
-// Returns false when n is not a power of two >= 2.
+// Any n >= 1.
 // `taps` (optional) receives the n windowed impulse-response values (already
 // rounded to Flt when as_f32): the filter is z[k] = sum_m taps[m] * x[k - m].
 bool design_filter_response(const FreqResp& f, const WindowFn& w, double sample_rate, size_t n, bool as_f32,

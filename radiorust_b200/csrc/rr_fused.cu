@@ -79,6 +79,22 @@ __device__ __forceinline__ void mb_wait(uint32_t bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// the same for waits that are expected to be long (a transform warp waiting for its block to be filled: ~60 % of its
+// time): the suspend-time hint lets the hardware park the warp instead of re-issuing the test (the retries of the plain
+// form were 7 % of all issued instructions and compete with the front-end warps of the same scheduler)
+__device__ __forceinline__ void mb_wait_long(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LWAIT_%=:\n"
+        "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra LDONE_%=;\n"
+        "bra LWAIT_%=;\n"
+        "LDONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity), "r"(20000u)
+        : "memory");
+}
 __device__ __forceinline__ pc f_lds(uint32_t addr) {
     pc r;
     asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(addr));
@@ -539,7 +555,7 @@ k_fused(const __grid_constant__ CUtensorMap tmap, const FusedArgs a, const int n
                 if (q < hist_rows_per_lane && r < Lmax) hreg[q] = __ldg(kin + ((long long)r * FRK) / 2 + warp);
             }
         }
-        mb_wait(bar_full + (uint32_t)(gb & 1) * 8, (uint32_t)((gb >> 1) & 1));
+        mb_wait_long(bar_full + (uint32_t)(gb & 1) * 8, (uint32_t)((gb >> 1) & 1));
         // rows [0, Lmax) of this warp's strip: from the previous push (b == 0) or from the previous block (keep buffer);
         // rows [V, V + Lmax) of the strip are the next block's
 #pragma unroll

@@ -82,6 +82,17 @@ cudaError_t launch_upsample(const void* in, long long in_stride, long long len, 
                             const T* ir, int L, RateState rate, long long n_out, void* out, long long out_stride,
                             int n_streams, cudaStream_t st);
 
+// The resamplers with their firing pattern from tables (rates that are not integer valued; the tables replay the
+// reference's f64 `pos` recurrence, resampling.rs:109-111 / :247-266): fire[o] = input sample of this push that output o
+// ends at; qpos[p] = output cell input p starts at, cnt[i] = inputs with qpos <= i
+template <typename T>
+cudaError_t launch_downsample_indexed(const void* in, long long in_stride, long long len, const void* tail_in, void* tail_out, const T* ir, int L,
+                                      const int* fire, long long n_out, void* out, long long out_stride, int n_streams, cudaStream_t st);
+template <typename T>
+cudaError_t launch_upsample_indexed(const void* in, long long in_stride, long long len, const void* acc_in, void* acc_out, const T* ir, int L,
+                                    const int* qpos, const int* cnt, long long n_out, void* out, long long out_stride, int n_streams,
+                                    cudaStream_t st);
+
 // FM discriminator (src/blocks/modulation.rs:116-126)
 template <typename T>
 cudaError_t launch_fmdemod(const void* in, long long in_stride, void* out, long long out_stride, long long len,

@@ -153,6 +153,35 @@ __global__ void __launch_bounds__(256) k_downsample(const cx<T>* __restrict__ in
     if (lane == 0) st_cx(&out[(long long)s * out_stride + o], cx<T>(ax, ay));
 }
 
+// The same with the firing instants from a table (rates that are not integer valued: the reference's f64 `pos`
+// recurrence, replayed on the host): output o ends at input sample fire[o] of this push.
+template <typename T>
+__global__ void __launch_bounds__(256) k_downsample_idx(const cx<T>* __restrict__ in, long long in_stride, const cx<T>* __restrict__ tail_in,
+                                                        const T* __restrict__ ir, int L, const int* __restrict__ fire, long long n_out,
+                                                        cx<T>* __restrict__ out, long long out_stride) {
+    const int s = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const long long o = (long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (o >= n_out) return;
+    const cx<T>* src = in + (long long)s * in_stride;
+    const cx<T>* tl = tail_in + (long long)s * (L - 1);
+    const long long first = (long long)fire[o] - L + 1;  // index (in this push) of the oldest window sample
+    T ax = (T)0, ay = (T)0;
+    for (int t = lane; t < L; t += 32) {
+        const long long idx = first + t;
+        const cx<T> z = (idx < 0) ? ld_cx(&tl[(L - 1) + idx]) : ld_cx(&src[idx]);
+        const T h = ir[t];
+        ax = fma(z.x, h, ax);
+        ay = fma(z.y, h, ay);
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        ax += __shfl_xor_sync(0xffffffffu, ax, d);
+        ay += __shfl_xor_sync(0xffffffffu, ay, d);
+    }
+    if (lane == 0) st_cx(&out[(long long)s * out_stride + o], cx<T>(ax, ay));
+}
+
 // new tail = last L-1 samples of [tail_in | input]
 template <typename T>
 __global__ void k_tail_update(const cx<T>* __restrict__ in, long long in_stride, long long len,
@@ -180,6 +209,22 @@ cudaError_t launch_downsample(const void* in, long long in_stride, long long len
         dim3 grid((unsigned)((L - 1 + 127) / 128), (unsigned)n_streams);
         k_tail_update<T><<<grid, 128, 0, st>>>(reinterpret_cast<const cx<T>*>(in), in_stride, len,
                                                reinterpret_cast<const cx<T>*>(tail_in),
+                                               reinterpret_cast<cx<T>*>(tail_out), L);
+    }
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_downsample_indexed(const void* in, long long in_stride, long long len, const void* tail_in, void* tail_out, const T* ir, int L,
+                                      const int* fire, long long n_out, void* out, long long out_stride, int n_streams, cudaStream_t st) {
+    if (n_out > 0) {
+        dim3 grid((unsigned)((n_out + 7) / 8), (unsigned)n_streams);
+        k_downsample_idx<T><<<grid, 256, 0, st>>>(reinterpret_cast<const cx<T>*>(in), in_stride, reinterpret_cast<const cx<T>*>(tail_in), ir, L, fire,
+                                                  n_out, reinterpret_cast<cx<T>*>(out), out_stride);
+    }
+    if (L > 1) {
+        dim3 grid((unsigned)((L - 1 + 127) / 128), (unsigned)n_streams);
+        k_tail_update<T><<<grid, 128, 0, st>>>(reinterpret_cast<const cx<T>*>(in), in_stride, len, reinterpret_cast<const cx<T>*>(tail_in),
                                                reinterpret_cast<cx<T>*>(tail_out), L);
     }
     return cudaGetLastError();
@@ -252,6 +297,43 @@ cudaError_t launch_upsample(const void* in, long long in_stride, long long len, 
     k_upsample<T><<<grid, 256, 0, st>>>(reinterpret_cast<const cx<T>*>(in), in_stride, len,
                                         reinterpret_cast<const cx<T>*>(acc_in), reinterpret_cast<cx<T>*>(acc_out), ir,
                                         L, rate, n_out, reinterpret_cast<cx<T>*>(out), out_stride);
+    return cudaGetLastError();
+}
+
+// The same with the input positions from tables (rates that are not integer valued): qpos[p] = output cell (relative
+// to this push's first output) that input p starts at, cnt[i] = number of inputs with qpos <= i.
+template <typename T>
+__global__ void __launch_bounds__(256) k_upsample_idx(const cx<T>* __restrict__ in, long long in_stride, const cx<T>* __restrict__ acc_in,
+                                                      cx<T>* __restrict__ acc_out, const T* __restrict__ ir, int L, const int* __restrict__ qpos,
+                                                      const int* __restrict__ cnt, long long n_out, cx<T>* __restrict__ out, long long out_stride) {
+    const int s = blockIdx.y;
+    const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n_out + L) return;
+    const cx<T>* src = in + (long long)s * in_stride;
+    cx<T> acc = (o < L) ? ld_cx(&acc_in[(long long)s * L + o]) : cx<T>((T)0, (T)0);
+    const int p_hi = cnt[o] - 1;
+    const int p_lo = (o - L >= 0) ? cnt[o - L] : 0;
+    for (int p = p_lo; p <= p_hi; ++p) {  // input order, like the ring (resampling.rs:239-246)
+        const int t = (int)(o - qpos[p]);
+        if (t >= 0 && t < L) {
+            const cx<T> x = ld_cx(&src[p]);
+            const T h = ir[t];
+            acc.x = fma(x.x, h, acc.x);
+            acc.y = fma(x.y, h, acc.y);
+        }
+    }
+    if (o < n_out) st_cx(&out[(long long)s * out_stride + o], acc);
+    else st_cx(&acc_out[(long long)s * L + (o - n_out)], acc);
+}
+template <typename T>
+cudaError_t launch_upsample_indexed(const void* in, long long in_stride, long long len, const void* acc_in, void* acc_out, const T* ir, int L,
+                                    const int* qpos, const int* cnt, long long n_out, void* out, long long out_stride, int n_streams,
+                                    cudaStream_t st) {
+    (void)len;
+    const long long total = n_out + L;
+    dim3 grid((unsigned)((total + 255) / 256), (unsigned)n_streams);
+    k_upsample_idx<T><<<grid, 256, 0, st>>>(reinterpret_cast<const cx<T>*>(in), in_stride, reinterpret_cast<const cx<T>*>(acc_in),
+                                            reinterpret_cast<cx<T>*>(acc_out), ir, L, qpos, cnt, n_out, reinterpret_cast<cx<T>*>(out), out_stride);
     return cudaGetLastError();
 }
 
@@ -345,6 +427,10 @@ cudaError_t launch_level(const void* in, long long in_stride, long long chunk_le
                                               RateState, long long, void*, long long, int, cudaStream_t);              \
     template cudaError_t launch_upsample<T>(const void*, long long, long long, const void*, void*, const T*, int,      \
                                             RateState, long long, void*, long long, int, cudaStream_t);                \
+    template cudaError_t launch_downsample_indexed<T>(const void*, long long, long long, const void*, void*, const T*, int, const int*, \
+                                                      long long, void*, long long, int, cudaStream_t);                 \
+    template cudaError_t launch_upsample_indexed<T>(const void*, long long, long long, const void*, void*, const T*, int, const int*,   \
+                                                    const int*, long long, void*, long long, int, cudaStream_t);       \
     template cudaError_t launch_fmdemod<T>(const void*, long long, void*, long long, long long, int, void*, void*,     \
                                            int, double, cudaStream_t);                                                 \
     template cudaError_t launch_level<T>(const void*, long long, long long, long long, int, double*, cudaStream_t);

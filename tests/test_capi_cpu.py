@@ -174,3 +174,20 @@ def test_fused_filter_rank_gives_up_on_wideband_filters(lib):
     # contract violations
     assert _fused_rank(lib, orc.lowpass(3000.0), 1_024_000.0, 4096, 48000.0, 6000.0, 2.0e-8, 10)[0] == _ffi.RR_ERR_UNSUPPORTED  # 64/3
     assert _fused_rank(lib, orc.lowpass(3000.0), 2_400_000.0, 4000, 48000.0, 6000.0, 2.0e-8, 10)[0] == _ffi.RR_ERR_INVALID
+
+
+@pytest.mark.parametrize("n", [3, 33, 1000, 4800])
+def test_filter_design_at_any_chunk_length(lib, n):
+    """filters.rs:200,227-228 plans every length: the host design (Bluestein on the power-of-two transform) against the oracle."""
+    f = orc.lowpass(5000.0)
+
+    def cb(_u, b, fr, re, im):
+        v = f(int(b), float(fr))
+        re[0], im[0] = v.real, v.imag
+
+    out = np.zeros(4 * n)
+    rc = lib.rr_design_filter_response(_ffi.FREQ_RESP_FN(cb), None, _ffi.RR_WINDOW_KAISER, math.sqrt(3.0), _ffi.WINDOW_FN(), None, 48000.0, n,
+                                       _ffi.RR_C64, out.ctypes.data_as(C.POINTER(C.c_double)))
+    assert rc == 0
+    want = orc.design_filter_response(f, orc.Kaiser.with_null_at_bin(2.0), 48000.0, n, "f64")
+    assert np.linalg.norm(out.view(np.complex128) - want) <= 1e-13 * np.linalg.norm(want)
