@@ -2308,8 +2308,9 @@ int rr_design_fused_rank(rr_freq_resp_fn f, void* f_user, int32_t window_kind, d
         return std::complex<double>(re, im);
     };
     std::vector<std::complex<double>> resp, taps;
+    if (!is_pow2(n)) return fail(RR_ERR_INVALID, "rr_design_fused_rank: the fused kernels run on power-of-two chunk lengths >= 2");
     if (!rr::design_filter_response(fr, make_window(window_kind, window_beta, w, w_user), sample_rate, n, true, &resp, &taps))
-        return fail(RR_ERR_INVALID, "rr_design_fused_rank: chunk length must be a power of two >= 2");
+        return fail(RR_ERR_INVALID, "rr_design_fused_rank: filter design failed");
     if (!integer_valued(sample_rate) || !integer_valued(output_rate) || output_rate <= 0.0 || sample_rate < output_rate)
         return fail(RR_ERR_INVALID, "rr_design_fused_rank: rates must be integer valued, input >= output > 0");
     const long long g = std::gcd((long long)sample_rate, (long long)output_rate);
