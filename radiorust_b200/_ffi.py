@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libradiorust_b200.so")
+# RR_LIB_PATH: load another build of the same library (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("RR_LIB_PATH") or os.path.join(HERE, "lib", "libradiorust_b200.so")
 
 RR_OK = 0
 RR_ERR_INVALID = -1

@@ -291,6 +291,7 @@ struct rr_chain {
     bool allow_front = true; // RR_DISABLE_FRONT=1: k_poly2 on all P branches instead of the rank-reduced front end
     bool allow_fused = true; // RR_DISABLE_FUSED=1: k_front + k_poly2 (u through HBM) instead of k_fused
     int fused_min_streams = -1;  // streams from which k_fused is used (default: two per SM; RR_FUSED_MIN_STREAMS)
+    long long fused_min_rows = 1;  // new rows (outputs) per stream and push from which k_fused is used (RR_FUSED_MIN_ROWS)
     // optional CUDA-event timing of the dominant kernel of a push (bench.py's roofline)
     bool timing = false;
     std::vector<cudaEvent_t> evs;  // pairs (start, stop), one per timed launch since rr_chain_set_timing
@@ -1348,7 +1349,7 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
                 // there are enough streams to give every SM whole streams; everything else takes k_front + k_poly2.
                 if (ds.poly2_valid && ds.front_valid && ds.fused_valid && c->allow_fused && tma_ok && ca == 0 && was_ucache_valid &&
                     c->allow_ucache && ds.ucache_ptr && Qq == 1 && m0 == 0 && a.J0 >= 0 && a.J0 < Pq && S >= c->fused_min_streams &&
-                    m_hi - m_lo + 1 >= std::max<long long>(ds.poly_Lmax, 2 * ds.poly2_V)) {
+                    m_hi - m_lo + 1 >= c->fused_min_rows && a.len >= 33 * Pq) {
                     constexpr int RK = 10;
                     const long long n_out = m_hi - m_lo + 1;
                     const long long Lh = ds.poly_Lmax;
@@ -2410,6 +2411,7 @@ int rr_chain_create(rr_ctx* ctx, const rr_chain_desc* desc, rr_chain** out) {
     if (const char* e = std::getenv("RR_DISABLE_FUSED")) c->allow_fused = !(e[0] == '1');
     c->fused_min_streams = 2 * ctx->sm_count;
     if (const char* e = std::getenv("RR_FUSED_MIN_STREAMS")) c->fused_min_streams = std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("RR_FUSED_MIN_ROWS")) c->fused_min_rows = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("RR_DISABLE_UCACHE")) c->allow_ucache = !(e[0] == '1');
     if (const char* e = std::getenv("RR_DISABLE_SAB")) c->allow_sab = !(e[0] == '1');
     if (const char* e = std::getenv("RR_BIG_OS_SCRATCH_MB")) c->big_os_scratch_bytes = (size_t)std::max(1, std::atoi(e)) << 20;

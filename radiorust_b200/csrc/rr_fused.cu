@@ -555,6 +555,16 @@ k_fused(const __grid_constant__ CUtensorMap tmap, const FusedArgs a, const int n
                 if (q < hist_rows_per_lane && r < Lmax) hreg[q] = __ldg(kin + ((long long)r * FRK) / 2 + warp);
             }
         }
+        if (b == 0 && n_out < Lmax) {
+            // a push with fewer new rows than the filter reaches back: the rows kept for the NEXT push are the tail of
+            // [this push's history rows | its new rows]; the history part moves over here (this warp's strip of it, read
+            // again: a cold path that must not lengthen the live range of the registers above), the new rows are written by
+            // the front-end warps
+            const float4* __restrict__ kin = reinterpret_cast<const float4*>(reinterpret_cast<const float2*>(a.ukeep_in) + (long long)s * a.ukeep_in_stride);
+            float4* __restrict__ kout = reinterpret_cast<float4*>(reinterpret_cast<float2*>(a.ukeep_out) + (long long)s * a.ukeep_out_stride);
+#pragma unroll 1
+            for (int r = n_out + lane; r < Lmax; r += 32) kout[((long long)(r - n_out) * FRK) / 2 + warp] = __ldg(kin + ((long long)r * FRK) / 2 + warp);
+        }
         mb_wait_long(bar_full + (uint32_t)(gb & 1) * 8, (uint32_t)((gb >> 1) & 1));
         // rows [0, Lmax) of this warp's strip: from the previous push (b == 0) or from the previous block (keep buffer);
         // rows [V, V + Lmax) of the strip are the next block's

@@ -252,7 +252,7 @@ struct FusedArgs {
     int coef_slot;         // constant-memory slot holding acoef ([P/2][2][10], as FrontArgs::acoef)
     int coef_off4;         // set by the launcher
     long long J0;          // 0 <= J0 < P
-    int n_out;             // new rows (= outputs) per stream, >= Lmax
+    int n_out;             // new rows (= outputs) per stream, >= 1
     int Lmax, V;           // reach of the low-rate filter, new rows per block (511 - Lmax)
     const void* ukeep_in;  // [S][ukeep_in_stride] complex: the Lmax rows of u preceding row 0, rows of 10
     long long ukeep_in_stride;

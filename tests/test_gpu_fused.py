@@ -44,7 +44,9 @@ def _run(ctx, stages, x, sr, n, pushes, shifts, env):
     return np.concatenate(parts, axis=1), plans
 
 
-@pytest.mark.parametrize("S,pushes", [(6, [3, 12, 12, 11, 14]), (3, [2, 25, 11]), (149, [3, 11, 11])])
+@pytest.mark.parametrize("S,pushes", [(6, [3, 12, 12, 11, 14]), (3, [2, 25, 11]), (149, [3, 11, 11]),
+                                      (5, [3, 1, 1, 1, 1, 2, 1, 1, 3, 1, 1, 1]),   # one chunk per message: fewer new rows than the filter reaches back
+                                      (4, [2, 1, 8, 1, 8])])
 def test_fused_matches_oracle_and_two_kernel_path(ctx, S, pushes):
     import radiorust_b200 as rr
 
