@@ -399,7 +399,10 @@ def run_cuda(args):
     ctx = rr.Context(local)
     stages = [rr.FreqShifter(0.0), rr.Filter.new(lowpass(CUTOFF)), rr.Downsampler(OUT_CHUNK, OUT_RATE, BANDWIDTH)]
     chain = rr.Chain(ctx, stages, "f32", n_streams=S)
-    chain.set_shifts(0, [stream_shift(rank * S + s) for s in range(S)])
+    from radiorust_b200 import sharding
+
+    g_lo, g_hi = sharding.weak_scaling_streams(rank, world, S)  # global stream ids of this rank (weak scaling)
+    chain.set_shifts(0, [stream_shift(g) for g in range(g_lo, g_hi)])
 
     gen = torch.Generator(device="cuda")
     gen.manual_seed(20260000 + 3 * 100000 + rank)
@@ -505,7 +508,7 @@ def run_cuda(args):
         ch_p2p = rr.Chain(ctx, stages, "f32", n_streams=S)
         ch_loc = rr.Chain(ctx, stages, "f32", n_streams=S)
         for chx in (ch_p2p, ch_loc):
-            chx.set_shifts(0, [stream_shift(rank * S + s) for s in range(S)])
+            chx.set_shifts(0, [stream_shift(g) for g in range(g_lo, g_hi)])
         y_loc = torch.zeros((S, cap, 2), device="cuda", dtype=torch.float32)
         for _ in range(3):
             ch_p2p.push_device(SAMPLE_RATE, CHUNK_LEN, C_, x.data_ptr(), length, my_out, cap, cap)
@@ -553,18 +556,19 @@ def run_cuda(args):
         del y_loc
 
         # ---- strong scaling: configs[2]'s 4096 streams in total, sharded over the ranks ------------------------
-        S_str = args.streams // world
-        if S_str >= 1:
+        s_lo, s_hi = sharding.stream_range(rank, world, args.streams)  # block partition of the 4096 streams
+        S_str = s_hi - s_lo
+        if args.streams >= world:
             ch_s = rr.Chain(ctx, stages, "f32", n_streams=S_str)
-            ch_s.set_shifts(0, [stream_shift(rank * S_str + s) for s in range(S_str)])
+            ch_s.set_shifts(0, [stream_shift(g) for g in range(s_lo, s_hi)])
             ch_s.push_device(SAMPLE_RATE, CHUNK_LEN, C_, x.data_ptr(), length, y.data_ptr(), cap, cap)
             dist.barrier()
             ms_s = _time_pushes(torch, ch_s, SAMPLE_RATE, CHUNK_LEN, C_, x.data_ptr(), length, y.data_ptr(), cap, args.steps, 3)
             t = torch.tensor([ms_s], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms_s = float(t.item())
-            strong = {"scaling": "strong", "streams_total": S_str * world, "streams_per_gpu": S_str, "ms_per_step": ms_s,
-                      "value": S_str * world * length / (ms_s * 1e-3) / 1e6, "unit": UNIT, "plan": ch_s.plan}
+            strong = {"scaling": "strong", "streams_total": args.streams, "streams_per_gpu": S_str, "ms_per_step": ms_s,
+                      "value": sharding.aggregate_throughput(args.streams * length, 1, ms_s * 1e-3) / 1e6, "unit": UNIT, "plan": ch_s.plan}
             ch_s.close()
 
     # ---- end to end: pinned host chunks in, host result out, through rr_chain_push ----
