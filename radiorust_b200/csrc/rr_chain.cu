@@ -1906,9 +1906,24 @@ int run_push(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_chunks,
                                                           (const T*)s.ir.p, s.h.r_L, rs, (long long)a.n_new, o, (long long)s.obuf_cap, S, st));
                     plan += "downsample";
                 } else {
-                    RR_TIMED_LAUNCH(c, "k_upsample", 1, rr::launch_upsample<T>(cur.p, cur.stride, len, s.tail[s.tail_cur].p, s.tail[s.tail_cur ^ 1].p,
-                                                        (const T*)s.ir.p, s.h.r_L, rs, (long long)a.n_new, o, (long long)s.obuf_cap, S, st));
+                    // last stage: whole output chunks go straight to the caller's buffer, the part behind them to the other
+                    // staging buffer (no copy of the new samples afterwards)
+                    const long long emit = (long long)a.out.len();
+                    bool direct = false;
+                    if (last && emit > 0 && emit >= (long long)a.pending_before && rr::upsample_tiled_supported<T>(rs, s.h.r_L)) {
+                        void* d1 = (char*)dev_out + a.pending_before * 2 * sizeof(T);
+                        RR_TIMED_LAUNCH(c, "k_upsample", 1, rr::launch_upsample<T>(cur.p, cur.stride, len, s.tail[s.tail_cur].p, s.tail[s.tail_cur ^ 1].p,
+                                                            (const T*)s.ir.p, s.h.r_L, rs, (long long)a.n_new, d1, (long long)out_stride, S, st,
+                                                            s.obuf[s.obuf_cur ^ 1].p, (long long)s.obuf_cap, emit - (long long)a.pending_before));
+                        direct = true;
+                    } else {
+                        RR_TIMED_LAUNCH(c, "k_upsample", 1, rr::launch_upsample<T>(cur.p, cur.stride, len, s.tail[s.tail_cur].p, s.tail[s.tail_cur ^ 1].p,
+                                                            (const T*)s.ir.p, s.h.r_L, rs, (long long)a.n_new, o, (long long)s.obuf_cap, S, st));
+                    }
                     plan += "upsample";
+                    s.tail_cur ^= 1;
+                    RR_TRY(resampler_emit<T>(c, s, a, last, dev_out, (long long)out_stride, &cur, direct));
+                    break;
                 }
                 s.tail_cur ^= 1;
                 RR_TRY(resampler_emit<T>(c, s, a, last, dev_out, (long long)out_stride, &cur));

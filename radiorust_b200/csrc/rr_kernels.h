@@ -77,10 +77,13 @@ cudaError_t launch_downsample(const void* in, long long in_stride, long long len
                               int n_streams, cudaStream_t st);
 
 // zero-stuffing interpolator, gather form (src/blocks/resampling.rs:238-267)
+// out2 (optional; integer interpolation factors only, see upsample_tiled_supported): outputs o >= out_split go to
+// out2[o - out_split] instead of out[o]
 template <typename T>
 cudaError_t launch_upsample(const void* in, long long in_stride, long long len, const void* acc_in, void* acc_out,
                             const T* ir, int L, RateState rate, long long n_out, void* out, long long out_stride,
-                            int n_streams, cudaStream_t st);
+                            int n_streams, cudaStream_t st, void* out2 = nullptr, long long out2_stride = 0, long long out_split = 0);
+template <typename T> bool upsample_tiled_supported(RateState rate, int L);
 
 // The resamplers with their firing pattern from tables (rates that are not integer valued; the tables replay the
 // reference's f64 `pos` recurrence, resampling.rs:109-111 / :247-266): fire[o] = input sample of this push that output o

@@ -288,10 +288,88 @@ __global__ void __launch_bounds__(256) k_upsample(const cx<T>* __restrict__ in, 
     else st_cx(&acc_out[(long long)s * L + (o - n_out)], acc);
 }
 
+// Integer interpolation factors (in/out = 1/Q, e.g. 48 kS/s -> 2.4 MS/s), tiled: a CTA takes UP_TILE consecutive outputs
+// of one stream, brings the inputs they depend on and the taps into shared memory once, and every thread then walks its
+// outputs' ~L/Q taps from there.  Same sums in the same order as k_upsample (inputs ascending, resampling.rs:239-246);
+// the general kernel spends most of its time on 64-bit index arithmetic and dependent global loads per tap.
+constexpr int UP_TILE = 2048;
+template <typename T>
+__global__ void __launch_bounds__(256) k_upsample_tiled(const cx<T>* __restrict__ in, long long in_stride, long long len,
+                                                        const cx<T>* __restrict__ acc_in, cx<T>* __restrict__ acc_out,
+                                                        const T* __restrict__ ir, int L, int Q, long long j0, long long m0, long long n_out,
+                                                        cx<T>* __restrict__ out, long long out_stride, int x_cap, cx<T>* __restrict__ out2,
+                                                        long long out2_stride, long long out_split) {
+    extern __shared__ __align__(16) unsigned char up_smem[];
+    T* irs = reinterpret_cast<T*>(up_smem);                                   // [L]
+    cx<T>* xs = reinterpret_cast<cx<T>*>(irs + ((L + 1) & ~1));                // [x_cap]
+    const int s = blockIdx.y;
+    const long long o0 = (long long)blockIdx.x * UP_TILE;
+    const long long total = n_out + L;
+    const long long o1 = min(o0 + UP_TILE, total);
+    const cx<T>* src = in + (long long)s * in_stride;
+    // inputs (global index p) that reach outputs [o0, o1): q_p = p*Q in (q - L, q]
+    const long long q_first = m0 + o0, q_last = m0 + o1 - 1;
+    long long p_lo = (q_first - L < 0) ? 0 : (q_first - L) / Q + 1;
+    long long p_hi = q_last / Q;
+    if (p_lo < j0) p_lo = j0;
+    if (p_hi > j0 + len - 1) p_hi = j0 + len - 1;
+    const int n_x = (int)max(0LL, p_hi - p_lo + 1);
+    for (int i = threadIdx.x; i < L; i += blockDim.x) irs[i] = ir[i];
+    for (int i = threadIdx.x; i < n_x; i += blockDim.x) xs[i] = ld_cx(&src[p_lo - j0 + i]);
+    __syncthreads();
+    for (long long o = o0 + threadIdx.x; o < o1; o += blockDim.x) {
+        const long long q = m0 + o;
+        cx<T> acc = (o < L) ? ld_cx(&acc_in[(long long)s * L + o]) : cx<T>((T)0, (T)0);
+        long long a_lo = (q - L < 0) ? 0 : (q - L) / Q + 1, a_hi = q / Q;
+        if (a_lo < p_lo) a_lo = p_lo;
+        if (a_hi > p_hi) a_hi = p_hi;
+        int t = (int)(q - a_lo * Q);       // tap of input a_lo, decreasing by Q per input
+        int xi = (int)(a_lo - p_lo);
+        for (long long p = a_lo; p <= a_hi; ++p, t -= Q, ++xi) {
+            if (t >= 0 && t < L) {
+                const cx<T> x = xs[xi];
+                const T h = irs[t];
+                acc.x = fma(x.x, h, acc.x);
+                acc.y = fma(x.y, h, acc.y);
+            }
+        }
+        if (o < n_out) {
+            // optional second destination: outputs from out_split on belong behind the last whole output chunk
+            if (out2 != nullptr && o >= out_split) st_cx(&out2[(long long)s * out2_stride + (o - out_split)], acc);
+            else st_cx(&out[(long long)s * out_stride + o], acc);
+        } else {
+            st_cx(&acc_out[(long long)s * L + (o - n_out)], acc);
+        }
+    }
+}
+
+template <typename T> bool upsample_tiled_supported(RateState rate, int L) {
+    if (!(rate.P == 1 && rate.Q >= 1 && rate.Q < (1LL << 30) && L <= 8192)) return false;
+    const int x_cap = (int)(UP_TILE / rate.Q + L / rate.Q + 4);
+    return (size_t)((L + 1) & ~1) * sizeof(T) + (size_t)x_cap * 2 * sizeof(T) <= 200 * 1024;
+}
+
 template <typename T>
 cudaError_t launch_upsample(const void* in, long long in_stride, long long len, const void* acc_in, void* acc_out,
                             const T* ir, int L, RateState rate, long long n_out, void* out, long long out_stride,
-                            int n_streams, cudaStream_t st) {
+                            int n_streams, cudaStream_t st, void* out2, long long out2_stride, long long out_split) {
+    if (rate.P == 1 && rate.Q >= 1 && rate.Q < (1LL << 30) && L <= 8192) {
+        // inputs per tile: at most UP_TILE / Q + L / Q + 2
+        const int x_cap = (int)(UP_TILE / rate.Q + L / rate.Q + 4);
+        const size_t smem = (size_t)((L + 1) & ~1) * sizeof(T) + (size_t)x_cap * 2 * sizeof(T);
+        if (smem <= 200 * 1024) {
+            const long long total = n_out + L;
+            auto k = k_upsample_tiled<T>;
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            dim3 grid((unsigned)((total + UP_TILE - 1) / UP_TILE), (unsigned)n_streams);
+            k<<<grid, 256, smem, st>>>(reinterpret_cast<const cx<T>*>(in), in_stride, len, reinterpret_cast<const cx<T>*>(acc_in),
+                                       reinterpret_cast<cx<T>*>(acc_out), ir, L, (int)rate.Q, rate.j0, rate.m0, n_out,
+                                       reinterpret_cast<cx<T>*>(out), out_stride, x_cap, reinterpret_cast<cx<T>*>(out2), out2_stride, out_split);
+            return cudaGetLastError();
+        }
+    }
+    if (out2 != nullptr) return cudaErrorInvalidValue;  // the split destination is the tiled kernel's (callers check upsample_tiled_supported)
     const long long total = n_out + L;
     dim3 grid((unsigned)((total + 255) / 256), (unsigned)n_streams);
     k_upsample<T><<<grid, 256, 0, st>>>(reinterpret_cast<const cx<T>*>(in), in_stride, len,
@@ -426,7 +504,8 @@ cudaError_t launch_level(const void* in, long long in_stride, long long chunk_le
     template cudaError_t launch_downsample<T>(const void*, long long, long long, const void*, void*, const T*, int,    \
                                               RateState, long long, void*, long long, int, cudaStream_t);              \
     template cudaError_t launch_upsample<T>(const void*, long long, long long, const void*, void*, const T*, int,      \
-                                            RateState, long long, void*, long long, int, cudaStream_t);                \
+                                            RateState, long long, void*, long long, int, cudaStream_t, void*, long long, long long); \
+    template bool upsample_tiled_supported<T>(RateState, int);                                                         \
     template cudaError_t launch_downsample_indexed<T>(const void*, long long, long long, const void*, void*, const T*, int, const int*, \
                                                       long long, void*, long long, int, cudaStream_t);                 \
     template cudaError_t launch_upsample_indexed<T>(const void*, long long, long long, const void*, void*, const T*, int, const int*,   \
