@@ -730,11 +730,14 @@ cudaError_t launch_cfg(int n_streams, const FusedArgs& a, const CUtensorMap& tm,
     if (smem > (size_t)227 * 1024) return cudaErrorInvalidConfiguration;
     const int grid = std::min(n_streams, sm_count);
     void (*kern)(const CUtensorMap, const FusedArgs, const int);
-    // decimation factors with an unrolled front end (2.4 MS/s -> 48 kS/s and other common SDR ratios); any other even P
-    // takes the run-time loop
+    // one instantiation per decimation factor: the front end's step loop must be unrolled completely for its coefficient
+    // loads to go through the uniform datapath (with a run-time loop they are vector LDC loads and the kernel is slower
+    // than k_front + k_poly2).  Common SDR ratios: 2.4 MS/s, 1.92 MS/s, 960 kS/s -> 48 kS/s.
     switch (a.P) {
         case 50: kern = a.nco ? k_fused<FW, D, NB, true, 50> : k_fused<FW, D, NB, false, 50>; break;
-        default: kern = a.nco ? k_fused<FW, D, NB, true, 0> : k_fused<FW, D, NB, false, 0>; break;
+        case 40: kern = a.nco ? k_fused<FW, D, NB, true, 40> : k_fused<FW, D, NB, false, 40>; break;
+        case 20: kern = a.nco ? k_fused<FW, D, NB, true, 20> : k_fused<FW, D, NB, false, 20>; break;
+        default: return cudaErrorNotSupported;
     }
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -758,7 +761,7 @@ cudaError_t launch_cfg(int n_streams, const FusedArgs& a, const CUtensorMap& tm,
 int fused_coef_slots() { return kFusedSlots; }
 
 bool fused_supported(int rank_pad, long long P, int Lmax) {
-    if (rank_pad != FRK || P < 4 || P > 254 || (P % 2) != 0 || fused_encode_fn() == nullptr) return false;
+    if (rank_pad != FRK || !(P == 50 || P == 40 || P == 20) || fused_encode_fn() == nullptr) return false;  // launch_cfg's instantiations
     if (Lmax < 1 || FK - 1 - Lmax < 128 || Lmax > 383) return false;
     if ((P / 2) * 2 * FRK > kFusedSlotFloats) return false;
     return fused_smem<7, 2, 5>((int)P, Lmax) <= (size_t)227 * 1024;
@@ -789,15 +792,14 @@ cudaError_t launch_fused(int n_streams, const FusedArgs& a0, int sm_count, cudaS
                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
     // configuration <front-end warps, ring depth, parked spectra>: seven front-end warps fill the register file next to the five
-    // transform warps (12 warps x 168 registers) and were the fastest measured (RR_FUSED_CFG=1|2 picks the others)
+    // transform warps (12 warps x 168 registers) and were the fastest measured (RR_FUSED_CFG=1: six front-end warps, eight parked spectra)
     static int cfg = -1;
     if (cfg < 0) {
         cfg = 0;
         if (const char* e = std::getenv("RR_FUSED_CFG")) cfg = std::atoi(e);
     }
     switch (cfg) {
-        case 1: return launch_cfg<4, 3, 10>(n_streams, a, tm, sm_count, st);
-        case 2: return launch_cfg<6, 2, 8>(n_streams, a, tm, sm_count, st);
+        case 1: return launch_cfg<6, 2, 8>(n_streams, a, tm, sm_count, st);
         default: return launch_cfg<7, 2, 5>(n_streams, a, tm, sm_count, st);
     }
 }

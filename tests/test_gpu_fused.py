@@ -130,3 +130,29 @@ def test_fused_then_event_then_short_pushes(ctx):
         w = np.concatenate(want[s])
         assert w.shape == g[s].shape
         assert orc.rel_l2(g[s], w) <= 1e-5
+
+
+@pytest.mark.parametrize("sr,n,out_rate,bw,ocl", [
+    (960_000.0, 2048, 48000.0, 20000.0, 17),      # P = 20
+    (1_920_000.0, 4096, 48000.0, 6000.0, 64),     # P = 40 (an even number of 16-byte units per half row: padded slots)
+    (2_400_000.0, 8192, 48000.0, 6000.0, 64),     # P = 50, longer Filter: Lmax = 170
+    (2_400_000.0, 2048, 48000.0, 20000.0, 100),   # P = 50, wider Downsampler (rank permitting)
+    (3_072_000.0, 4096, 48000.0, 6000.0, 64),     # P = 64: no instantiation, k_front + k_poly2
+    (4_800_000.0, 4096, 48000.0, 6000.0, 64),     # P = 100
+])
+def test_fused_other_decimation_factors_and_filter_lengths(ctx, sr, n, out_rate, bw, ocl):
+    import radiorust_b200 as rr
+
+    S = 3
+    pushes = [3, 14, 13]
+    x = np.stack([orc.synth_noise(6100 + s, sum(pushes) * n, "f32") for s in range(S)])
+    shifts = [sr / 7.0, -sr / 5.0, 12345.0]
+    stages = [rr.FreqShifter(0.0), rr.Filter.new(orc.lowpass(bw / 2)), rr.Downsampler(ocl, out_rate, bw)]
+    got, plans = _run(ctx, stages, x, sr, n, pushes, shifts, {"RR_FUSED_MIN_STREAMS": "1"})
+    for s in range(S):
+        want = orc.Chain([orc.FreqShifter("f32", 1.0, shifts[s]), orc.Filter.new("f32", orc.lowpass(bw / 2)),
+                          orc.Downsampler("f32", ocl, out_rate, bw)]).run(sr, x[s], n)
+        assert want.shape == got[s].shape
+        assert orc.rel_l2(got[s], want) <= 1e-5, (s, plans)
+    # (a filter that does not factor to rank 10 keeps the polyphase kernels on all branches: still correct, reported here)
+    print(sr, n, plans[-1])
