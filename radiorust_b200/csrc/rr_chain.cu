@@ -2633,8 +2633,11 @@ int rr_chain_push(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_ch
     RR_TRY(c->stage_out[b].ensure(S * ocap * c->esz));
     // H2D of this push: behind the kernels of the push before last, which read the same slot
     RR_CUDA(cudaStreamWaitEvent(c->h2d_stream, c->ev_comp[b], 0));
-    RR_CUDA(cudaMemcpy2DAsync(c->stage_in[b].p, len * c->esz, host_in, in_stride * c->esz, len * c->esz, S, cudaMemcpyHostToDevice,
-                              c->h2d_stream));
+    if (in_stride == len || S == 1)  // contiguous: one linear copy
+        RR_CUDA(cudaMemcpyAsync(c->stage_in[b].p, host_in, S * len * c->esz, cudaMemcpyHostToDevice, c->h2d_stream));
+    else
+        RR_CUDA(cudaMemcpy2DAsync(c->stage_in[b].p, len * c->esz, host_in, in_stride * c->esz, len * c->esz, S, cudaMemcpyHostToDevice,
+                                  c->h2d_stream));
     RR_CUDA(cudaEventRecord(c->ev_h2d[b], c->h2d_stream));
     // kernels: behind that copy and behind the D2H copy that still reads this slot's output
     RR_CUDA(cudaStreamWaitEvent(c->stream, c->ev_h2d[b], 0));
@@ -2645,8 +2648,11 @@ int rr_chain_push(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_ch
     RR_CUDA(cudaEventRecord(c->ev_comp[b], c->stream));
     if (produced > 0) {
         RR_CUDA(cudaStreamWaitEvent(c->d2h_stream, c->ev_comp[b], 0));
-        RR_CUDA(cudaMemcpy2DAsync(host_out, out_stride * c->esz, c->stage_out[b].p, ocap * c->esz, produced * c->esz, S,
-                                  cudaMemcpyDeviceToHost, c->d2h_stream));
+        if ((out_stride == ocap && produced == ocap) || S == 1)
+            RR_CUDA(cudaMemcpyAsync(host_out, c->stage_out[b].p, (S == 1 ? produced : S * ocap) * c->esz, cudaMemcpyDeviceToHost, c->d2h_stream));
+        else
+            RR_CUDA(cudaMemcpy2DAsync(host_out, out_stride * c->esz, c->stage_out[b].p, ocap * c->esz, produced * c->esz, S,
+                                      cudaMemcpyDeviceToHost, c->d2h_stream));
         RR_CUDA(cudaEventRecord(c->ev_d2h[b], c->d2h_stream));
     }
     c->slot ^= 1;
