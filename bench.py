@@ -540,6 +540,47 @@ def run_cuda(args):
                          for r in range(world))
             del host
         dist.barrier()
+        # (c) the same gather by copy engine: outputs stay local (two buffers), and a device-to-device copy on the chain's
+        # copy stream moves each push's outputs into rank 0's buffer while the next push computes
+        ys2 = [y_loc, torch.zeros_like(y_loc)]
+        ch_ce = rr.Chain(ctx, stages, "f32", n_streams=S)
+        ch_ce.set_shifts(0, [stream_shift(g) for g in range(g_lo, g_hi)])
+
+        def ce_steps(k):
+            ext2 = torch.cuda.ExternalStream(ch_ce.cuda_stream)
+            e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(ext2):
+                e_a.record(ext2)
+            last = 0
+            for i in range(k):
+                yy = ys2[i & 1]
+                cnt_i, _ = ch_ce.push_device(SAMPLE_RATE, CHUNK_LEN, C_, x.data_ptr(), length, yy.data_ptr(), cap, cap)
+                ch_ce.copy_out_async(my_out, cap, yy.data_ptr(), cap, cnt_i)
+                last = cnt_i
+            with torch.cuda.stream(ext2):
+                e_b.record(ext2)
+            t0 = time.perf_counter()
+            ch_ce.sync()
+            torch.cuda.synchronize()
+            return e_a.elapsed_time(e_b) / k, last
+
+        for _ in range(2):
+            ce_steps(2)
+        dist.barrier()
+        t_w0 = time.perf_counter()
+        ms_ce_dev, cnt_ce = ce_steps(args.steps)
+        ms_ce = (time.perf_counter() - t_w0) * 1e3 / args.steps  # host clock: includes the last copy
+        t = torch.tensor([ms_ce, ms_ce_dev], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_ce, ms_ce_dev = float(t[0].item()), float(t[1].item())
+        ch_ce.close()
+        gather["copy_engine_into_root"] = {
+            "what": "outputs stay local (two buffers); rr_chain_copy_out_async moves each push's outputs into rank 0's buffer on the "
+                    "chain's copy stream (copy engine over NVLink) under the next push's kernels",
+            "ms_per_step": ms_ce, "ms_per_step_kernels_only": ms_ce_dev, "ms_per_step_local_output": ms_loc,
+            "overhead_frac": ms_ce / ms_loc - 1.0, "value": S * length * world / (ms_ce * 1e-3) / 1e6, "unit": UNIT,
+        }
+        del ys2
         gather["p2p_store_into_root"] = {
             "what": "every rank's last kernel stores its outputs into rank 0's buffer (CUDA IPC mapping, NVLink peer stores)",
             "ms_per_step": ms_p2p, "ms_per_step_local_output": ms_loc, "overhead_frac": ms_p2p / ms_loc - 1.0,
@@ -553,7 +594,6 @@ def run_cuda(args):
         dist.barrier()
         if rank == 0:
             lib.rr_device_free(ctx._h, root_ptr)
-        del y_loc
 
         # ---- strong scaling: configs[2]'s 4096 streams in total, sharded over the ranks ------------------------
         s_lo, s_hi = sharding.stream_range(rank, world, args.streams)  # block partition of the 4096 streams

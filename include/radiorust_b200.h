@@ -265,6 +265,11 @@ int rr_chain_push_device(rr_chain* chain, double sample_rate, size_t chunk_len, 
                          size_t in_stride, void* dev_out, size_t out_capacity, size_t out_stride, size_t* out_count,
                          double* out_sample_rate);
 int rr_chain_sync(rr_chain* chain);
+/* Copy `n_samples` samples per stream from one device buffer to another (a buffer of another GPU opened with rr_ipc_open,
+ * for example) on the chain's copy stream -- a copy engine, no SM -- behind everything queued on the chain so far: a
+ * push's outputs travel to the gathering GPU while the next push computes.  Keep src_dev untouched until the copy has
+ * run (alternate between two output buffers); rr_chain_sync waits for it. */
+int rr_chain_copy_out_async(rr_chain* chain, void* dst_dev, size_t dst_stride, const void* src_dev, size_t src_stride, size_t n_samples);
 /* The fused Filter -> Downsampler kernels (rank-reduced front end + low-rate
  * polyphase part, or the polyphase kernels on all P branches) are used whenever
  * the chain allows it; enable = 0 forces the stateful overlap-save path (same

@@ -396,6 +396,10 @@ class Chain:
         )
         return cnt.value, rate.value
 
+    def copy_out_async(self, dst_dev: int, dst_stride: int, src_dev: int, src_stride: int, n_samples: int):
+        """``rr_chain_copy_out_async``: copy-engine copy of a push's outputs (raw device pointers), behind the queued work."""
+        check(self._lib.rr_chain_copy_out_async(self._h, dst_dev, dst_stride, src_dev, src_stride, n_samples))
+
     def sync(self):
         check(self._lib.rr_chain_sync(self._h))
 

@@ -279,6 +279,7 @@ struct rr_chain {
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     DevBuf stage_in[2], stage_out[2];
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+    cudaEvent_t ev_copy = nullptr;
     int slot = 0;
     std::string plan;
     uint64_t samples_lost = 0;  // SamplesLost events generated by Rechunker / Overlapper stages
@@ -2457,6 +2458,7 @@ int rr_chain_destroy(rr_chain* c) {
         if (c->ev_d2h[k]) cudaEventDestroy(c->ev_d2h[k]);
     }
     for (cudaEvent_t e : c->evs) cudaEventDestroy(e);
+    if (c->ev_copy) cudaEventDestroy(c->ev_copy);
     if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -2657,6 +2659,30 @@ int rr_chain_push(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_ch
     }
     c->slot ^= 1;
     if (out_count) *out_count = produced;
+    return RR_OK;
+}
+
+// Device-to-device copy of `n_samples` samples per stream on the chain's copy stream (copy engine, no SM), ordered
+// behind everything queued on the chain so far: moves a push's outputs into a buffer of another GPU (rr_ipc_open)
+// while the next push computes.  The caller keeps `src_dev` untouched until the copy has run (two output buffers).
+int rr_chain_copy_out_async(rr_chain* c, void* dst_dev, size_t dst_stride, const void* src_dev, size_t src_stride, size_t n_samples) {
+    if (!c || (!dst_dev && n_samples) || (!src_dev && n_samples)) return fail(RR_ERR_INVALID, "rr_chain_copy_out_async: null argument");
+    if (n_samples == 0) return RR_OK;
+    RR_CUDA(cudaSetDevice(c->ctx->device));
+    if (!c->d2h_stream) {
+        RR_CUDA(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+        RR_CUDA(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            RR_CUDA(cudaEventCreateWithFlags(&c->ev_h2d[k], cudaEventDisableTiming));
+            RR_CUDA(cudaEventCreateWithFlags(&c->ev_comp[k], cudaEventDisableTiming));
+            RR_CUDA(cudaEventCreateWithFlags(&c->ev_d2h[k], cudaEventDisableTiming));
+        }
+    }
+    if (!c->ev_copy) RR_CUDA(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
+    RR_CUDA(cudaEventRecord(c->ev_copy, c->stream));
+    RR_CUDA(cudaStreamWaitEvent(c->d2h_stream, c->ev_copy, 0));
+    RR_CUDA(cudaMemcpy2DAsync(dst_dev, dst_stride * c->esz, src_dev, src_stride * c->esz, n_samples * c->esz, (size_t)c->S, cudaMemcpyDeviceToDevice,
+                              c->d2h_stream));
     return RR_OK;
 }
 
