@@ -113,6 +113,15 @@ __device__ __forceinline__ void f_ldg2(const float4* p, pc& a, pc& b) {
     asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(b.x), "=f"(b.y) : "l"(p));
 }
 
+// exp(j * sign * 2*pi * (numer*d mod denom) / denom), the phase advance over d samples: rr_poly.cuh's nco_rotation (same
+// integer phase, same double-precision evaluation) without its 64-bit divisions; inv_m = 1 / denom
+__device__ __forceinline__ pc f_rotation(uint32_t d, uint32_t numer_abs, uint32_t denom, double inv_m, int sign) {
+    const uint32_t r = mulmod_fast(numer_abs, d % denom, denom, inv_m);
+    double s, c;
+    sincospi(2.0 * (double)r / (double)denom, &s, &c);
+    return pc((float)c, (float)(sign < 0 ? -s : s));
+}
+
 // pass 1 of the 512-point transform of this thread's 32 inputs (rows t + 16*i1), as in rr_poly2.cu
 __device__ __forceinline__ void f_pass1_store(pc (&v)[32], uint32_t tw_row, uint32_t xch_wr) {
     pdft_regs<32, +1>(v);
@@ -201,6 +210,7 @@ k_fused(const __grid_constant__ CUtensorMap tmap, const FusedArgs a, const int n
     unsigned char* const p_colph = p_ring + (size_t)FW * D * geo.slot_stride;
     unsigned char* const p_bar = p_colph + (((size_t)FW * P * 8 + 127) / 128 * 128);
     const uint32_t bar_full = s_u32(p_bar), bar_empty = bar_full + 16, bar_ring = bar_full + 32;
+    const uint32_t left_cnt = bar_ring + FW * D * 8;  // per stage: transform warps that have left it (two 32-bit counters)
 
     // ---- one-time set-up: zero the stages (stale rows must be finite), twiddles, barriers ----------------------
     for (int e = threadIdx.x; e < 2 * STAGE_BYTES / 16; e += blockDim.x) reinterpret_cast<float4*>(p_stage)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -220,6 +230,7 @@ k_fused(const __grid_constant__ CUtensorMap tmap, const FusedArgs a, const int n
         mb_init(bar_empty, T_WARPS);
         mb_init(bar_empty + 8, T_WARPS);
         for (int q = 0; q < FW * D; ++q) mb_init(bar_ring + q * 8, 1);
+        asm volatile("st.shared.v2.u32 [%0], {%1, %1};" ::"r"(left_cnt), "r"(0u) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -241,25 +252,33 @@ k_fused(const __grid_constant__ CUtensorMap tmap, const FusedArgs a, const int n
         const int J0 = (int)a.J0;
         const int hist_len = (int)(2 * a.n);
         const int hist_from = (int)a.hist_from;
-        const int tiles_w = fw < n_tiles ? (n_tiles - fw + FW - 1) / FW : 0;  // tiles of this warp per stream
+        // Tile j of the CTA's stream number so belongs to warp (j + so * n_live) mod FW, n_live = the tiles with a valid row:
+        // the live tiles of consecutive streams go round the warps without a gap.  (A one-chunk push has three live tiles
+        // per stream: without the rotation three of the warps would do all the work.)
+        const int n_live = (n_out + F_ROWS - 1) / F_ROWS;
+        const int rot_step = n_live % FW;
+        auto tiles_from = [&](int j0) { return j0 < n_tiles ? (n_tiles - j0 + FW - 1) / FW : 0; };  // tiles j0, j0 + FW, ... below n_tiles
         const int BV = B * V;
         const int tile_step = FW * F_ROWS;  // rows between consecutive tiles of this warp
 
         // ---- issue side: (stream ordinal, tile, half) of the next copy, its ring slot ------------------------------
         int i_so = 0, i_k = 0, i_half = 0, i_slot = 0;
+        int i_j0 = fw, i_rot = 0, i_tw = tiles_from(fw);  // first tile, rotation and tile count of this warp in stream i_so
         auto issue_next = [&]() {
             // advance to the next item that has a copy (tiles with no valid row have none) and start it
             while (i_so < n_my) {
-                if (i_k >= tiles_w) {  // (only when tiles_w == 0)
-                    i_so = n_my;
-                    break;
-                }
-                const int j = fw + i_k * FW, half = i_half, so = i_so;
-                i_half ^= 1;
-                if (i_half == 0 && ++i_k == tiles_w) {
-                    i_k = 0;
+                if (i_k >= i_tw) {  // on to the next stream
                     ++i_so;
+                    i_k = 0;
+                    i_rot += rot_step;
+                    if (i_rot >= FW) i_rot -= FW;
+                    i_j0 = fw - i_rot + (fw < i_rot ? FW : 0);
+                    i_tw = tiles_from(i_j0);
+                    continue;
                 }
+                const int j = i_j0 + i_k * FW, half = i_half, so = i_so;
+                i_half ^= 1;
+                if (i_half == 0) ++i_k;
                 const int rows_ok = min(F_ROWS, n_out - j * F_ROWS);
                 if (rows_ok <= 0) continue;
                 const int pos0 = j * (F_ROWS * P) - J0;
@@ -301,27 +320,34 @@ k_fused(const __grid_constant__ CUtensorMap tmap, const FusedArgs a, const int n
             if (gb_done > gb_arr) gb_arr = gb_done;
         };
 
+        int rot = 0;  // so * n_live mod FW
 #pragma unroll 1
         for (int so = 0; so < n_my; ++so) {
+            PROF(const long long pst0 = clock64();)
             const int s = (int)blockIdx.x + so * (int)gridDim.x;
             const int gb0 = so * B;  // global index of this stream's block 0
+            const int j0 = fw - rot + (fw < rot ? FW : 0);  // this warp's first tile of the stream
+            const int tiles_w = tiles_from(j0);
+            rot += rot_step;
+            if (rot >= FW) rot -= FW;
             // ---- per-stream NCO constants -------------------------------------------------------------
             uint32_t denom = 1, numer_abs = 0, idx0 = 0;
             int sign = 0;
             float start = 0.f;
             pc rot_tile(1.f, 0.f);
-            if (HAS_NCO) {
+            double inv_denom = 1.0;
+            if (HAS_NCO && j0 < n_live) {  // (a warp without a live tile in this stream needs none of it)
                 const NcoStream ns = a.nco[s];
                 denom = ns.denom;
                 numer_abs = ns.numer_abs;
                 sign = ns.sign;
                 idx0 = ns.idx;
                 start = (float)ns.start_phase;
-                const cx<float> r = nco_rotation<float>((long long)tile_step * P, numer_abs, denom, sign);
-                rot_tile = pc(r.x, r.y);
+                inv_denom = 1.0 / (double)denom;
+                rot_tile = f_rotation((uint32_t)(tile_step * P), numer_abs, denom, inv_denom, sign);
                 __syncwarp();  // the previous stream's column phasors are no longer read
                 for (int p = lane; p < P; p += 32) {
-                    const cx<float> c = nco_rotation<float>(p, numer_abs, denom, sign);
+                    const pc c = f_rotation((uint32_t)p, numer_abs, denom, inv_denom, sign);
                     colph[p] = make_float2(c.x, c.y);
                 }
                 __syncwarp();
@@ -333,12 +359,13 @@ k_fused(const __grid_constant__ CUtensorMap tmap, const FusedArgs a, const int n
             const float4* cf_base = c_fcoef + a.coef_off4;
             const float4* __restrict__ crow = reinterpret_cast<const float4*>(colph);
 
+            PROF(pr[7] += clock64() - pst0;)
             // block and offset within the block of the tile's first row
-            int blk = (fw * F_ROWS) / V, off = (fw * F_ROWS) - blk * V;
+            int blk = (j0 * F_ROWS) / V, off = (j0 * F_ROWS) - blk * V;
             pc rowph(1.f, 0.f);
 #pragma unroll 1
             for (int k = 0; k < tiles_w; ++k) {
-                const int r0 = (fw + k * FW) * F_ROWS;  // first row of the tile
+                const int r0 = (j0 + k * FW) * F_ROWS;  // first row of the tile
                 const int row = r0 + lane;              // this lane's row
                 const int pos0 = r0 * P - J0;
                 pc acc[FRK];
@@ -348,9 +375,12 @@ k_fused(const __grid_constant__ CUtensorMap tmap, const FusedArgs a, const int n
                 if (r0 < n_out) {
                     if (HAS_NCO) {
                         if ((k & 15) == 0) {
-                            long long kk = ((long long)idx0 + pos0 + (long long)lane * P) % (long long)denom;
+                            // table index (idx0 + offset of the row) mod denom, without a 64-bit division
+                            const long long v = (long long)idx0 + pos0 + (long long)lane * P;
+                            long long kk = v - (long long)floor((double)v * inv_denom) * (long long)denom;
                             if (kk < 0) kk += denom;
-                            const cx<float> c = nco_phasor<float>(mulmod_u32(numer_abs, (uint32_t)kk, denom), denom, sign, start);
+                            else if (kk >= (long long)denom) kk -= denom;
+                            const cx<float> c = nco_phasor<float>(mulmod_fast(numer_abs, (uint32_t)kk, denom, inv_denom), denom, sign, start);
                             rowph = pc(c.x, c.y);
                         } else {
                             rowph = pcmul(rowph, rot_tile);
@@ -509,7 +539,8 @@ k_fused(const __grid_constant__ CUtensorMap tmap, const FusedArgs a, const int n
         }
         PROF(if (fw == 0 && lane == 0) {
             for (int q = 0; q < 7; ++q) g_fused_prof[blockIdx.x * 16 + q] = pr[q];
-            g_fused_prof[blockIdx.x * 16 + 7] = clock64() - pr_t0;
+            g_fused_prof[blockIdx.x * 16 + 7] = pr[7];
+            g_fused_prof[blockIdx.x * 16 + 8] = clock64() - pr_t0;
         })
         return;
     }
@@ -532,9 +563,27 @@ k_fused(const __grid_constant__ CUtensorMap tmap, const FusedArgs a, const int n
     const int hist_rows_per_lane = (Lmax + 31) / 32;  // <= 12 (Lmax <= 383)
 
     const int n_blocks_total = n_my * B;
+    // The Lmax rows of u the previous push kept enter rows [0, Lmax) of the stage of a stream's first block by one bulk copy
+    // that completes on the stage's `full` barrier (the block then arrives whole, and no transform warp holds history rows
+    // in registers over the wait).  It is started the moment the stage falls free: by the transform warp that is last to
+    // leave it, before that warp's arrival on `empty` (so no front-end warp can have passed it), two blocks ahead.
+    auto copy_kept = [&](int so_k, int gb_k) {
+        const uint32_t bytes = (uint32_t)(Lmax * PITCH), bar = bar_full + (uint32_t)(gb_k & 1) * 8;
+        const float2* src = reinterpret_cast<const float2*>(a.ukeep_in) + (long long)((int)blockIdx.x + so_k * (int)gridDim.x) * a.ukeep_in_stride;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the stage's rows were last written by ordinary stores
+        asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(stage0 + (uint32_t)(gb_k & 1) * STAGE_BYTES),
+                     "l"(src), "r"(bytes), "r"(bar)
+                     : "memory");
+    };
+    if (tid == 0) {
+        copy_kept(0, 0);
+        if (B == 1 && n_my > 1) copy_kept(1, 1);
+    }
     int parked = 0;      // spectra waiting for their inverse transform
     int gb_first = 0;    // global block of parked job 0
     int so = 0, b = -1;  // stream ordinal and block of the current global block
+    PROF(long long tp[6] = {0, 0, 0, 0, 0, 0}; long long tc = clock64();)
 
 #pragma unroll 1
     for (int gb = 0; gb < n_blocks_total; ++gb) {
@@ -545,40 +594,36 @@ k_fused(const __grid_constant__ CUtensorMap tmap, const FusedArgs a, const int n
         const int s = (int)blockIdx.x + so * (int)gridDim.x;
         const uint32_t stg = stage0 + (uint32_t)(gb & 1) * STAGE_BYTES;
 
-        // history rows of the stream's first block: kept by the previous push (loads in flight during the wait)
-        float4 hreg[12];
-        if (b == 0) {
-            const float4* __restrict__ kin = reinterpret_cast<const float4*>(reinterpret_cast<const float2*>(a.ukeep_in) + (long long)s * a.ukeep_in_stride);
-#pragma unroll
-            for (int q = 0; q < 12; ++q) {
-                const int r = lane + 32 * q;
-                if (q < hist_rows_per_lane && r < Lmax) hreg[q] = __ldg(kin + ((long long)r * FRK) / 2 + warp);
-            }
-        }
-        if (b == 0 && n_out < Lmax) {
-            // a push with fewer new rows than the filter reaches back: the rows kept for the NEXT push are the tail of
-            // [this push's history rows | its new rows]; the history part moves over here (this warp's strip of it, read
-            // again: a cold path that must not lengthen the live range of the registers above), the new rows are written by
-            // the front-end warps
-            const float4* __restrict__ kin = reinterpret_cast<const float4*>(reinterpret_cast<const float2*>(a.ukeep_in) + (long long)s * a.ukeep_in_stride);
-            float4* __restrict__ kout = reinterpret_cast<float4*>(reinterpret_cast<float2*>(a.ukeep_out) + (long long)s * a.ukeep_out_stride);
-#pragma unroll 1
-            for (int r = n_out + lane; r < Lmax; r += 32) kout[((long long)(r - n_out) * FRK) / 2 + warp] = __ldg(kin + ((long long)r * FRK) / 2 + warp);
-        }
+        PROF({ long long n_ = clock64(); tp[0] += n_ - tc; tc = n_; })
         mb_wait_long(bar_full + (uint32_t)(gb & 1) * 8, (uint32_t)((gb >> 1) & 1));
-        // rows [0, Lmax) of this warp's strip: from the previous push (b == 0) or from the previous block (keep buffer);
-        // rows [V, V + Lmax) of the strip are the next block's
+        PROF({ long long n_ = clock64(); tp[1] += n_ - tc; tc = n_; })
+        // rows [0, Lmax) of this warp's strip: the stream's first block has them in the stage already (the rows the previous
+        // push kept, copied in by the front-end warp of tile 0), later blocks take them from the keep buffer, where rows
+        // [V, V + Lmax) of every block's strip go for its successor
 #pragma unroll
         for (int q = 0; q < 12; ++q) {
             const int r = lane + 32 * q;
             if (q < hist_rows_per_lane && r < Lmax) {
-                float4 h;
-                if (b == 0) h = hreg[q];
-                else asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(h.x), "=f"(h.y), "=f"(h.z), "=f"(h.w) : "r"(keep_s + r * PITCH));
                 float4 nx;
                 asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(nx.x), "=f"(nx.y), "=f"(nx.z), "=f"(nx.w) : "r"(stg + (V + r) * PITCH + warp * 16));
-                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + r * PITCH + warp * 16), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+                if (b != 0) {
+                    float4 h;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(h.x), "=f"(h.y), "=f"(h.z), "=f"(h.w) : "r"(keep_s + r * PITCH));
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + r * PITCH + warp * 16), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+                }
                 asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(keep_s + r * PITCH), "f"(nx.x), "f"(nx.y), "f"(nx.z), "f"(nx.w) : "memory");
+            }
+        }
+        if (b == 0 && n_out < Lmax) {
+            // a push with fewer new rows than the filter reaches back: the rows kept for the NEXT push are the tail of
+            // [this push's history rows | its new rows]; the history part moves over here (this warp's strip of it), the
+            // new rows are written by the front-end warps
+            float4* __restrict__ kout = reinterpret_cast<float4*>(reinterpret_cast<float2*>(a.ukeep_out) + (long long)s * a.ukeep_out_stride);
+#pragma unroll 1
+            for (int r = n_out + lane; r < Lmax; r += 32) {
+                float4 h;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(h.x), "=f"(h.y), "=f"(h.z), "=f"(h.w) : "r"(stg + r * PITCH + warp * 16));
+                kout[((long long)(r - n_out) * FRK) / 2 + warp] = h;
             }
         }
         // row 511 takes part in the transform but in no stored output (the l = -1 slot of the low-rate filter is empty for
@@ -617,6 +662,7 @@ k_fused(const __grid_constant__ CUtensorMap tmap, const FusedArgs a, const int n
                 }
             }
         }
+        PROF({ long long n_ = clock64(); tp[2] += n_ - tc; tc = n_; })
         // ---- sum the ten partial spectra through the stage, park the block's spectrum ------------------------------
         __syncwarp();
 #pragma unroll
@@ -640,6 +686,7 @@ k_fused(const __grid_constant__ CUtensorMap tmap, const FusedArgs a, const int n
             }
         }
         ++parked;
+        PROF({ long long n_ = clock64(); tp[3] += n_ - tc; tc = n_; })
 
         // ---- inverse transforms of the parked spectra (column g takes job g), through the stage this block still holds
         if (parked == NB || gb + 1 == n_blocks_total) {
@@ -688,10 +735,25 @@ k_fused(const __grid_constant__ CUtensorMap tmap, const FusedArgs a, const int n
             parked = 0;
             sync_t();  // the parked spectra may be overwritten
         }
+        PROF({ long long n_ = clock64(); tp[4] += n_ - tc; tc = n_; })
         // ---- hand the stage back to the front-end warps ---------------------------------------------------------------
         __syncwarp();
-        if (lane == 0) mb_arrive(bar_empty + (uint32_t)(gb & 1) * 8);
+        if (lane == 0) {
+            uint32_t left;
+            asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(left) : "r"(left_cnt + (uint32_t)(gb & 1) * 4) : "memory");
+            if (left % T_WARPS == T_WARPS - 1) {
+                // the last transform warp to leave the stage: if the block after next is a stream's first, its kept rows start now
+                int b2 = b + 2, so2 = so;
+                while (b2 >= B) {
+                    b2 -= B;
+                    ++so2;
+                }
+                if (b2 == 0 && so2 < n_my) copy_kept(so2, gb + 2);
+            }
+            mb_arrive(bar_empty + (uint32_t)(gb & 1) * 8);
+        }
     }
+    PROF(if (tid == 0) for (int q = 0; q < 5; ++q) g_fused_prof[blockIdx.x * 16 + 9 + q] = tp[q];)
 }
 
 // ---------------------------------------------------------------------------
@@ -744,13 +806,17 @@ cudaError_t launch_cfg(int n_streams, const FusedArgs& a, const CUtensorMap& tm,
     kern<<<grid, T_THREADS + 32 * FW, smem, st>>>(tm, a, n_streams);
 #ifdef RR_FUSED_PROF
     static int calls = 0;
-    if (++calls == 12) {
+    static int at = std::getenv("RR_FUSED_PROF_CALL") ? std::atoi(std::getenv("RR_FUSED_PROF_CALL")) : 12;
+    if (++calls == at) {
         cudaDeviceSynchronize();
         long long h[256 * 16];
         cudaMemcpyFromSymbol(h, g_fused_prof, sizeof h);
         for (int c : {0, 100})
-            fprintf(stderr, "cta %d F0: tile-head %lld ring-wait %lld steps %lld fence+sync %lld issue %lld empty-wait %lld finalize %lld | total %lld\n", c, h[c * 16],
-                    h[c * 16 + 1], h[c * 16 + 2], h[c * 16 + 3], h[c * 16 + 4], h[c * 16 + 5], h[c * 16 + 6], h[c * 16 + 7]);
+            fprintf(stderr,
+                    "cta %d n_out %d F0: tile-head %lld ring-wait %lld steps %lld fence+sync %lld issue %lld empty-wait %lld finalize %lld stream-setup %lld | total %lld"
+                    " || T0: pre %lld wait-full %lld fwd+prod %lld sum+park %lld inverse %lld\n",
+                    c, a.n_out, h[c * 16], h[c * 16 + 1], h[c * 16 + 2], h[c * 16 + 3], h[c * 16 + 4], h[c * 16 + 5], h[c * 16 + 6], h[c * 16 + 7], h[c * 16 + 8], h[c * 16 + 9],
+                    h[c * 16 + 10], h[c * 16 + 11], h[c * 16 + 12], h[c * 16 + 13]);
     }
 #endif
     return cudaGetLastError();
@@ -779,6 +845,8 @@ cudaError_t launch_fused(int n_streams, const FusedArgs& a0, int sm_count, cudaS
     if (!enc) return cudaErrorNotSupported;
     FusedArgs a = a0;
     a.coef_off4 = a.coef_slot * (kFusedSlotFloats / 4);
+    // the kept rows of a stream enter the stage by one bulk copy: 16-byte aligned source
+    if ((uintptr_t)a.ukeep_in % 16 != 0 || (n_streams > 1 && a.ukeep_in_stride % 2 != 0)) return cudaErrorInvalidValue;
     const FusedGeom geo = fused_geom(a.P);
     // the stream as overlapping rows of P samples: element (c0, i, s) = in[s*in_stride + c0 + i*P]; a box is half a
     // row wide and F_ROWS rows tall
