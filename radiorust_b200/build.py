@@ -49,6 +49,7 @@ def translation_units():
         ("rr_chunk_kernels.o", "rr_chunk_kernels.cu", []),
         ("rr_metering.o", "rr_metering.cu", []),
         ("rr_big_os.o", "rr_big_os.cu", []),
+        ("rr_long_os.o", "rr_long_os.cu", []),
         ("rr_chain_os_dispatch.o", "rr_chain_os_dispatch.cu", []),
         ("rr_poly.o", "rr_poly.cu", []),
         ("rr_poly2.o", "rr_poly2.cu", []),

@@ -194,13 +194,17 @@ static inline void shape_for(long long N, int* Na, int* Nb) {
 template <typename T> constexpr int max_row_plan() { return sizeof(T) == 4 ? 16384 : 4096; }
 
 template <typename T> bool big_os_supported(int n) {
+    if (long_os_supported(n)) return true;
     if (n < 2048 || (n & (n - 1)) != 0) return false;
     const long long N = 2LL * n;
     int Na, Nb;
     shape_for(N, &Na, &Nb);
     return Nb >= 64 && Nb <= max_row_plan<T>() && (long long)Na * Nb == N;
 }
-template <typename T> void big_os_shape(int n, int* Na, int* Nb) { shape_for(2LL * n, Na, Nb); }
+template <typename T> void big_os_shape(int n, int* Na, int* Nb) {
+    if (long_os_supported(n)) return long_os_shape(n, Na, Nb);
+    shape_for(2LL * n, Na, Nb);
+}
 
 template <typename T, int NB> static long long row_hperm(long long k2) { return PlanFor<T, NB>::type::hperm_index((int)k2); }
 
@@ -209,6 +213,7 @@ template <typename T, int NB> static long long row_hperm(long long k2) { return 
 #define RR_COL_SIZES(X) X(64) X(128) X(256) X(512) X(1024)
 
 template <> long long big_os_hperm_index<float>(int n, long long k) {
+    if (long_os_supported(n)) return long_os_hperm_index(n, k);
     int Na, Nb;
     shape_for(2LL * n, &Na, &Nb);
     const long long k1 = k % Na, k2 = k / Na;
@@ -220,6 +225,7 @@ template <> long long big_os_hperm_index<float>(int n, long long k) {
     return -1;
 }
 template <> long long big_os_hperm_index<double>(int n, long long k) {
+    if (long_os_supported(n)) return long_os_hperm_index(n, k);
     int Na, Nb;
     shape_for(2LL * n, &Na, &Nb);
     const long long k1 = k % Na, k2 = k / Na;
@@ -278,6 +284,7 @@ template <typename T> static cudaError_t cols_dispatch(bool fwd, int Na, int Nb,
 }
 
 template <> cudaError_t launch_big_os<float>(int n, int n_streams, const BigOsArgs<float>& a, cudaStream_t st) {
+    if (long_os_supported(n)) return launch_long_os<float>(n, n_streams, a, st);
     int Na, Nb;
     shape_for(2LL * n, &Na, &Nb);
     cudaError_t e = cols_dispatch<float>(true, Na, Nb, n_streams, a, st);
@@ -292,6 +299,7 @@ template <> cudaError_t launch_big_os<float>(int n, int n_streams, const BigOsAr
     return cols_dispatch<float>(false, Na, Nb, n_streams, a, st);
 }
 template <> cudaError_t launch_big_os<double>(int n, int n_streams, const BigOsArgs<double>& a, cudaStream_t st) {
+    if (long_os_supported(n)) return launch_long_os<double>(n, n_streams, a, st);
     int Na, Nb;
     shape_for(2LL * n, &Na, &Nb);
     cudaError_t e = cols_dispatch<double>(true, Na, Nb, n_streams, a, st);
