@@ -215,7 +215,7 @@ struct Stage {
     std::vector<std::complex<double>> taps;  // windowed impulse response (Flt-rounded), for the polyphase tables
     bool taps_valid = false;
     // big overlap-save tables
-    DevBuf big_h, big_twA, big_twB, big_twC, big_scratch, big_counters;
+    DevBuf big_h, big_twA, big_twB, big_twC, big_scratch;
     // RESAMPLERS
     DevBuf ir, tail[2], obuf[2];
     int tail_cur = 0, obuf_cur = 0;
@@ -290,7 +290,7 @@ struct rr_chain {
     // long Filters (rr_long_os.cu, three kernels per launch group): groups of long_os_group_bytes of scratch go round
     // long_os_lanes side streams, so that the groups' scratch stays in L2 while another group's kernels fill the gaps
     size_t long_os_group_bytes = (size_t)24 << 20;  // RR_LONG_OS_GROUP_MB
-    int long_os_lanes = 4;                          // RR_LONG_OS_LANES (1: everything on the chain's stream)
+    int long_os_lanes = 1;                          // RR_LONG_OS_LANES (1: everything on the chain's stream, one launch group)
     cudaStream_t lane_stream[8] = {};
     cudaEvent_t lane_fork = nullptr, lane_join[8] = {};
     bool allow_sab = true;    // RR_DISABLE_SAB=1: short pushes keep one low-rate block (and inverse round) per stream
@@ -970,36 +970,6 @@ int run_os(rr_chain* c, Stage& s, const FilterIo& io, size_t k, bool fih, void* 
     const size_t n_blocks = k - first;
     if (n_blocks == 0) return RR_OK;
     const size_t esz = 2 * sizeof(T);
-    {
-        // 2n = 2^15 .. 2^20: one persistent kernel takes every block of the push through the three phases; its teams'
-        // scratch slots stay in L2 (rr_long_os.cu)
-        int n_teams = 0, team_size = 0;
-        RR_CUDA(rr::long_os_team_plan<T>((int)n, (int)((size_t)S * n_blocks), &n_teams, &team_size));
-        if (n_teams > 0) {
-            RR_TRY(s.big_scratch.ensure((size_t)n_teams * N * esz));
-            RR_TRY(s.big_counters.ensure((size_t)n_teams * sizeof(unsigned int)));
-            rr::BigOsArgs<T> a{};
-            a.in = src;
-            a.in_stride = src_stride;
-            a.hist = hist_newer;
-            a.hist_stride = hist_stride;
-            a.first_chunk = (int)first;
-            a.n_blocks = (int)n_blocks;
-            a.scratch = s.big_scratch.p;
-            a.hbig = s.big_h.p;
-            a.twN = s.tw.p;
-            a.twA = s.big_twA.p;
-            a.twB = s.big_twB.p;
-            a.twC = s.big_twC.p;
-            a.out = dst;
-            a.out_stride = dst_stride;
-            a.team_counters = s.big_counters.p;
-            a.n_teams = n_teams;
-            a.team_size = team_size;
-            RR_TIMED_LAUNCH(c, "k_long_os", 1, rr::launch_big_os<T>((int)n, S, a, c->stream));
-            return RR_OK;
-        }
-    }
     if (rr::long_os_supported((int)n) && c->long_os_lanes > 1) {
         // the three streaming kernels over launch groups whose scratch fits L2, the groups going round side streams: the
         // scratch of a group is read back while it is still in L2, and the kernels of the other lanes cover a lane's
@@ -2536,7 +2506,7 @@ int rr_chain_destroy(rr_chain* c) {
     cudaSetDevice(c->ctx->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto& s : c->st) {
-        DevBuf* bufs[] = {&s.nco_d, &s.hperm, &s.tw, &s.hist2[0], &s.hist2[1], &s.ztmp, &s.gtab, &s.twK, &s.big_h, &s.big_twA, &s.big_twB, &s.big_twC, &s.big_scratch, &s.big_counters,
+        DevBuf* bufs[] = {&s.nco_d, &s.hperm, &s.tw, &s.hist2[0], &s.hist2[1], &s.ztmp, &s.gtab, &s.twK, &s.big_h, &s.big_twA, &s.big_twB, &s.big_twC, &s.big_scratch,
                           &s.ir, &s.tail[0], &s.tail[1], &s.obuf[0], &s.obuf[1], &s.fm_prev, &s.fm_last, &s.out,
                           &s.gtab2, &s.twK2, &s.acoef, &s.gtab3, &s.ubuf[0], &s.ubuf[1], &s.fwin, &s.ftw, &s.fm_phase, &s.ukeep[0], &s.ukeep[1],
                           &s.stg_in, &s.stg_out, &s.zero_chunk, &s.idx_a, &s.idx_b};

@@ -156,9 +156,6 @@ template <typename T> struct BigOsArgs {
     void* out;              // [S][out_stride]
     long long out_stride;
     const void* twC;        // rr_long_os.cu: [long_os_twc_size] W_N^(long_os_twc_exponent(i)), the column tiles' twiddle factors
-    // persistent form (rr_long_os.cu, long_os_team_plan): scratch is [n_teams][N], one launch takes every block
-    void* team_counters;    // [n_teams] u32
-    int n_teams, team_size; // 0: the three kernels, scratch [S*n_blocks][N]
 };
 template <typename T> bool big_os_supported(int n);
 template <typename T> void big_os_shape(int n, int* Na, int* Nb);
@@ -174,8 +171,6 @@ template <typename T>
 cudaError_t launch_long_os(int n, int n_streams, const BigOsArgs<T>& a, cudaStream_t st);
 template <typename T> int long_os_twc_size(int n);
 template <typename T> long long long_os_twc_exponent(int n, int i);
-// teams x CTAs per team of the persistent kernel for `total_blocks` overlap-save blocks (0 x 0: use the three kernels)
-template <typename T> cudaError_t long_os_team_plan(int n, int total_blocks, int* n_teams, int* team_size);
 
 // ---- polyphase fused chain: NCO -> Filter -> Downsampler without the full-rate
 // intermediate (rr_poly.cuh) ---------------------------------------------------

@@ -16,10 +16,12 @@
 // built in registers from one or two table reads with multiplication depth <= 4 (geo_twiddle).  complex<f32> arithmetic
 // runs on the packed two-wide instructions (rr_pk.cuh), complex<f64> on rr_complex.cuh's scalar forms.
 //
-// Streaming the scratch through HBM makes the three kernels HBM bound at 11 point transfers per output sample.
-// k_long_os runs the same three phases in ONE persistent kernel: teams of co-resident CTAs take a block through the
-// phases with a team barrier in between, and the teams are few enough for every team's scratch slot to stay in L2, so
-// HBM sees the input and the output only.  Other sizes keep rr_big_os.cu's kernels.  sm_100a.
+// The scratch streams through HBM (11 point transfers per output sample).  The column kernels run at 71-75 % of the DRAM
+// peak, the row kernel at 61 % with the fp32 pipe 66 % busy (two radix-32 passes each way: ~85 flop per point and
+// direction); both floors lie within 1.5 x of each other, so no single change moves the path far.  Measured and not kept:
+// launch groups whose scratch fits L2 going round side streams (rr_chain.cu keeps the switch), the three phases in one
+// persistent kernel with teams of CTAs and team barriers (commit 71727ba), the row kernel's next row prefetched by a bulk
+// copy (fewer warps fit; 854 -> 1020 us).  Other sizes keep rr_big_os.cu's kernels.  sm_100a.
 #include <cstdlib>
 
 #include "rr_kernels.h"
@@ -240,7 +242,7 @@ __device__ __forceinline__ void rows_row(cx<T>* __restrict__ sm, cx<T>* __restri
     __syncwarp();
 }
 
-// ---- the three phases as kernels of their own (RR_LONG_OS_SPLIT=1; scratch of a whole launch group) ----------------
+// ---- the three kernels -------------------------------------------------------------------------------------------------
 template <typename T, int A, int B, int W>
 __global__ void __launch_bounds__(kThreads)
 k_long_cols_fwd(const cx<T>* __restrict__ in, long long in_stride, const cx<T>* __restrict__ hist, long long hist_stride, int first_chunk, int n_blocks,
@@ -280,76 +282,6 @@ k_long_rows(cx<T>* __restrict__ scratch, long long n_rows, int Na, const cx<T>* 
 #pragma unroll 1
     for (long long row = (long long)blockIdx.x * kRowWarps + warp; row < n_rows; row += (long long)gridDim.x * kRowWarps)
         rows_row<T>(sm, scratch + row * kRowLen, hbig + (row % Na) * kRowLen, wl);
-}
-
-// ---- the three phases in ONE persistent kernel --------------------------------------------------------------------------
-// A team of `team_size` co-resident CTAs takes a block through the phases, with a team-wide barrier (a counter in global
-// memory) between them; the team's scratch slot (N points) is written and read again while it is in L2, and the teams
-// are few enough for all slots to stay there.  CTAs of other teams on the same SM fill the barrier waits.
-struct LongOsTeamArgs {
-    int n_teams, team_size;
-    int total_blocks;         // n_streams * n_blocks
-    unsigned int* counters;   // [n_teams], zero at launch
-};
-
-__device__ __forceinline__ void team_barrier(unsigned int* counter, unsigned int target) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(counter, 1u);
-        unsigned int seen;
-        do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
-            if (seen < target) __nanosleep(64);
-        } while (seen < target);
-        __threadfence();
-    }
-    __syncthreads();
-}
-
-template <typename T, int A, int B, int W> constexpr size_t team_smem() {
-    return cols_smem<T, A, B, W>() > rows_smem<T>() ? cols_smem<T, A, B, W>() : rows_smem<T>();
-}
-
-template <typename T, int A, int B, int W>
-__global__ void __launch_bounds__(kThreads)
-k_long_os(const cx<T>* __restrict__ in, long long in_stride, const cx<T>* __restrict__ hist, long long hist_stride, int first_chunk, int n_blocks,
-          cx<T>* __restrict__ scratch, const cx<T>* __restrict__ hbig, const cx<T>* __restrict__ twN, const cx<T>* __restrict__ twA,
-          const cx<T>* __restrict__ twB, const cx<T>* __restrict__ twC, cx<T>* __restrict__ out, long long out_stride, const LongOsTeamArgs ta) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    cx<T>* sm = reinterpret_cast<cx<T>*>(smem_raw);
-    constexpr int Na = A * B, TILES = kRowLen / W;
-    const long long n = (long long)Na * kRowLen / 2;
-    const int team = blockIdx.x / ta.team_size, rank = blockIdx.x % ta.team_size;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    cx<T>* slot = scratch + (long long)team * Na * kRowLen;
-    unsigned int* counter = ta.counters + team;
-    unsigned int target = 0;
-    const typename CT<T>::C wl = CT<T>::ldg(&twB[lane]);
-#pragma unroll 1
-    for (int w = team; w < ta.total_blocks; w += ta.n_teams) {
-        const int s = w / n_blocks, b = w % n_blocks;
-        const int ch = first_chunk + b;
-        const cx<T>* cur = in + (long long)s * in_stride + (long long)ch * n;
-        const cx<T>* prev = (ch > 0) ? cur - n : hist + (long long)s * hist_stride;
-#pragma unroll 1
-        for (int tile = rank; tile < TILES; tile += ta.team_size) {
-            cols_fwd_tile<T, A, B, W>(sm, prev, cur, tile, slot, twN, twA, twC);
-            __syncthreads();
-        }
-        team_barrier(counter, target += ta.team_size);
-#pragma unroll 1
-        for (int row = rank * kRowWarps + warp; row < Na; row += ta.team_size * kRowWarps)
-            rows_row<T>(sm + warp * (32 * kRowPitch), slot + (long long)row * kRowLen, hbig + (long long)row * kRowLen, wl);
-        team_barrier(counter, target += ta.team_size);
-        cx<T>* dst = out + (long long)s * out_stride + (long long)b * n;
-#pragma unroll 1
-        for (int tile = rank; tile < TILES; tile += ta.team_size) {
-            cols_inv_tile<T, A, B, W>(sm, slot, tile, twN, twA, twC, dst);
-            __syncthreads();
-        }
-        team_barrier(counter, target += ta.team_size);  // the slot is free for the next block's forward tiles
-    }
 }
 
 // Na = A x B and the columns per tile: rows of 128 bytes or more where 128 / W row groups divide both passes; Na = 1024
@@ -436,81 +368,6 @@ long long long_os_hperm_index(int n, long long k) {
     return (k % Na) * kRowLen + k / Na;
 }
 
-namespace {
-
-// RR_LONG_OS_PERSISTENT=1: k_long_os instead of the three kernels per launch group (measured slower: see DESIGN 4.3)
-bool long_os_split() {
-    static const bool v = [] {
-        const char* e = std::getenv("RR_LONG_OS_PERSISTENT");
-        return !(e && std::atoi(e) != 0);
-    }();
-    return v;
-}
-long long env_ll(const char* name, long long dflt) {
-    const char* e = std::getenv(name);
-    return e ? std::atoll(e) : dflt;
-}
-
-template <typename T, int NA> cudaError_t team_plan_na(int total_blocks, int* n_teams, int* team_size) {
-    using S = ColShape<T, NA>;
-    auto k = k_long_os<T, S::A, S::B, S::W>;
-    constexpr size_t smem = team_smem<T, S::A, S::B, S::W>();
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int dev = 0, sms = 0, occ = 0;
-    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kThreads, smem)) != cudaSuccess) return e;
-    if (occ < 1) return cudaErrorLaunchOutOfResources;
-    const long long resident = (long long)occ * sms;
-    const long long block_bytes = (long long)NA * kRowLen * 2 * sizeof(T);
-    const long long budget = env_ll("RR_LONG_OS_L2_MB", 64) << 20;  // all teams' scratch slots together
-    constexpr int TILES = kRowLen / S::W;
-    long long ts = env_ll("RR_LONG_OS_TEAM", 0);
-    if (ts <= 0) {
-        ts = 1;
-        while (ts < TILES && (resident / ts) * block_bytes > budget) ts *= 2;
-    }
-    if (ts > resident) ts = resident;
-    long long teams = resident / ts;
-    if (teams > total_blocks) {  // few blocks: larger teams, as far as a block has tiles for them
-        teams = total_blocks;
-        while (ts * 2 <= TILES && ts * 2 * teams <= resident) ts *= 2;
-    }
-    *n_teams = (int)teams;
-    *team_size = (int)ts;
-    return cudaSuccess;
-}
-
-template <typename T, int NA> cudaError_t launch_team_na(int n_streams, const BigOsArgs<T>& a, cudaStream_t st) {
-    using S = ColShape<T, NA>;
-    auto k = k_long_os<T, S::A, S::B, S::W>;
-    constexpr size_t smem = team_smem<T, S::A, S::B, S::W>();
-    LongOsTeamArgs ta;
-    ta.n_teams = a.n_teams;
-    ta.team_size = a.team_size;
-    ta.total_blocks = n_streams * a.n_blocks;
-    ta.counters = reinterpret_cast<unsigned int*>(a.team_counters);
-    cudaError_t e = cudaMemsetAsync(a.team_counters, 0, sizeof(unsigned int) * (size_t)a.n_teams, st);
-    if (e != cudaSuccess) return e;
-    const cx<T>* in = reinterpret_cast<const cx<T>*>(a.in);
-    const cx<T>* hist = reinterpret_cast<const cx<T>*>(a.hist);
-    cx<T>* scratch = reinterpret_cast<cx<T>*>(a.scratch);
-    const cx<T>* hbig = reinterpret_cast<const cx<T>*>(a.hbig);
-    const cx<T>* twN = reinterpret_cast<const cx<T>*>(a.twN);
-    const cx<T>* twA = reinterpret_cast<const cx<T>*>(a.twA);
-    const cx<T>* twB = reinterpret_cast<const cx<T>*>(a.twB);
-    const cx<T>* twC = reinterpret_cast<const cx<T>*>(a.twC);
-    cx<T>* out = reinterpret_cast<cx<T>*>(a.out);
-    long long in_stride = a.in_stride, hist_stride = a.hist_stride, out_stride = a.out_stride;
-    int first_chunk = a.first_chunk, n_blocks = a.n_blocks;
-    void* args[] = {&in, &in_stride, &hist, &hist_stride, &first_chunk, &n_blocks, &scratch, &hbig, &twN, &twA, &twB, &twC, &out, &out_stride, &ta};
-    // cooperative: every CTA of a team must be resident for the team barrier to complete
-    return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(k), dim3((unsigned)(a.n_teams * a.team_size)), dim3(kThreads), args, smem, st);
-}
-
-}  // namespace
-
 // positions of the column kernels' small twiddle table (BigOsArgs::twC): entry i holds W_N^e, e = long_os_twc_exponent(i)
 template <typename T> int long_os_twc_size(int n) {
     int A = 0, W = 0;
@@ -538,37 +395,9 @@ template int long_os_twc_size<double>(int);
 template long long long_os_twc_exponent<float>(int, int);
 template long long long_os_twc_exponent<double>(int, int);
 
-template <typename T> cudaError_t long_os_team_plan(int n, int total_blocks, int* n_teams, int* team_size) {
-    *n_teams = 0;
-    *team_size = 0;
-    if (long_os_split() || !long_os_supported(n)) return cudaSuccess;
-    switch ((int)(2LL * n / kRowLen)) {
-        case 32: return team_plan_na<T, 32>(total_blocks, n_teams, team_size);
-        case 64: return team_plan_na<T, 64>(total_blocks, n_teams, team_size);
-        case 128: return team_plan_na<T, 128>(total_blocks, n_teams, team_size);
-        case 256: return team_plan_na<T, 256>(total_blocks, n_teams, team_size);
-        case 512: return team_plan_na<T, 512>(total_blocks, n_teams, team_size);
-        case 1024: return team_plan_na<T, 1024>(total_blocks, n_teams, team_size);
-    }
-    return cudaErrorInvalidValue;
-}
-template cudaError_t long_os_team_plan<float>(int, int, int*, int*);
-template cudaError_t long_os_team_plan<double>(int, int, int*, int*);
-
 template <typename T> cudaError_t launch_long_os(int n, int n_streams, const BigOsArgs<T>& a, cudaStream_t st) {
     int Na, Nb;
     long_os_shape(n, &Na, &Nb);
-    if (a.n_teams > 0) {
-        switch (Na) {
-            case 32: return launch_team_na<T, 32>(n_streams, a, st);
-            case 64: return launch_team_na<T, 64>(n_streams, a, st);
-            case 128: return launch_team_na<T, 128>(n_streams, a, st);
-            case 256: return launch_team_na<T, 256>(n_streams, a, st);
-            case 512: return launch_team_na<T, 512>(n_streams, a, st);
-            case 1024: return launch_team_na<T, 1024>(n_streams, a, st);
-        }
-        return cudaErrorInvalidValue;
-    }
     cudaError_t e = cols_dispatch<T>(true, Na, n_streams, a, st);
     if (e != cudaSuccess) return e;
     e = launch_rows<T>(Na, n_streams, a, st);
