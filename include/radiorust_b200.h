@@ -200,11 +200,11 @@ int rr_design_downsampler_taps(double input_rate, double output_rate, double ban
 int rr_design_upsampler_taps(double input_rate, double output_rate, double bandwidth, double quality,
                              size_t* ir_len, double* ir);   /* resampling.rs:205-233 */
 
-/* Diagnostic of the rank-reduced form of Filter -> Downsampler (integer decimation): the P x (Lmax+1)
- * matrix of the fused filter g = taps(filters.rs:184-238) * reversed taps(resampling.rs:82-101) is
- * factored as sum_c a_c b_c^T; *rank = smallest count whose discarded part is <= tol * |M|_F (0 if that
- * needs more than max_rank), *discarded = that part, *table_error = relative L2 distance between the
- * factorisation and the full polyphase tables (K = 512). */
+/* Diagnostic of the rank-reduced form of Filter -> Downsampler (in/out = P/Q reduced, Q <= 4): the P x (Lmax+1)
+ * matrix of the fused filter g = taps(filters.rs:184-238) * reversed taps(resampling.rs:82-101) -- for Q > 1 the Q
+ * phase matrices side by side -- is factored as sum_c a_c b_c^T; *rank = smallest count whose discarded part is
+ * <= tol * |M|_F (0 if that needs more than max_rank), *discarded = that part, *table_error = relative L2 distance
+ * between the factorisation and the full polyphase tables (K = 512). */
 int rr_design_fused_rank(rr_freq_resp_fn f, void* f_user, int32_t window_kind, double window_beta, rr_window_fn w, void* w_user,
                          double sample_rate, size_t n, double output_rate, double bandwidth, double quality, double tol,
                          int max_rank, int* rank, double* discarded, double* table_error);

@@ -247,6 +247,11 @@ struct Stage {
     bool front_valid = false;
     int front_rank = 0;
     double front_discarded = 0.0;
+    // in/out = P/Q with Q > 1 (f32): front end of kFrontQRank columns shared by the Q phases, then k_poly on u
+    bool frontq_valid = false;
+    int frontq_rank = 0;
+    double frontq_discarded = 0.0;
+    DevBuf acoef_q, gtab_q;
     bool poly2_valid = false;
     int poly2_G = 0, poly2_V = 0;
     size_t obuf_cap = 0;  // samples per stream in obuf
@@ -1101,6 +1106,8 @@ void fused_slot_release(int device, const void* owner) {
         if (g_slot_owner[device][i] == owner) g_slot_owner[device][i] = nullptr;
 }
 
+constexpr int kFrontQRank = 16;  // columns of the Q > 1 front end (two rounds of k_poly's G = 8)
+
 // (re)build the polyphase tables for the pair (filter f, downsampler ds)
 template <typename T> int poly_prepare(rr_chain* c, Stage& f, Stage& ds) {
     if (ds.poly_tried) return RR_OK;
@@ -1108,6 +1115,7 @@ template <typename T> int poly_prepare(rr_chain* c, Stage& f, Stage& ds) {
     ds.poly_valid = false;
     ds.poly2_valid = false;
     ds.front_valid = false;
+    ds.frontq_valid = false;
     ds.fused_valid = false;
     if (!f.taps_valid) return RR_OK;
     const long long P = ds.h.P, Q = ds.h.Q;
@@ -1161,6 +1169,40 @@ template <typename T> int poly_prepare(rr_chain* c, Stage& f, Stage& ds) {
     ds.poly_Lmax = (int)Lmax;
     ds.poly_V = (int)(bestK - 1 - Lmax);
     ds.poly_valid = true;
+
+    // Q > 1, complex f32: the Q phase matrices factored together (rr_design.h: design_rank_tables_q).  The front end
+    // (k_front, kFrontQRank columns) is shared by the phases; the low-rate part is k_poly on u as a stream of kFrontQRank
+    // branches with one table per phase -- kFrontQRank instead of P forward transforms per block
+    if (std::is_same<T, float>::value && Q > 1 && c->allow_front && rr::front_supported(kFrontQRank, P) && P > kFrontQRank &&
+        rr::poly_supported<T>(bestK, (int)Q, 8) && Lmax + 2 <= bestK) {
+        std::vector<double> acf;
+        std::vector<std::complex<double>> bq;
+        int rank = 0;
+        double disc = 0.0;
+        const int lmq = rr::design_rank_tables_q(f.taps, ds.ir_host_flt, P, Q, bestK, 2.0e-8, kFrontQRank, &rank, &acf, &bq, &disc);
+        if (rank > 0 && lmq == (int)Lmax) {
+            std::vector<float> ac((size_t)P * kFrontQRank);
+            for (size_t i = 0; i < ac.size(); ++i) ac[i] = (float)acf[i];
+            RR_TRY(ds.acoef_q.ensure(ac.size() * sizeof(float)));
+            RR_CUDA(cudaMemcpyAsync(ds.acoef_q.p, ac.data(), ac.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+            RR_CUDA(cudaStreamSynchronize(c->stream));  // `ac` is pageable and dies here
+            constexpr int GQ = 8;
+            const long long NRq = kFrontQRank / GQ;
+            perm.assign((size_t)(Q * NRq) * (size_t)bestK * (size_t)GQ, std::complex<double>(0.0, 0.0));
+            for (long long q = 0; q < Q; ++q)
+                for (int cc = 0; cc < kFrontQRank; ++cc) {
+                    const long long r = cc / GQ, gg = cc % GQ;
+                    for (int k = 0; k < bestK; ++k) {
+                        const size_t pos = (size_t)rr::poly_hperm_index<T>(bestK, k);
+                        perm[(((size_t)(q * NRq + r)) * bestK + pos) * GQ + gg] = bq[((size_t)q * kFrontQRank + cc) * bestK + k] * scale;
+                    }
+                }
+            RR_TRY(upload_complex<T>(ds.gtab_q, perm, c->stream));
+            ds.frontq_rank = rank;
+            ds.frontq_discarded = disc;
+            ds.frontq_valid = true;
+        }
+    }
 
     // the packed-fp32 / TMA kernel: complex f32, integer decimation, K = 512
     if (std::is_same<T, float>::value && c->allow_poly2 && rr::poly2_supported(512, P, Q) && 511 - Lmax >= 128) {
@@ -1383,7 +1425,7 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
         // outputs m (1-based, counted with the reduced counters) firing inside this part
         const long long m_lo = m0 + 1;
         const long long m_hi = floordiv128(j0 + zlen, Qq, Pq);
-        bool used_poly2 = false, used_front = false, used_fused = false;
+        bool used_poly2 = false, used_front = false, used_fused = false, used_frontq = false;
         if (m_hi >= m_lo) {
             rr::PolyArgs<T> a{};
             // filter output k aligns with push sample k; the part starts at push sample ca*n, and the
@@ -1615,6 +1657,69 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
                         used_front = true;
                     }
                 }
+                if (!done && ds.frontq_valid && tma_ok && Qq > 1) {
+                    // Q > 1: u rows [I_first-1-Lmax, I_last] (tap l = -1 of the phases q > 0 reads row I), then k_poly on u with
+                    // the Q phase tables.  Output m = Q*I + q keeps its index: block 0's window starts at u row 0, which is
+                    // row I_first-1-Lmax of the stream (PolyArgs::J0 in units of u samples).  No rows are kept between pushes
+                    // (the last row of a push is cut off by its end), the Filter's history is k_hist2_update's.
+                    constexpr int RQ = kFrontQRank, GQ = 8;
+                    const long long Lh = ds.poly_Lmax;
+                    const long long I_first = a.I_lo, I_last = I_hi;
+                    const long long row_first = I_first - 1 - Lh;
+                    const long long n_rows = I_last - I_first + 2 + Lh;
+                    const long long u_stride = n_rows * RQ;
+                    if (n_rows * Pq < (1LL << 31)) {
+                        DevBuf& ub = ds.ubuf[0];
+                        RR_TRY(ub.ensure((size_t)S * (size_t)u_stride * 2 * sizeof(float)));
+                        ds.ubuf_stride[0] = -1;
+                        rr::FrontArgs fa{};
+                        fa.in = a.in;
+                        fa.in_stride = a.in_stride;
+                        fa.len = a.len;
+                        fa.hist2 = f.hist2[f.hist_cur].p;
+                        fa.n = a.n;
+                        fa.nco = a.nco;
+                        fa.acoef = (const float*)ds.acoef_q.p;
+                        fa.P = (int)Pq;
+                        fa.J0 = a.J0;
+                        fa.row_first = row_first;
+                        fa.n_rows = (int)n_rows;
+                        fa.u = ub.p;
+                        fa.u_stride = u_stride;
+                        f.hist_fused_jlo = -1;
+                        f.hist_fused_jfirst = 0;
+                        RR_TIMED_LAUNCH(c, "k_front", 1, rr::launch_front(RQ, S, fa, st));
+                        rr::PolyArgs<float> b{};
+                        b.in = ub.p;
+                        b.in_stride = u_stride;
+                        b.len = n_rows * RQ;
+                        b.hist2 = ub.p;
+                        b.n = 0;
+                        b.nco = nullptr;
+                        b.gtab = ds.gtab_q.p;
+                        b.twK = ds.twK.p;
+                        b.P = RQ;
+                        b.Q = Qq;
+                        b.Lmax = (int)Lh;
+                        b.V = ds.poly_V;
+                        b.J0 = row_first * RQ;
+                        b.m0 = a.m0;
+                        b.m_lo = a.m_lo;
+                        b.m_hi = a.m_hi;
+                        b.I_lo = I_first;
+                        b.n_blocks = (int)((I_last - I_first) / b.V + 1);
+                        int nbpc = std::max(1, GQ / (int)Qq);
+                        while (nbpc > 1 && rr::poly_smem_bytes<float>(ds.poly_K, (int)Qq, GQ, nbpc) > (size_t)200 * 1024) --nbpc;
+                        while (nbpc > 1 && (long long)S * ((b.n_blocks + nbpc - 1) / nbpc) < 2LL * c->ctx->sm_count) --nbpc;
+                        const int nsb = (b.n_blocks + nbpc - 1) / nbpc;
+                        b.nbpc = (b.n_blocks + nsb - 1) / nsb;
+                        b.out = obase;
+                        b.out_stride = ostride;
+                        RR_TIMED_LAUNCH(c, "k_poly(u)", 1, rr::launch_poly<float>(ds.poly_K, (int)Qq, GQ, S, b, st));
+                        done = true;
+                        used_frontq = true;
+                    }
+                }
                 if (!done && ds.poly2_valid && tma_ok) {
                     a.gtab = ds.gtab2.p;
                     if (ds.poly2_tw_own) a.twK = ds.twK2.p;
@@ -1660,7 +1765,7 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
         }
         ds.ztail_stale = true;
         if (!plan->empty() && plan->back() != '+' && plan->back() != '|' && ca > 0) *plan += "|";
-        *plan += used_fused ? "fused[filter+down]" : (used_front ? "front+poly2[filter+down]" : (used_poly2 ? "poly2[filter+down]" : "poly[filter+down]"));
+        *plan += used_frontq ? "front+poly[filter+down]" : used_fused ? "fused[filter+down]" : (used_front ? "front+poly2[filter+down]" : (used_poly2 ? "poly2[filter+down]" : "poly[filter+down]"));
     }
     return RR_OK;
 }
@@ -2013,7 +2118,7 @@ void chain_restart(rr_chain* c) {
     for (auto& s : c->st) {
         s.h = StageHost{};
         s.taps_valid = false;
-        s.poly_valid = s.poly_tried = s.poly2_valid = s.front_valid = false;
+        s.poly_valid = s.poly_tried = s.poly2_valid = s.front_valid = s.frontq_valid = false;
         s.ztail_stale = false;
         s.ucache_valid = false;
         s.hist_fused_jlo = -1;
@@ -2395,7 +2500,7 @@ int rr_design_fused_rank(rr_freq_resp_fn f, void* f_user, int32_t window_kind, d
         return fail(RR_ERR_INVALID, "rr_design_fused_rank: rates must be integer valued, input >= output > 0");
     const long long g = std::gcd((long long)sample_rate, (long long)output_rate);
     const long long P = (long long)sample_rate / g, Q = (long long)output_rate / g;
-    if (Q != 1) return fail(RR_ERR_UNSUPPORTED, "rr_design_fused_rank: integer decimation only");
+    if (Q < 1 || Q > 4) return fail(RR_ERR_UNSUPPORTED, "rr_design_fused_rank: in/out = P/Q with Q <= 4 only");
     size_t L = 0;
     RR_TRY(design_taps(true, sample_rate, output_rate, bandwidth, quality, &L, nullptr));
     std::vector<double> ir(L);
@@ -2405,20 +2510,24 @@ int rr_design_fused_rank(rr_freq_resp_fn f, void* f_user, int32_t window_kind, d
     std::vector<double> a;
     std::vector<std::complex<double>> b, full;
     double disc = 0.0;
-    const int lmax = rr::design_rank_tables(taps, ir, P, K, tol, max_rank, rank, &a, &b, &disc);
+    // Q == 1: b is [max_rank][K]; Q > 1: the phases factored together, b is [Q][max_rank][K]
+    const int lmax = Q == 1 ? rr::design_rank_tables(taps, ir, P, K, tol, max_rank, rank, &a, &b, &disc)
+                            : rr::design_rank_tables_q(taps, ir, P, Q, K, tol, max_rank, rank, &a, &b, &disc);
     if (discarded) *discarded = disc;
     if (table_error) {
         *table_error = -1.0;
-        if (*rank > 0 && lmax + 1 < K) {
-            rr::design_poly_tables(taps, ir, P, 1, K, &full);
+        if (*rank > 0 && lmax + 2 <= K) {
+            rr::design_poly_tables(taps, ir, P, Q, K, &full);
             double num = 0.0, den = 0.0;
-            for (long long p = 0; p < P; ++p)
-                for (int k = 0; k < K; ++k) {
-                    std::complex<double> sum(0.0, 0.0);
-                    for (int c = 0; c < *rank; ++c) sum += a[(size_t)p * max_rank + c] * b[(size_t)c * K + k];
-                    num += std::norm(sum - full[(size_t)p * K + k]);
-                    den += std::norm(full[(size_t)p * K + k]);
-                }
+            for (long long q = 0; q < Q; ++q)
+                for (long long p = 0; p < P; ++p)
+                    for (int k = 0; k < K; ++k) {
+                        std::complex<double> sum(0.0, 0.0);
+                        for (int c = 0; c < *rank; ++c) sum += a[(size_t)p * max_rank + c] * b[((size_t)q * max_rank + c) * K + k];
+                        const std::complex<double> want = full[(size_t)(q * P + p) * K + k];
+                        num += std::norm(sum - want);
+                        den += std::norm(want);
+                    }
             *table_error = den > 0.0 ? std::sqrt(num / den) : 0.0;
         }
     }
@@ -2508,7 +2617,7 @@ int rr_chain_destroy(rr_chain* c) {
     for (auto& s : c->st) {
         DevBuf* bufs[] = {&s.nco_d, &s.hperm, &s.tw, &s.hist2[0], &s.hist2[1], &s.ztmp, &s.gtab, &s.twK, &s.big_h, &s.big_twA, &s.big_twB, &s.big_twC, &s.big_scratch,
                           &s.ir, &s.tail[0], &s.tail[1], &s.obuf[0], &s.obuf[1], &s.fm_prev, &s.fm_last, &s.out,
-                          &s.gtab2, &s.twK2, &s.acoef, &s.gtab3, &s.ubuf[0], &s.ubuf[1], &s.fwin, &s.ftw, &s.fm_phase, &s.ukeep[0], &s.ukeep[1],
+                          &s.gtab2, &s.twK2, &s.acoef, &s.gtab3, &s.acoef_q, &s.gtab_q, &s.ubuf[0], &s.ubuf[1], &s.fwin, &s.ftw, &s.fm_phase, &s.ukeep[0], &s.ukeep[1],
                           &s.stg_in, &s.stg_out, &s.zero_chunk, &s.idx_a, &s.idx_b};
         for (DevBuf* b : bufs) b->release();
         if (s.fused_slot >= 0) fused_slot_release(c->ctx->device, &s);

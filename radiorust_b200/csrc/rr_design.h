@@ -55,6 +55,13 @@ int design_poly_tables(const std::vector<std::complex<double>>& h, const std::ve
 // = FFT_K of b_c (natural bin order).  Returns Lmax.
 int design_rank_tables(const std::vector<std::complex<double>>& h, const std::vector<double>& ir, long long P, int K, double tol,
                        int max_rank, int* rank, std::vector<double>* a, std::vector<std::complex<double>>* b, double* discarded);
+// The same for in/out = P/Q with Q > 1: output m = Q*I + q fires at j_m = I*P + s_q and is
+//   y_m = sum_l sum_p M_q[p][l] * x'[(I-1-l)*P + p],   M_q[p][l] = g[P-1+s_q-p + l*P],  l = -1 .. Lmax.
+// The Q matrices are factored TOGETHER, [M_0 | .. | M_{Q-1}] = sum_c a_c [b_{c,0} | .. | b_{c,Q-1}]^T: the front end
+// u_c[i] = sum_p a_c[p] * x'[i*P + p] is shared by the phases, y_q = sum_c (b_{c,q} * u_c).  `bfft`: [Q][rank_pad][K],
+// tap l = -1 in slot K-1.
+int design_rank_tables_q(const std::vector<std::complex<double>>& h, const std::vector<double>& ir, long long P, long long Q, int K, double tol,
+                         int max_rank, int* rank, std::vector<double>* a, std::vector<std::complex<double>>* b, double* discarded);
 
 // unit-energy windowed-sinc taps, f64 (cast by the caller)
 void design_resampler_taps(size_t ir_len, double ratio, double null_bin, std::vector<double>* out);

@@ -53,7 +53,8 @@ __device__ __forceinline__ pc lds_front(uint32_t addr) {
 
 template <int RK, bool HAS_NCO>
 __global__ void __launch_bounds__(FR_WARPS * 32, 4) k_front(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_h, const FrontArgs a) {
-    static_assert(RK == 10, "the store split below (6 + 4 results per lane pair) is written for ten columns");
+    static_assert(RK == 10 || RK == 16, "results leave as 16-byte pairs: 6 + 4 per lane pair for ten columns, 8 + 8 for sixteen");
+    constexpr int RK_SPLIT = RK == 10 ? 6 : RK / 2;  // lane hh = 0 stores results [0, RK_SPLIT), lane hh = 1 the rest
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = lane >> 1, hh = lane & 1;  // row of the tile, half of its columns
     const int s = blockIdx.y;
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(FR_WARPS * 32, 4) k_front(const __grid_constan
         // every lane is done with the slot: it may be refilled (generic-proxy accesses ordered before the copy)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
-        // the two column halves of a row meet; lane hh = 0 stores results 0..5, lane hh = 1 results 6..9
+        // the two column halves of a row meet; lane hh = 0 stores results [0, RK_SPLIT), lane hh = 1 the others
 #pragma unroll
         for (int c = 0; c < RK; ++c)
             acc[c] = acc[c] + pc(__shfl_xor_sync(0xffffffffu, acc[c].x, 1), __shfl_xor_sync(0xffffffffu, acc[c].y, 1));
@@ -346,7 +347,7 @@ __global__ void __launch_bounds__(FR_WARPS * 32, 4) k_front(const __grid_constan
             float4* dst = u + ((long long)v * RK) / 2;
             if (hh == 0) {
 #pragma unroll
-                for (int c = 0; c < 6; c += 2) {
+                for (int c = 0; c < RK_SPLIT; c += 2) {
                     pc y0 = acc[c], y1 = acc[c + 1];
                     if (HAS_NCO) {
                         y0 = pcmul(y0, rowph);
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(FR_WARPS * 32, 4) k_front(const __grid_constan
                 }
             } else {
 #pragma unroll
-                for (int c = 6; c < RK; c += 2) {
+                for (int c = RK_SPLIT; c < RK; c += 2) {
                     pc y0 = acc[c], y1 = acc[c + 1];
                     if (HAS_NCO) {
                         y0 = pcmul(y0, rowph);
@@ -388,12 +389,12 @@ EncodeFn front_encode_fn() {
 bool front_supported(int rank_pad, long long P) {
     // even P (TMA rows are 16-byte multiples; the tile pitch is padded to an odd number of 16-byte units); one TMA
     // box per tile
-    return rank_pad == 10 && P >= 2 && P <= 254 && (P % 2) == 0 && front_encode_fn() != nullptr;
+    return (rank_pad == 10 || rank_pad == 16) && P >= 2 && P <= 254 && (P % 2) == 0 && front_encode_fn() != nullptr;
 }
 
 cudaError_t launch_front(int rank_pad, int n_streams, const FrontArgs& a0, cudaStream_t st) {
     EncodeFn enc = front_encode_fn();
-    if (!enc || rank_pad != 10) return cudaErrorNotSupported;
+    if (!enc || (rank_pad != 10 && rank_pad != 16)) return cudaErrorNotSupported;
     FrontArgs a = a0;
     const int tiles = (a.n_rows + FR_ROWS - 1) / FR_ROWS;
     // long-lived warps amortise the per-CTA tables: as few CTAs per stream as keep ~4 CTAs per SM in the
@@ -423,20 +424,21 @@ cudaError_t launch_front(int rank_pad, int n_streams, const FrontArgs& a0, cudaS
             a.has_hist_map = 1;
     }
     const int tile_stride = (FR_ROWS * pitch * 8 + 127) / 128 * 128;
-    const size_t smem = (size_t)FR_WARPS * FR_STAGES * tile_stride + (size_t)(a.P / 2) * 2 * 10 * 4 + (size_t)a.P * 8 + FR_WARPS * FR_STAGES * 8 + 16;
+    const size_t smem = (size_t)FR_WARPS * FR_STAGES * tile_stride + (size_t)(a.P / 2) * 2 * rank_pad * 4 + (size_t)a.P * 8 + FR_WARPS * FR_STAGES * 8 + 16;
     const dim3 grid((unsigned)((tiles + FR_WARPS * a.tiles_per_warp - 1) / (FR_WARPS * a.tiles_per_warp)), (unsigned)n_streams);
-    cudaError_t e;
-    if (a.nco) {
-        auto kern = k_front<10, true>;
+    cudaError_t e = cudaSuccess;
+    auto go = [&](auto kern) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        kern<<<grid, FR_WARPS * 32, smem, st>>>(tm, tmh, a);
+        if (e == cudaSuccess) kern<<<grid, FR_WARPS * 32, smem, st>>>(tm, tmh, a);
+    };
+    if (rank_pad == 10) {
+        if (a.nco) go(k_front<10, true>);
+        else go(k_front<10, false>);
     } else {
-        auto kern = k_front<10, false>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        kern<<<grid, FR_WARPS * 32, smem, st>>>(tm, tmh, a);
+        if (a.nco) go(k_front<16, true>);
+        else go(k_front<16, false>);
     }
+    if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
 

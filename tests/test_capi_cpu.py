@@ -172,7 +172,22 @@ def test_fused_filter_rank_gives_up_on_wideband_filters(lib):
     rc, rank, disc, err = _fused_rank(lib, lambda b, f: 1.0, 2_400_000.0, 4096, 240000.0, 100000.0, 2.0e-8, 64)
     assert rc == 0 and (rank == 0 or err <= 2.5e-8)
     # contract violations
-    assert _fused_rank(lib, orc.lowpass(3000.0), 1_024_000.0, 4096, 48000.0, 6000.0, 2.0e-8, 10)[0] == _ffi.RR_ERR_UNSUPPORTED  # 64/3
+    assert _fused_rank(lib, orc.lowpass(3000.0), 1_000_000.0, 4096, 48000.0, 6000.0, 2.0e-8, 10)[0] == _ffi.RR_ERR_UNSUPPORTED  # 125/6
+
+
+@pytest.mark.parametrize("sr,n,cut,out_rate,bw", [
+    (1_024_000.0, 4096, 3000.0, 48000.0, 6000.0),     # C1: in/out = 64/3
+    (1_200_000.0, 4096, 3000.0, 32000.0, 6000.0),     # 75/2
+    (1_120_000.0, 4096, 3000.0, 64000.0, 6000.0),     # 35/2
+])
+def test_fused_filter_rank_with_output_phases(lib, sr, n, cut, out_rate, bw):
+    """in/out = P/Q, Q > 1: the Q phase matrices factored together (one front end for all phases) reproduce the full
+    [Q][P][K] polyphase tables to below f32 rounding within the sixteen columns the front end is built for."""
+    rc, rank, disc, err = _fused_rank(lib, orc.lowpass(cut), sr, n, out_rate, bw, 2.0e-8, 16)
+    assert rc == 0
+    assert 1 <= rank <= 16, rank
+    assert disc <= 2.0e-8
+    assert 0.0 <= err <= 2.5e-8, err
     assert _fused_rank(lib, orc.lowpass(3000.0), 2_400_000.0, 4000, 48000.0, 6000.0, 2.0e-8, 10)[0] == _ffi.RR_ERR_INVALID
 
 

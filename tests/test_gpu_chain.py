@@ -349,6 +349,44 @@ def test_poly_rates(ctx, flt, n, sr, out_rate, bw, ocl):
     check(got, want, flt)
 
 
+@pytest.mark.parametrize("sr,out_rate,ocl,pushes", [
+    (1_024_000.0, 48000.0, 192, [3, 10, 1, 2, 13]),   # C1: P/Q = 64/3
+    (1_200_000.0, 32000.0, 100, [2, 9, 15]),          # 75/2 ... odd P: the chain keeps k_poly
+    (1_120_000.0, 64000.0, 64, [4, 1, 1, 12]),        # 35/2 ... odd P as well
+    (1_536_000.0, 64000.0, 64, [4, 1, 1, 12]),        # 24/1 is Q = 1; 1 536 000 / 64 000 = 24
+    (2_048_000.0, 96000.0, 128, [3, 8, 1, 14]),       # 64/3 at another rate
+])
+def test_front_end_shared_by_output_phases(ctx, sr, out_rate, ocl, pushes):
+    """in/out = P/Q with Q > 1 and even P: the steady state runs the rank-reduced front end (sixteen columns shared by
+    the Q phases) and k_poly on u; several streams with their own shifts, pushes of one chunk and of many."""
+    import radiorust_b200 as rr
+
+    n, S = 4096, 3
+    x = np.stack([noise(9100 + s, sum(pushes) * n, "f32") for s in range(S)])
+    stages = [rr.FreqShifter(0.0), rr.Filter.new(orc.lowpass(3000.0)), rr.Downsampler(ocl, out_rate, 6000.0)]
+    ch = rr.Chain(ctx, stages, "f32", n_streams=S)
+    shifts = [sr / 7.0, -123456.0, 0.0]
+    ch.set_shifts(0, shifts)
+    got, plans, pos = [], [], 0
+    for k in pushes:
+        y, _ = ch.push(sr, np.ascontiguousarray(x[:, pos * n : (pos + k) * n]), n)
+        got.append(y.copy())
+        plans.append(ch.plan)
+        pos += k
+    ch.close()
+    got = np.concatenate(got, axis=1)
+    g = math.gcd(int(sr), int(out_rate))
+    P, Q = int(sr) // g, int(out_rate) // g
+    if Q > 1 and P % 2 == 0:
+        assert any("front+poly[" in p for p in plans), plans
+    for s in range(S):
+        oc = orc.Chain([orc.FreqShifter("f32", 1.0, shifts[s]), orc.Filter.new("f32", orc.lowpass(3000.0)),
+                        orc.Downsampler("f32", ocl, out_rate, 6000.0)])
+        want = oc.run(sr, x[s], n)
+        assert want.shape == got[s].shape, (want.shape, got[s].shape)
+        assert orc.rel_l2(got[s], want) <= TOL["f32"]
+
+
 def test_poly_filter_down_without_nco_multi_stream(ctx):
     import radiorust_b200 as rr
 
