@@ -43,6 +43,10 @@ namespace {
 constexpr int FR_WARPS = 4;
 constexpr int FR_ROWS = 16;  // rows per tile: a lane pair per row, each lane half of the columns
 constexpr int FR_STAGES = 2;  // tiles per warp in shared memory (one being filled while the other is used)
+// bytes between the coefficient rows of consecutive steps ([2][RK] floats each).  The two lanes of a pair read rows that
+// lie a multiple of four steps apart: sixteen columns (128-byte rows) get one 16-byte unit of padding, so that those rows
+// start on different banks
+constexpr int front_coef_pitch(int rk) { return 2 * rk * 4 + ((2 * rk * 4) % 128 == 0 ? 16 : 0); }
 
 __device__ __forceinline__ uint32_t f_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ pc lds_front(uint32_t addr) {
@@ -75,13 +79,19 @@ __global__ void __launch_bounds__(FR_WARPS * 32, 4) k_front(const __grid_constan
             if (((full / 2 + d) & 7) == 4) split = full / 2 + d;
     }
     const int st0 = hh ? split : 0, st1 = hh ? full : split;
+    // lane hh = 1 walks its steps from `rot` on and wraps round: at any moment its 16-byte unit of the row (and its
+    // coefficient row) lies split + rot = 4 (mod 8) units from its partner's, whatever the split -- the two halves of a
+    // quarter warp then never meet on a bank.  (The sums are taken in another order than with rot = 0; still one fixed order.)
+    const int cnt = st1 - st0;
+    const int rot = (hh && cnt > 0) ? ((4 - (split & 7)) & 7) % cnt : 0;
+    constexpr int CP = front_coef_pitch(RK);
 
     extern __shared__ __align__(128) unsigned char smem[];
     const int tile_bytes = FR_ROWS * pitch * 8;
     const int tile_stride = (tile_bytes + 127) / 128 * 128;
     unsigned char* tiles = smem + warp * (FR_STAGES * tile_stride);          // this warp's ring of tiles
     float* coef = reinterpret_cast<float*>(smem + FR_WARPS * FR_STAGES * tile_stride);  // [steps][2][RK]
-    float2* colph = reinterpret_cast<float2*>(coef + steps * 2 * RK);        // [P]
+    float2* colph = reinterpret_cast<float2*>(coef + (steps + 1) * (CP / 4));  // [P]
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(colph + P);
     const uint32_t bar0 = f_smem_u32(&bars[warp * FR_STAGES]);
 
@@ -96,7 +106,7 @@ __global__ void __launch_bounds__(FR_WARPS * 32, 4) k_front(const __grid_constan
         idx0 = ns.idx;
         start = (float)ns.start_phase;
     }
-    for (int e = threadIdx.x; e < steps * 2 * RK; e += FR_WARPS * 32) coef[e] = a.acoef[e];
+    for (int e = threadIdx.x; e < P * RK; e += FR_WARPS * 32) coef[(e / (2 * RK)) * (CP / 4) + e % (2 * RK)] = a.acoef[e];
     for (int p = threadIdx.x; p < P; p += FR_WARPS * 32) {
         cx<float> r(1.f, 0.f);
         if (HAS_NCO) r = nco_rotation<float>(p, numer_abs, denom, sign);
@@ -261,7 +271,9 @@ __global__ void __launch_bounds__(FR_WARPS * 32, 4) k_front(const __grid_constan
         const bool staged = a.hist_staged != 0;
         auto run_row = [&](auto write_hist) {
 #pragma unroll 4
-            for (int st = st0; st < st1; ++st) {
+            for (int it = 0; it < cnt; ++it) {
+                int st = st0 + rot + it;
+                if (st >= st1) st -= cnt;
                 pc x0, x1;
                 asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x0.x), "=f"(x0.y), "=f"(x1.x), "=f"(x1.y) : "r"(row_s + st * 16));
                 if (HAS_NCO) {
@@ -291,7 +303,7 @@ __global__ void __launch_bounds__(FR_WARPS * 32, 4) k_front(const __grid_constan
                 for (int q = 0; q < (2 * RK) / 4; ++q)
                     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                                  : "=f"(cf[4 * q]), "=f"(cf[4 * q + 1]), "=f"(cf[4 * q + 2]), "=f"(cf[4 * q + 3])
-                                 : "r"(coef_s + st * (2 * RK * 4) + q * 16));
+                                 : "r"(coef_s + st * CP + q * 16));
 #pragma unroll
                 for (int c = 0; c < RK; ++c) {
                     acc[c] = pfma_s(x0, cf[c], acc[c]);
@@ -316,7 +328,7 @@ __global__ void __launch_bounds__(FR_WARPS * 32, 4) k_front(const __grid_constan
                 static_assert(RK % 2 == 0, "coefficient rows are read in pairs");
 #pragma unroll
                 for (int q = 0; q < RK / 2; ++q)
-                    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(cf[2 * q]), "=f"(cf[2 * q + 1]) : "r"(coef_s + p * (RK * 4) + q * 8));
+                    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(cf[2 * q]), "=f"(cf[2 * q + 1]) : "r"(coef_s + (p >> 1) * CP + (p & 1) * (RK * 4) + q * 8));
 #pragma unroll
                 for (int c = 0; c < RK; ++c) acc[c] = pfma_s(x0, cf[c], acc[c]);
             }
@@ -424,7 +436,7 @@ cudaError_t launch_front(int rank_pad, int n_streams, const FrontArgs& a0, cudaS
             a.has_hist_map = 1;
     }
     const int tile_stride = (FR_ROWS * pitch * 8 + 127) / 128 * 128;
-    const size_t smem = (size_t)FR_WARPS * FR_STAGES * tile_stride + (size_t)(a.P / 2) * 2 * rank_pad * 4 + (size_t)a.P * 8 + FR_WARPS * FR_STAGES * 8 + 16;
+    const size_t smem = (size_t)FR_WARPS * FR_STAGES * tile_stride + (size_t)(a.P / 2 + 1) * front_coef_pitch(rank_pad) + (size_t)a.P * 8 + FR_WARPS * FR_STAGES * 8 + 16;
     const dim3 grid((unsigned)((tiles + FR_WARPS * a.tiles_per_warp - 1) / (FR_WARPS * a.tiles_per_warp)), (unsigned)n_streams);
     cudaError_t e = cudaSuccess;
     auto go = [&](auto kern) {
