@@ -1686,8 +1686,20 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
                         fa.n_rows = (int)n_rows;
                         fa.u = ub.p;
                         fa.u_stride = u_stride;
+                        // the rows cover push offsets [row_first*P - J0, (I_last+1)*P - J0), cut off at the end of the push: when
+                        // that reaches back to len - 2n the kernel also writes the Filter's next history
+                        const long long cover_lo = row_first * Pq - a.J0, cover_hi = std::min<long long>((I_last + 1) * Pq - a.J0, a.len);
                         f.hist_fused_jlo = -1;
                         f.hist_fused_jfirst = 0;
+                        const long long hfrom = a.len - 2 * a.n, hstart = std::max<long long>(hfrom, 0);
+                        if (cover_lo <= hstart && cover_hi > hstart) {
+                            fa.hist_out = f.hist2[f.hist_cur ^ 1].p;
+                            fa.hist_from = hfrom;
+                            fa.hist_stride = 2 * a.n;
+                            fa.hist_staged = a.len < 4 * a.n ? 1 : 0;
+                            f.hist_fused_jlo = cover_hi - hfrom;
+                            f.hist_fused_jfirst = hstart - hfrom;
+                        }
                         RR_TIMED_LAUNCH(c, "k_front", 1, rr::launch_front(RQ, S, fa, st));
                         rr::PolyArgs<float> b{};
                         b.in = ub.p;
@@ -2037,8 +2049,9 @@ int run_push(rr_chain* c, double sample_rate, size_t chunk_len, size_t n_chunks,
                         if (s.hist_fused_jfirst > 0)
                             RR_TIMED_LAUNCH(c, "k_hist2_update", 1, rr::launch_hist2_update<T>(io.in, io.in_stride, len, hin, hout, (long long)n, ncop, S,
                                                                                                 st, 0, s.hist_fused_jfirst));
-                        RR_TIMED_LAUNCH(c, "k_hist2_update", 1, rr::launch_hist2_update<T>(io.in, io.in_stride, len, hin, hout, (long long)n, ncop, S, st,
-                                                                                            s.hist_fused_jlo, -1));
+                        if (s.hist_fused_jlo < (long long)(2 * n))
+                            RR_TIMED_LAUNCH(c, "k_hist2_update", 1, rr::launch_hist2_update<T>(io.in, io.in_stride, len, hin, hout, (long long)n, ncop, S, st,
+                                                                                                s.hist_fused_jlo, -1));
                     } else {
                         RR_TIMED_LAUNCH(c, "k_hist2_update", 1, rr::launch_hist2_update<T>(io.in, io.in_stride, len, hin, hout, (long long)n, ncop, S, st, 0, -1));
                     }

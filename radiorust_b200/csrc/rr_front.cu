@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(FR_WARPS * 32, 4) k_front(const __grid_constan
     const float2* __restrict__ hist_end = reinterpret_cast<const float2*>(a.hist2) + ((long long)s + 1) * 2 * a.n;
     float4* __restrict__ u = reinterpret_cast<float4*>(reinterpret_cast<float2*>(a.u) + (long long)s * a.u_stride);
     const long long len = a.len, hist_len = 2 * a.n;
+    const long long hist_cap = len - a.hist_from;  // entries of hist_out that exist: push offsets below len
     float2* __restrict__ hist_o = a.hist_out ? reinterpret_cast<float2*>(a.hist_out) + (long long)s * a.hist_stride : nullptr;
     const uint32_t tiles_s = f_smem_u32(tiles);
     const uint32_t coef_s = f_smem_u32(coef), col_s = f_smem_u32(colph);
@@ -292,9 +293,9 @@ __global__ void __launch_bounds__(FR_WARPS * 32, 4) k_front(const __grid_constan
                                          : "memory");
                     } else {
                         const long long j = prow + 2 * st - a.hist_from;
-                        if (row_ok && j >= -1) {
+                        if (row_ok && j >= -1 && j < hist_cap) {  // (a last row may reach past the pushed samples)
                             if (j >= 0) hist_o[j] = make_float2(y0.x, y0.y);
-                            hist_o[j + 1] = make_float2(y1.x, y1.y);
+                            if (j + 1 < hist_cap) hist_o[j + 1] = make_float2(y1.x, y1.y);
                         }
                     }
                 }
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(FR_WARPS * 32, 4) k_front(const __grid_constan
                         if (HAS_NCO) asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(row_s + p * 8), "f"(y0.x), "f"(y0.y) : "memory");
                     } else {
                         const long long j = prow + p - a.hist_from;
-                        if (row_ok && j >= 0) hist_o[j] = make_float2(y0.x, y0.y);
+                        if (row_ok && j >= 0 && j < hist_cap) hist_o[j] = make_float2(y0.x, y0.y);
                     }
                 }
                 float cf[RK];
@@ -344,7 +345,7 @@ __global__ void __launch_bounds__(FR_WARPS * 32, 4) k_front(const __grid_constan
             for (int r = 0; r < rows_ok; ++r) {
                 const long long j0 = (long long)pos0 + (long long)r * P - a.hist_from;
                 for (int p = lane; p < P; p += 32)
-                    if (j0 + p >= 0) hist_o[j0 + p] = src[r * pitch + p];
+                    if (j0 + p >= 0 && j0 + p < hist_cap) hist_o[j0 + p] = src[r * pitch + p];
             }
         }
         // every lane is done with the slot: it may be refilled (generic-proxy accesses ordered before the copy)
