@@ -246,6 +246,21 @@ def test_big_overlap_save_f64(ctx):
     check(got, want, "f64")
 
 
+@pytest.mark.parametrize("flt", ["f32", "f64"])
+@pytest.mark.parametrize("n", [16384, 32768, 131072, 262144, 524288])
+def test_long_filter_every_shape(ctx, flt, n):
+    """Every column shape of the streaming four-step kernels (rr_long_os.cu: 2n = Na x 1024, Na = 32 ... 1024; n = 65536
+    is covered above), two streams, pushes of one and of two chunks."""
+    import radiorust_b200 as rr
+
+    sr = 2_400_000.0
+    x = np.stack([noise(31337 + n + s, 3 * n, flt) for s in range(2)])
+    got, want, plan = run_both(ctx, [rr.Filter.new(orc.lowpass(20000.0))], flt, sr, x, n, pushes=[1, 2])
+    assert "big_os" in plan
+    assert got.shape[1] == 2 * n
+    check(got, want, flt)
+
+
 def test_config2_chain(ctx):
     """20 MS/s stream, n = 65536: FreqShifter -> Filter -> Downsampler(48 kS/s), L = 2858."""
     import radiorust_b200 as rr
