@@ -54,6 +54,7 @@ def translation_units():
         ("rr_poly.o", "rr_poly.cu", []),
         ("rr_poly2.o", "rr_poly2.cu", []),
         ("rr_front.o", "rr_front.cu", []),
+        ("rr_front_wide.o", "rr_front_wide.cu", []),
         ("rr_fused.o", "rr_fused.cu", []),
         ("rr_fourier.o", "rr_fourier.cu", []),
     ]

@@ -249,6 +249,8 @@ struct Stage {
     double front_discarded = 0.0;
     // in/out = P/Q with Q > 1 (f32): front end of kFrontQRank columns shared by the Q phases, then k_poly on u
     bool frontq_valid = false;
+    bool frontq_wide = false;  // k_front_wide (any P) instead of k_front (even P <= 254)
+    int frontq_cols = 0;       // columns of u: 16 or 32
     int frontq_rank = 0;
     double frontq_discarded = 0.0;
     DevBuf acoef_q, gtab_q;
@@ -1171,34 +1173,41 @@ template <typename T> int poly_prepare(rr_chain* c, Stage& f, Stage& ds) {
     ds.poly_valid = true;
 
     // Q > 1, complex f32: the Q phase matrices factored together (rr_design.h: design_rank_tables_q).  The front end
-    // (k_front, kFrontQRank columns) is shared by the phases; the low-rate part is k_poly on u as a stream of kFrontQRank
-    // branches with one table per phase -- kFrontQRank instead of P forward transforms per block
-    if (std::is_same<T, float>::value && Q > 1 && c->allow_front && rr::front_supported(kFrontQRank, P) && P > kFrontQRank &&
-        rr::poly_supported<T>(bestK, (int)Q, 8) && Lmax + 2 <= bestK) {
+    // (16 or 32 columns: k_front for even P <= 254, k_front_wide for any P) is shared by the phases; the low-rate part is
+    // k_poly on u as a stream of that many branches with one table per phase -- 16 / 32 instead of P forward transforms
+    // per block
+    if (std::is_same<T, float>::value && Q > 1 && c->allow_front && P > 2 * kFrontQRank && rr::poly_supported<T>(bestK, (int)Q, 8) &&
+        Lmax + 2 <= bestK) {
+        constexpr int RMAX = 2 * kFrontQRank;
         std::vector<double> acf;
         std::vector<std::complex<double>> bq;
         int rank = 0;
         double disc = 0.0;
-        const int lmq = rr::design_rank_tables_q(f.taps, ds.ir_host_flt, P, Q, bestK, 2.0e-8, kFrontQRank, &rank, &acf, &bq, &disc);
-        if (rank > 0 && lmq == (int)Lmax) {
-            std::vector<float> ac((size_t)P * kFrontQRank);
-            for (size_t i = 0; i < ac.size(); ++i) ac[i] = (float)acf[i];
+        const int lmq = rr::design_rank_tables_q(f.taps, ds.ir_host_flt, P, Q, bestK, 2.0e-8, RMAX, &rank, &acf, &bq, &disc);
+        const int cols = rank <= kFrontQRank ? kFrontQRank : RMAX;
+        const bool narrow = cols == kFrontQRank && rr::front_supported(kFrontQRank, P);
+        if (rank > 0 && lmq == (int)Lmax && (narrow || rr::front_wide_supported(cols, P))) {
+            std::vector<float> ac((size_t)P * cols);
+            for (long long p = 0; p < P; ++p)
+                for (int cc = 0; cc < cols; ++cc) ac[(size_t)p * cols + cc] = (float)acf[(size_t)p * RMAX + cc];
             RR_TRY(ds.acoef_q.ensure(ac.size() * sizeof(float)));
             RR_CUDA(cudaMemcpyAsync(ds.acoef_q.p, ac.data(), ac.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
             RR_CUDA(cudaStreamSynchronize(c->stream));  // `ac` is pageable and dies here
             constexpr int GQ = 8;
-            const long long NRq = kFrontQRank / GQ;
+            const long long NRq = cols / GQ;
             perm.assign((size_t)(Q * NRq) * (size_t)bestK * (size_t)GQ, std::complex<double>(0.0, 0.0));
             for (long long q = 0; q < Q; ++q)
-                for (int cc = 0; cc < kFrontQRank; ++cc) {
+                for (int cc = 0; cc < cols; ++cc) {
                     const long long r = cc / GQ, gg = cc % GQ;
                     for (int k = 0; k < bestK; ++k) {
                         const size_t pos = (size_t)rr::poly_hperm_index<T>(bestK, k);
-                        perm[(((size_t)(q * NRq + r)) * bestK + pos) * GQ + gg] = bq[((size_t)q * kFrontQRank + cc) * bestK + k] * scale;
+                        perm[(((size_t)(q * NRq + r)) * bestK + pos) * GQ + gg] = bq[((size_t)q * RMAX + cc) * bestK + k] * scale;
                     }
                 }
             RR_TRY(upload_complex<T>(ds.gtab_q, perm, c->stream));
             ds.frontq_rank = rank;
+            ds.frontq_cols = cols;
+            ds.frontq_wide = !narrow;
             ds.frontq_discarded = disc;
             ds.frontq_valid = true;
         }
@@ -1657,12 +1666,13 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
                         used_front = true;
                     }
                 }
-                if (!done && ds.frontq_valid && tma_ok && Qq > 1) {
+                if (!done && ds.frontq_valid && (tma_ok || ds.frontq_wide) && Qq > 1) {
                     // Q > 1: u rows [I_first-1-Lmax, I_last] (tap l = -1 of the phases q > 0 reads row I), then k_poly on u with
                     // the Q phase tables.  Output m = Q*I + q keeps its index: block 0's window starts at u row 0, which is
                     // row I_first-1-Lmax of the stream (PolyArgs::J0 in units of u samples).  No rows are kept between pushes
                     // (the last row of a push is cut off by its end), the Filter's history is k_hist2_update's.
-                    constexpr int RQ = kFrontQRank, GQ = 8;
+                    const int RQ = ds.frontq_cols;
+                    constexpr int GQ = 8;
                     const long long Lh = ds.poly_Lmax;
                     const long long I_first = a.I_lo, I_last = I_hi;
                     const long long row_first = I_first - 1 - Lh;
@@ -1692,7 +1702,7 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
                         f.hist_fused_jlo = -1;
                         f.hist_fused_jfirst = 0;
                         const long long hfrom = a.len - 2 * a.n, hstart = std::max<long long>(hfrom, 0);
-                        if (cover_lo <= hstart && cover_hi > hstart) {
+                        if (!ds.frontq_wide && cover_lo <= hstart && cover_hi > hstart) {
                             fa.hist_out = f.hist2[f.hist_cur ^ 1].p;
                             fa.hist_from = hfrom;
                             fa.hist_stride = 2 * a.n;
@@ -1700,7 +1710,8 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
                             f.hist_fused_jlo = cover_hi - hfrom;
                             f.hist_fused_jfirst = hstart - hfrom;
                         }
-                        RR_TIMED_LAUNCH(c, "k_front", 1, rr::launch_front(RQ, S, fa, st));
+                        if (ds.frontq_wide) RR_TIMED_LAUNCH(c, "k_front_wide", 1, rr::launch_front_wide(RQ, S, fa, st));
+                        else RR_TIMED_LAUNCH(c, "k_front", 1, rr::launch_front(RQ, S, fa, st));
                         rr::PolyArgs<float> b{};
                         b.in = ub.p;
                         b.in_stride = u_stride;

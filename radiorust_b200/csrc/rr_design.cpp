@@ -299,6 +299,98 @@ int design_rank_tables(const std::vector<std::complex<double>>& h, const std::ve
     return Lmax;
 }
 
+namespace {
+// one-sided Jacobi (Hestenes) on the columns of W (rows x nc, row-major): afterwards the columns are orthogonal,
+// W_final = W * V with V (nc x nc) the accumulated rotations
+void hestenes_columns(std::vector<double>& W, std::vector<double>& V, int rows, int nc) {
+    V.assign((size_t)nc * nc, 0.0);
+    for (int p = 0; p < nc; ++p) V[(size_t)p * nc + p] = 1.0;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0;
+        for (int i = 0; i < nc - 1; ++i)
+            for (int j = i + 1; j < nc; ++j) {
+                double aii = 0.0, ajj = 0.0, aij = 0.0;
+                for (int r = 0; r < rows; ++r) {
+                    const double wi = W[(size_t)r * nc + i], wj = W[(size_t)r * nc + j];
+                    aii += wi * wi;
+                    ajj += wj * wj;
+                    aij += wi * wj;
+                }
+                if (aij == 0.0 || std::fabs(aij) <= 1e-17 * std::sqrt(aii * ajj)) continue;
+                off = std::max(off, std::fabs(aij) / std::sqrt(aii * ajj));
+                const double zeta = (ajj - aii) / (2.0 * aij);
+                const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+                const double cs = 1.0 / std::sqrt(1.0 + t * t), sn = cs * t;
+                for (int r = 0; r < rows; ++r) {
+                    const double wi = W[(size_t)r * nc + i], wj = W[(size_t)r * nc + j];
+                    W[(size_t)r * nc + i] = cs * wi - sn * wj;
+                    W[(size_t)r * nc + j] = sn * wi + cs * wj;
+                }
+                for (int r = 0; r < nc; ++r) {
+                    const double vi = V[(size_t)r * nc + i], vj = V[(size_t)r * nc + j];
+                    V[(size_t)r * nc + i] = cs * vi - sn * vj;
+                    V[(size_t)r * nc + j] = sn * vi + cs * vj;
+                }
+            }
+        if (off < 1e-15) break;
+    }
+}
+
+// Row space of W (rows x np, row-major) by pivoted Gram-Schmidt (each new vector re-orthogonalised): W = C * Qb + R with
+// Qb (r x np) orthonormal rows and |R|_F^2 = *resid <= stop2.  Cheap when the numerical rank is far below both dimensions
+// (the fused filter of a long decimation: P in the thousands, rank in the twenties).
+int row_space(const std::vector<double>& W, int rows, int np, int rmax, double stop2, std::vector<double>* Qb, std::vector<double>* C, double* resid) {
+    std::vector<double> R = W, rn((size_t)rows, 0.0);
+    double res = 0.0;
+    for (int i = 0; i < rows; ++i) {
+        double t = 0.0;
+        for (int p = 0; p < np; ++p) t += R[(size_t)i * np + p] * R[(size_t)i * np + p];
+        rn[(size_t)i] = t;
+        res += t;
+    }
+    Qb->assign((size_t)rmax * np, 0.0);
+    C->assign((size_t)rows * rmax, 0.0);
+    int r = 0;
+    std::vector<double> q((size_t)np);
+    while (r < rmax && res > stop2) {
+        int best = 0;
+        for (int i = 1; i < rows; ++i)
+            if (rn[(size_t)i] > rn[(size_t)best]) best = i;
+        if (!(rn[(size_t)best] > 0.0)) break;
+        for (int p = 0; p < np; ++p) q[(size_t)p] = R[(size_t)best * np + p];
+        for (int pass = 0; pass < 2; ++pass)
+            for (int k = 0; k < r; ++k) {
+                double d = 0.0;
+                for (int p = 0; p < np; ++p) d += q[(size_t)p] * (*Qb)[(size_t)k * np + p];
+                for (int p = 0; p < np; ++p) q[(size_t)p] -= d * (*Qb)[(size_t)k * np + p];
+            }
+        double nq = 0.0;
+        for (int p = 0; p < np; ++p) nq += q[(size_t)p] * q[(size_t)p];
+        if (!(nq > 0.0)) break;
+        nq = std::sqrt(nq);
+        for (int p = 0; p < np; ++p) (*Qb)[(size_t)r * np + p] = q[(size_t)p] / nq;
+        res = 0.0;
+        for (int i = 0; i < rows; ++i) {
+            double d = 0.0;
+            const double* qb = Qb->data() + (size_t)r * np;
+            double* ri = R.data() + (size_t)i * np;
+            for (int p = 0; p < np; ++p) d += ri[p] * qb[p];
+            (*C)[(size_t)i * rmax + r] = d;
+            double t = 0.0;
+            for (int p = 0; p < np; ++p) {
+                ri[p] -= d * qb[p];
+                t += ri[p] * ri[p];
+            }
+            rn[(size_t)i] = t;
+            res += t;
+        }
+        ++r;
+    }
+    *resid = res;
+    return r;
+}
+}  // namespace
+
 // The Q > 1 form: the Q phase matrices M_q[p][l] = g[P-1+s_q-p + l*P], l = -1 .. Lmax, side by side share one set of
 // a_c (the front end does not know the phase); the low-rate part has one b_{c,q} per phase.
 int design_rank_tables_q(const std::vector<std::complex<double>>& h, const std::vector<double>& ir, long long P, long long Q, int K, double tol,
@@ -316,12 +408,10 @@ int design_rank_tables_q(const std::vector<std::complex<double>>& h, const std::
     const int nl = Lmax + 2, np = (int)P, nq = (int)Q;  // slot l + 1 holds tap l
     *rank = 0;
     if (nl > K) return Lmax;
-    // W: per phase q the rows [Re M_q^T ; Im M_q^T] (2*nl rows of P columns); Hestenes rotations make the columns
-    // orthogonal, V accumulates them: W_final = W * V, column c = (b_{c,q} re | b_{c,q} im)_q, a_c = V[:, c]
+    // W: per phase q the rows [Re M_q^T ; Im M_q^T] (2*nl rows of P columns)
     const int rows = 2 * nl * nq;
-    std::vector<double> W((size_t)rows * np, 0.0), V((size_t)np * np, 0.0);
-    for (int p = 0; p < np; ++p) {
-        V[(size_t)p * np + p] = 1.0;
+    std::vector<double> W((size_t)rows * np, 0.0);
+    for (int p = 0; p < np; ++p)
         for (int q = 0; q < nq; ++q) {
             const long long sq = ((long long)q * P + Q - 1) / Q;
             for (int l = -1; l <= Lmax; ++l) {
@@ -331,49 +421,41 @@ int design_rank_tables_q(const std::vector<std::complex<double>>& h, const std::
                 W[(size_t)(q * 2 * nl + nl + l + 1) * np + p] = g[(size_t)idx].imag();
             }
         }
-    }
     double total = 0.0;
     for (double w : W) total += w * w;
     if (!(total > 0.0)) return Lmax;
-    for (int sweep = 0; sweep < 60; ++sweep) {
-        double off = 0.0;
-        for (int i = 0; i < np - 1; ++i)
-            for (int j = i + 1; j < np; ++j) {
-                double aii = 0.0, ajj = 0.0, aij = 0.0;
-                for (int r = 0; r < rows; ++r) {
-                    const double wi = W[(size_t)r * np + i], wj = W[(size_t)r * np + j];
-                    aii += wi * wi;
-                    ajj += wj * wj;
-                    aij += wi * wj;
-                }
-                if (aij == 0.0 || std::fabs(aij) <= 1e-17 * std::sqrt(aii * ajj)) continue;
-                off = std::max(off, std::fabs(aij) / std::sqrt(aii * ajj));
-                const double zeta = (ajj - aii) / (2.0 * aij);
-                const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
-                const double cs = 1.0 / std::sqrt(1.0 + t * t), sn = cs * t;
-                for (int r = 0; r < rows; ++r) {
-                    const double wi = W[(size_t)r * np + i], wj = W[(size_t)r * np + j];
-                    W[(size_t)r * np + i] = cs * wi - sn * wj;
-                    W[(size_t)r * np + j] = sn * wi + cs * wj;
-                }
-                for (int r = 0; r < np; ++r) {
-                    const double vi = V[(size_t)r * np + i], vj = V[(size_t)r * np + j];
-                    V[(size_t)r * np + i] = cs * vi - sn * vj;
-                    V[(size_t)r * np + j] = sn * vi + cs * vj;
-                }
-            }
-        if (off < 1e-15) break;
+    // Many branches (P well above the rank): first the row space of W by pivoted Gram-Schmidt, W = C * Qb + R with
+    // |R| a tenth of the tolerance, then the small C (rows x r) takes W's place; a_c = Qb^T v_c.  Few branches: W itself.
+    std::vector<double> Qb, V;
+    int nc = np;
+    double resid = 0.0;
+    const bool compress = np > 128;
+    if (compress) {
+        std::vector<double> C;
+        const int rmax = std::min(std::min(rows, np), 4 * max_rank + 16);
+        const double stop = 0.1 * tol;
+        const int r = row_space(W, rows, np, rmax, stop * stop * total, &Qb, &C, &resid);
+        if (r < 1) return Lmax;
+        std::vector<double> W2((size_t)rows * r);
+        for (int i = 0; i < rows; ++i)
+            for (int k = 0; k < r; ++k) W2[(size_t)i * r + k] = C[(size_t)i * rmax + k];
+        W.swap(W2);
+        nc = r;
     }
-    std::vector<double> sig2((size_t)np, 0.0);
-    std::vector<int> order((size_t)np);
-    for (int c = 0; c < np; ++c) {
+    // Hestenes rotations make the columns orthogonal, V accumulates them: W_final = W * V,
+    // column c = (b_{c,q} re | b_{c,q} im)_q, a_c = V[:, c] (through Qb when compressed)
+    hestenes_columns(W, V, rows, nc);
+    std::vector<double> sig2((size_t)nc, 0.0);
+    std::vector<int> order((size_t)nc);
+    for (int c = 0; c < nc; ++c) {
         order[(size_t)c] = c;
-        for (int r = 0; r < rows; ++r) sig2[(size_t)c] += W[(size_t)r * np + c] * W[(size_t)r * np + c];
+        for (int r = 0; r < rows; ++r) sig2[(size_t)c] += W[(size_t)r * nc + c] * W[(size_t)r * nc + c];
     }
     std::sort(order.begin(), order.end(), [&](int x, int y) { return sig2[(size_t)x] > sig2[(size_t)y]; });
-    int rk = np;
-    double tail = 0.0;
-    for (int c = np - 1; c >= 0; --c) {
+    int rk = nc;
+    double tail = resid;
+    if (std::sqrt(tail / total) > tol) return Lmax;
+    for (int c = nc - 1; c >= 0; --c) {
         const double t2 = tail + sig2[(size_t)order[(size_t)c]];
         if (std::sqrt(t2 / total) > tol) break;
         tail = t2;
@@ -388,12 +470,19 @@ int design_rank_tables_q(const std::vector<std::complex<double>>& h, const std::
     std::vector<std::complex<double>> buf((size_t)K);
     for (int c = 0; c < rk; ++c) {
         const int col = order[(size_t)c];
-        for (int p = 0; p < np; ++p) (*a)[(size_t)p * max_rank + c] = V[(size_t)p * np + col];
+        if (compress) {
+            for (int k = 0; k < nc; ++k) {
+                const double v = V[(size_t)k * nc + col];
+                for (int p = 0; p < np; ++p) (*a)[(size_t)p * max_rank + c] += v * Qb[(size_t)k * np + p];
+            }
+        } else {
+            for (int p = 0; p < np; ++p) (*a)[(size_t)p * max_rank + c] = V[(size_t)p * np + col];
+        }
         for (int q = 0; q < nq; ++q) {
             std::fill(buf.begin(), buf.end(), std::complex<double>(0.0, 0.0));
             for (int l = -1; l <= Lmax; ++l)
                 buf[(size_t)((l + K) % K)] =
-                    std::complex<double>(W[(size_t)(q * 2 * nl + l + 1) * np + col], W[(size_t)(q * 2 * nl + nl + l + 1) * np + col]);
+                    std::complex<double>(W[(size_t)(q * 2 * nl + l + 1) * nc + col], W[(size_t)(q * 2 * nl + nl + l + 1) * nc + col]);
             fft_pow2(buf, false);
             std::copy(buf.begin(), buf.end(), b->begin() + ((size_t)q * max_rank + c) * (size_t)K);
         }

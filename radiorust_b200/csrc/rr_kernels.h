@@ -250,6 +250,10 @@ struct FrontArgs {
 };
 bool front_supported(int rank_pad, long long P);
 cudaError_t launch_front(int rank_pad, int n_streams, const FrontArgs& a, cudaStream_t st);
+// k_front_wide (rr_front_wide.cu): the same front end for any P (odd, thousands), 16 or 32 columns; `acoef` is
+// [P][rank_pad]; hist_out and kept rows are not taken
+bool front_wide_supported(int rank_pad, long long P);
+cudaError_t launch_front_wide(int rank_pad, int n_streams, const FrontArgs& a, cudaStream_t st);
 
 // ---- k_fused (rr_fused.cu): front end + low-rate part in one persistent kernel; u stays in shared memory.
 // Rows are numbered from the push's first new row: row r, column p is push sample r*P + p - J0, output r = row r's.
