@@ -17,6 +17,8 @@
 // Reference semantics: transform.rs:333-348 (NCO), filters.rs:240-253, resampling.rs:103-121.  sm_100a.
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "rr_kernels.h"
 #include "rr_pk.cuh"
 #include "rr_poly.cuh"
@@ -77,28 +79,37 @@ __global__ void __launch_bounds__(FW_THREADS) k_front_wide(const FrontArgs a) {
     const long long pos_step = (long long)RS * P;
     float2 pre[LD];
     float preb[2];
-    auto fetch = [&](int k0) {
-        const bool col_ok = k0 + kk_t < P;
+    // a tile whose rows all exist and lie inside the pushed samples takes its whole chunks without a bounds check
+    const bool tile_inside = pos_tile >= 0 && pos_tile + (long long)TILE * P <= len && row0 + TILE <= a.n_rows;
+    auto fetch = [&](int k0, auto checked) {
+        constexpr bool CHECK = decltype(checked)::value;
+        const bool col_ok = !CHECK || k0 + kk_t < P;
+        const float2* src0 = in + pos_t + k0;
 #pragma unroll
         for (int j = 0; j < LD; ++j) {
-            const long long pos = pos_t + j * pos_step + k0;
-            const bool ok = col_ok && (row0 + r_t + RS * j < a.n_rows) && (pos >= 0 ? pos < len : pos >= -hist_len);
-            const float2* src = pos >= 0 ? in + pos : hist_end + pos;
-            pre[j] = make_float2(0.f, 0.f);
-            if (ok) pre[j] = __ldg(src);
+            if (CHECK) {
+                const long long pos = pos_t + j * pos_step + k0;
+                const bool ok = col_ok && (row0 + r_t + RS * j < a.n_rows) && (pos >= 0 ? pos < len : pos >= -hist_len);
+                const float2* src = pos >= 0 ? in + pos : hist_end + pos;
+                pre[j] = make_float2(0.f, 0.f);
+                if (ok) pre[j] = __ldg(src);
+            } else {
+                pre[j] = __ldg(src0 + j * pos_step);
+            }
         }
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int e = tid + j * FW_THREADS;
             const int kk = e / R, c = e % R;
-            preb[j] = (e < KC * R && k0 + kk < P) ? __ldg(a.acoef + (long long)(k0 + kk) * R + c) : 0.f;
+            preb[j] = (e < KC * R && (!CHECK || k0 + kk < P)) ? __ldg(a.acoef + (long long)(k0 + kk) * R + c) : 0.f;
         }
     };
-    auto stash = [&](int buf, int k0) {
+    auto stash = [&](int buf, int k0, auto checked) {
+        constexpr bool CHECK = decltype(checked)::value;
         float2* A = As + buf * TILE * PITCH;
         pc cp(1.f, 0.f);
         if (HAS_NCO) {
-            const float2 c = colph[min(k0 + kk_t, P - 1)];
+            const float2 c = colph[CHECK ? min(k0 + kk_t, P - 1) : k0 + kk_t];
             cp = pc(c.x, c.y);
         }
 #pragma unroll
@@ -108,9 +119,11 @@ __global__ void __launch_bounds__(FW_THREADS) k_front_wide(const FrontArgs a) {
             if (HAS_NCO) {
                 // pushed samples get the column factor; history samples are already mixed: they get the conjugate of the
                 // row phasor the results are multiplied by
-                const float2 rp = rowph[r];
-                const bool hist = pos_t + j * pos_step + k0 < 0;
-                const pc y = hist ? pcmulc(pc(x.x, x.y), pc(rp.x, rp.y)) : pcmul(pc(x.x, x.y), cp);
+                pc y = pcmul(pc(x.x, x.y), cp);
+                if (CHECK && pos_t + j * pos_step + k0 < 0) {
+                    const float2 rp = rowph[r];
+                    y = pcmulc(pc(x.x, x.y), pc(rp.x, rp.y));
+                }
                 x = make_float2(y.x, y.y);
             }
             A[r * PITCH + kk_t] = x;
@@ -122,44 +135,54 @@ __global__ void __launch_bounds__(FW_THREADS) k_front_wide(const FrontArgs a) {
             if (e < KC * R) B[e] = preb[j];
         }
     };
+    auto fetch_any = [&](int k0) {
+        if (tile_inside && k0 + KC <= P) fetch(k0, std::false_type{});
+        else fetch(k0, std::true_type{});
+    };
+    auto stash_any = [&](int buf, int k0) {
+        if (tile_inside && k0 + KC <= P) stash(buf, k0, std::false_type{});
+        else stash(buf, k0, std::true_type{});
+    };
 
     // thread (column group cg, row group rg): rows rg + (FW_THREADS/4)*m, columns cg*TN .. cg*TN + TN-1
     const int cg = tid & 3, rg = tid >> 2;
-    pc acc[TM][TN];
+    // accumulators, samples and (coefficient, coefficient) pairs as packed 64-bit values: a sample is loaded as one, a
+    // coefficient is paired once per step and serves the thread's TM rows
+    unsigned long long acc[TM][TN];
 #pragma unroll
     for (int m = 0; m < TM; ++m)
 #pragma unroll
-        for (int c = 0; c < TN; ++c) acc[m][c] = pc(0.f, 0.f);
+        for (int c = 0; c < TN; ++c) acc[m][c] = 0ull;
 
     const int n_chunks = (P + KC - 1) / KC;
-    fetch(0);
-    stash(0, 0);
+    fetch_any(0);
+    stash_any(0, 0);
     __syncthreads();
 #pragma unroll 1
     for (int ch = 0; ch < n_chunks; ++ch) {
         const int buf = ch & 1;
-        if (ch + 1 < n_chunks) fetch((ch + 1) * KC);
-        const float2* A = As + buf * TILE * PITCH;
+        if (ch + 1 < n_chunks) fetch_any((ch + 1) * KC);
+        const unsigned long long* A = reinterpret_cast<const unsigned long long*>(As + buf * TILE * PITCH) + rg * PITCH;
         const float* B = Bs + buf * KC * R + cg * TN;
 #pragma unroll
         for (int kk = 0; kk < KC; ++kk) {
-            float bf[TN];
+            unsigned long long bp[TN];
 #pragma unroll
             for (int c = 0; c < TN; c += 4) {
                 const float4 v = *reinterpret_cast<const float4*>(B + kk * R + c);
-                bf[c] = v.x;
-                bf[c + 1] = v.y;
-                bf[c + 2] = v.z;
-                bf[c + 3] = v.w;
+                bp[c] = pk2(v.x, v.x);
+                bp[c + 1] = pk2(v.y, v.y);
+                bp[c + 2] = pk2(v.z, v.z);
+                bp[c + 3] = pk2(v.w, v.w);
             }
 #pragma unroll
             for (int m = 0; m < TM; ++m) {
-                const float2 x = A[(rg + (FW_THREADS / 4) * m) * PITCH + kk];
+                const unsigned long long x = A[(FW_THREADS / 4) * m * PITCH + kk];
 #pragma unroll
-                for (int c = 0; c < TN; ++c) acc[m][c] = pfma_s(pc(x.x, x.y), bf[c], acc[m][c]);
+                for (int c = 0; c < TN; ++c) acc[m][c] = f2_fma(x, bp[c], acc[m][c]);
             }
         }
-        if (ch + 1 < n_chunks) stash(buf ^ 1, (ch + 1) * KC);
+        if (ch + 1 < n_chunks) stash_any(buf ^ 1, (ch + 1) * KC);
         __syncthreads();
     }
 
@@ -177,7 +200,7 @@ __global__ void __launch_bounds__(FW_THREADS) k_front_wide(const FrontArgs a) {
         float4* dst = reinterpret_cast<float4*>(u + (long long)v * R + cg * TN);
 #pragma unroll
         for (int c = 0; c < TN; c += 2) {
-            pc y0 = acc[m][c], y1 = acc[m][c + 1];
+            pc y0 = upk2(acc[m][c]), y1 = upk2(acc[m][c + 1]);
             if (HAS_NCO) {
                 y0 = pcmul(y0, ph);
                 y1 = pcmul(y1, ph);
