@@ -31,7 +31,7 @@ constexpr int FW_THREADS = 256;
 constexpr int FW_KC = 16;           // samples per chunk
 constexpr int FW_PITCH = FW_KC + 1; // tile row pitch in samples: the eight rows a warp reads at once lie on distinct banks
 
-template <int R> constexpr int fw_tm() { return R == 16 ? 4 : 2; }          // rows per thread
+template <int R> constexpr int fw_tm() { return 2; }                        // rows per thread
 template <int R> constexpr int fw_tile() { return (FW_THREADS / 4) * fw_tm<R>(); }  // rows per CTA (four column groups)
 template <int R> constexpr size_t fw_smem(int P) {
     return (size_t)2 * fw_tile<R>() * FW_PITCH * 8 + (size_t)2 * FW_KC * R * 4 + (size_t)fw_tile<R>() * 8 + (size_t)P * 8;
