@@ -1702,7 +1702,7 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
                         f.hist_fused_jlo = -1;
                         f.hist_fused_jfirst = 0;
                         const long long hfrom = a.len - 2 * a.n, hstart = std::max<long long>(hfrom, 0);
-                        if (!ds.frontq_wide && cover_lo <= hstart && cover_hi > hstart) {
+                        if (cover_lo <= hstart && cover_hi > hstart) {
                             fa.hist_out = f.hist2[f.hist_cur ^ 1].p;
                             fa.hist_from = hfrom;
                             fa.hist_stride = 2 * a.n;

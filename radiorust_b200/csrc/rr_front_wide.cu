@@ -29,7 +29,8 @@ namespace {
 
 constexpr int FW_THREADS = 256;
 constexpr int FW_KC = 16;           // samples per chunk
-constexpr int FW_PITCH = FW_KC + 1; // tile row pitch in samples: the eight rows a warp reads at once lie on distinct banks
+constexpr int FW_PITCH = FW_KC + 2; // tile row pitch in samples (144 B = 9 x 16 B): the eight rows a warp reads at once, two samples
+                                    // of a row per 16-byte load, lie on distinct banks
 
 template <int R> constexpr int fw_tm() { return 2; }                        // rows per thread
 template <int R> constexpr int fw_tile() { return (FW_THREADS / 4) * fw_tm<R>(); }  // rows per CTA (four column groups)
@@ -81,6 +82,9 @@ __global__ void __launch_bounds__(FW_THREADS) k_front_wide(const FrontArgs a) {
     float preb[2];
     // a tile whose rows all exist and lie inside the pushed samples takes its whole chunks without a bounds check
     const bool tile_inside = pos_tile >= 0 && pos_tile + (long long)TILE * P <= len && row0 + TILE <= a.n_rows;
+    // the Filter's next history = the fully mixed samples at push offsets >= hist_from: tiles that reach there write them
+    float2* __restrict__ hist_o = a.hist_out ? reinterpret_cast<float2*>(a.hist_out) + (long long)s * a.hist_stride : nullptr;
+    const bool tile_hist = hist_o != nullptr && pos_tile + (long long)TILE * P > a.hist_from;
     auto fetch = [&](int k0, auto checked) {
         constexpr bool CHECK = decltype(checked)::value;
         const bool col_ok = !CHECK || k0 + kk_t < P;
@@ -127,6 +131,18 @@ __global__ void __launch_bounds__(FW_THREADS) k_front_wide(const FrontArgs a) {
                 x = make_float2(y.x, y.y);
             }
             A[r * PITCH + kk_t] = x;
+            if (tile_hist) {
+                const long long pos = pos_t + j * pos_step + k0;
+                if (pos >= a.hist_from && pos >= 0 && pos < len && (!CHECK || (k0 + kk_t < P && row0 + r < a.n_rows))) {
+                    float2 h = x;
+                    if (HAS_NCO) {
+                        const float2 rp = rowph[r];
+                        const pc y = pcmul(pc(x.x, x.y), pc(rp.x, rp.y));
+                        h = make_float2(y.x, y.y);
+                    }
+                    hist_o[pos - a.hist_from] = h;
+                }
+            }
         }
         float* B = Bs + buf * KC * R;
 #pragma unroll
@@ -165,21 +181,28 @@ __global__ void __launch_bounds__(FW_THREADS) k_front_wide(const FrontArgs a) {
         const unsigned long long* A = reinterpret_cast<const unsigned long long*>(As + buf * TILE * PITCH) + rg * PITCH;
         const float* B = Bs + buf * KC * R + cg * TN;
 #pragma unroll
-        for (int kk = 0; kk < KC; ++kk) {
-            unsigned long long bp[TN];
+        for (int kk = 0; kk < KC; kk += 2) {
+            // two samples of a row per 16-byte load
+            ulonglong2 xx[TM];
 #pragma unroll
-            for (int c = 0; c < TN; c += 4) {
-                const float4 v = *reinterpret_cast<const float4*>(B + kk * R + c);
-                bp[c] = pk2(v.x, v.x);
-                bp[c + 1] = pk2(v.y, v.y);
-                bp[c + 2] = pk2(v.z, v.z);
-                bp[c + 3] = pk2(v.w, v.w);
-            }
+            for (int m = 0; m < TM; ++m) xx[m] = *reinterpret_cast<const ulonglong2*>(A + (FW_THREADS / 4) * m * PITCH + kk);
 #pragma unroll
-            for (int m = 0; m < TM; ++m) {
-                const unsigned long long x = A[(FW_THREADS / 4) * m * PITCH + kk];
+            for (int h = 0; h < 2; ++h) {
+                unsigned long long bp[TN];
 #pragma unroll
-                for (int c = 0; c < TN; ++c) acc[m][c] = f2_fma(x, bp[c], acc[m][c]);
+                for (int c = 0; c < TN; c += 4) {
+                    const float4 v = *reinterpret_cast<const float4*>(B + (kk + h) * R + c);
+                    bp[c] = pk2(v.x, v.x);
+                    bp[c + 1] = pk2(v.y, v.y);
+                    bp[c + 2] = pk2(v.z, v.z);
+                    bp[c + 3] = pk2(v.w, v.w);
+                }
+#pragma unroll
+                for (int m = 0; m < TM; ++m) {
+                    const unsigned long long x = h ? xx[m].y : xx[m].x;
+#pragma unroll
+                    for (int c = 0; c < TN; ++c) acc[m][c] = f2_fma(x, bp[c], acc[m][c]);
+                }
             }
         }
         if (ch + 1 < n_chunks) stash_any(buf ^ 1, (ch + 1) * KC);
@@ -226,14 +249,14 @@ template <int R> cudaError_t launch_wide_r(int n_streams, const FrontArgs& a, cu
 
 }  // namespace
 
-// `acoef` of FrontArgs is [P][rank_pad] here (a_c[p] at p*rank_pad + c); hist_out / kept rows are not taken
+// `acoef` of FrontArgs is [P][rank_pad] here (a_c[p] at p*rank_pad + c); kept rows are not taken
 bool front_wide_supported(int rank_pad, long long P) {
     if (rank_pad != 16 && rank_pad != 32) return false;
     if (P < 2 || P > 16384) return false;
     return (rank_pad == 16 ? fw_smem<16>((int)P) : fw_smem<32>((int)P)) <= (size_t)200 * 1024;
 }
 cudaError_t launch_front_wide(int rank_pad, int n_streams, const FrontArgs& a, cudaStream_t st) {
-    if (!front_wide_supported(rank_pad, a.P) || a.n_rows < 1 || n_streams > 65535 || a.hist_out || a.kept_rows) return cudaErrorNotSupported;
+    if (!front_wide_supported(rank_pad, a.P) || a.n_rows < 1 || n_streams > 65535 || a.kept_rows) return cudaErrorNotSupported;
     if (((uintptr_t)a.u % 16) != 0 || (a.u_stride % 2) != 0) return cudaErrorInvalidValue;
     return rank_pad == 16 ? launch_wide_r<16>(n_streams, a, st) : launch_wide_r<32>(n_streams, a, st);
 }

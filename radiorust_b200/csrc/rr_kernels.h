@@ -251,7 +251,7 @@ struct FrontArgs {
 bool front_supported(int rank_pad, long long P);
 cudaError_t launch_front(int rank_pad, int n_streams, const FrontArgs& a, cudaStream_t st);
 // k_front_wide (rr_front_wide.cu): the same front end for any P (odd, thousands), 16 or 32 columns; `acoef` is
-// [P][rank_pad]; hist_out and kept rows are not taken
+// [P][rank_pad]; kept rows are not taken
 bool front_wide_supported(int rank_pad, long long P);
 cudaError_t launch_front_wide(int rank_pad, int n_streams, const FrontArgs& a, cudaStream_t st);
 
