@@ -206,3 +206,17 @@ def test_filter_design_at_any_chunk_length(lib, n):
     assert rc == 0
     want = orc.design_filter_response(f, orc.Kaiser.with_null_at_bin(2.0), 48000.0, n, "f64")
     assert np.linalg.norm(out.view(np.complex128) - want) <= 1e-13 * np.linalg.norm(want)
+
+
+def test_fused_filter_rank_many_branches(lib):
+    """BASELINE config 2 (in/out = 1250/3, n = 65536): with P in the thousands the factorisation first takes the row space
+    by pivoted Gram-Schmidt (seconds instead of minutes) and must still reproduce the full tables to below f32 rounding."""
+    import time
+
+    t0 = time.time()
+    rc, rank, disc, err = _fused_rank(lib, orc.lowpass(3000.0), 20_000_000.0, 65536, 48000.0, 6000.0, 2.0e-8, 32)
+    assert rc == 0
+    assert 17 <= rank <= 32, rank
+    assert disc <= 2.0e-8
+    assert 0.0 <= err <= 2.5e-8, err
+    assert time.time() - t0 < 60.0
