@@ -277,8 +277,7 @@ int rr_chain_copy_out_async(rr_chain* chain, void* dst_dev, size_t dst_stride, c
  * sets the default to off; RR_DISABLE_FRONT=1 / RR_DISABLE_POLY2=1 step back to
  * k_poly2 on all branches / to k_poly (RR_DISABLE_FRONT also switches off the shared
  * front end of rates with several output phases).  Long Filters (2n = 2^15 .. 2^20):
- * RR_BIG_OS_LEGACY=1 keeps the round-1 four-step kernels, RR_LONG_OS_LANES=k /
- * RR_LONG_OS_GROUP_MB=m send launch groups of m MiB of scratch round k side streams. */
+ * RR_BIG_OS_LEGACY=1 keeps the round-1 four-step kernels. */
 int rr_chain_set_fast_path(rr_chain* chain, int enable);
 /* Measurement aid: while enabled, CUDA events on the chain's stream bracket the
  * dominant kernel of every push (no synchronisation is added).

@@ -294,12 +294,6 @@ struct rr_chain {
     bool allow_poly = true;  // rr_chain_set_fast_path
     bool allow_poly2 = true; // RR_DISABLE_POLY2=1: keep the generic polyphase kernel (k_poly) for f32 too
     size_t big_os_scratch_bytes = (size_t)2 << 30;  // RR_BIG_OS_SCRATCH_MB
-    // long Filters (rr_long_os.cu, three kernels per launch group): groups of long_os_group_bytes of scratch go round
-    // long_os_lanes side streams, so that the groups' scratch stays in L2 while another group's kernels fill the gaps
-    size_t long_os_group_bytes = (size_t)24 << 20;  // RR_LONG_OS_GROUP_MB
-    int long_os_lanes = 1;                          // RR_LONG_OS_LANES (1: everything on the chain's stream, one launch group)
-    cudaStream_t lane_stream[8] = {};
-    cudaEvent_t lane_fork = nullptr, lane_join[8] = {};
     bool allow_sab = true;    // RR_DISABLE_SAB=1: short pushes keep one low-rate block (and inverse round) per stream
     bool allow_ucache = true; // RR_DISABLE_UCACHE=1: recompute the history rows of u from hist2 in every push
     bool allow_front = true; // RR_DISABLE_FRONT=1: k_poly2 on all P branches instead of the rank-reduced front end
@@ -977,60 +971,11 @@ int run_os(rr_chain* c, Stage& s, const FilterIo& io, size_t k, bool fih, void* 
     const size_t n_blocks = k - first;
     if (n_blocks == 0) return RR_OK;
     const size_t esz = 2 * sizeof(T);
-    if (rr::long_os_supported((int)n) && c->long_os_lanes > 1) {
-        // the three streaming kernels over launch groups whose scratch fits L2, the groups going round side streams: the
-        // scratch of a group is read back while it is still in L2, and the kernels of the other lanes cover a lane's
-        // launch gaps and tails.  Blocks of one stream stay together (the older half of a window is the previous block's)
-        const int lanes = c->long_os_lanes;
-        size_t gmax = c->long_os_group_bytes / (N * esz);
-        if (gmax < 1) gmax = 1;
-        const size_t per_launch = std::min(n_blocks, gmax);
-        const size_t sg = std::min<size_t>((size_t)S, std::max<size_t>(1, gmax / per_launch));
-        const size_t slot_elems = sg * per_launch * N;
-        RR_TRY(s.big_scratch.ensure((size_t)lanes * slot_elems * esz));
-        if (!c->lane_fork) RR_CUDA(cudaEventCreateWithFlags(&c->lane_fork, cudaEventDisableTiming));
-        for (int k = 0; k < lanes; ++k) {
-            if (!c->lane_stream[k]) RR_CUDA(cudaStreamCreateWithFlags(&c->lane_stream[k], cudaStreamNonBlocking));
-            if (!c->lane_join[k]) RR_CUDA(cudaEventCreateWithFlags(&c->lane_join[k], cudaEventDisableTiming));
-        }
-        const int t__ = c->timing_begin();
-        RR_CUDA(cudaEventRecord(c->lane_fork, c->stream));
-        for (int k = 0; k < lanes; ++k) RR_CUDA(cudaStreamWaitEvent(c->lane_stream[k], c->lane_fork, 0));
-        size_t item = 0;
-        for (size_t s0 = 0; s0 < (size_t)S; s0 += sg) {
-            const int sn = (int)std::min(sg, (size_t)S - s0);
-            for (size_t b0 = 0; b0 < n_blocks; b0 += per_launch, ++item) {
-                const size_t nb = std::min(per_launch, n_blocks - b0);
-                const int lane = (int)(item % (size_t)lanes);
-                rr::BigOsArgs<T> a{};
-                a.in = (const char*)src + s0 * (size_t)src_stride * esz;
-                a.in_stride = src_stride;
-                a.hist = hist_newer + s0 * (size_t)hist_stride * esz;
-                a.hist_stride = hist_stride;
-                a.first_chunk = (int)(first + b0);
-                a.n_blocks = (int)nb;
-                a.scratch = (char*)s.big_scratch.p + (size_t)lane * slot_elems * esz;
-                a.hbig = s.big_h.p;
-                a.twN = s.tw.p;
-                a.twA = s.big_twA.p;
-                a.twB = s.big_twB.p;
-                a.twC = s.big_twC.p;
-                a.out = (char*)dst + (s0 * (size_t)dst_stride + b0 * n) * esz;
-                a.out_stride = dst_stride;
-                RR_LAUNCH(3, rr::launch_big_os<T>((int)n, sn, a, c->lane_stream[lane]));
-            }
-        }
-        for (int k = 0; k < lanes; ++k) {
-            RR_CUDA(cudaEventRecord(c->lane_join[k], c->lane_stream[k]));
-            RR_CUDA(cudaStreamWaitEvent(c->stream, c->lane_join[k], 0));
-        }
-        if (t__) c->timing_end("k_long_os(3 kernels x groups)");
-        return RR_OK;
-    }
     // the three kernels of a launch group exchange their blocks through `scratch`.  Measured (256 x 8 blocks of 2^17
     // points f32, 16 x 4 blocks of 2^20 points f64): groups small enough to keep the scratch in L2 (24-96 MiB) are
-    // 15-30 % SLOWER than one large launch on ONE stream -- small launches, and their tails, cost more than the L2 hits
-    // save -- so the bound only limits the memory taken (2 GiB)
+    // 15-30 % SLOWER than one large launch on one stream -- small launches, and their tails, cost more than the L2 hits
+    // save -- and level with it when the groups go round 2-6 side streams (commit 2f092e5 has that form); the kernels sit
+    // on the fp32 / fp64 pipe right behind the HBM bound.  So the bound only limits the memory taken (2 GiB)
     size_t max_blocks = c->big_os_scratch_bytes / (N * 2 * sizeof(T));
     if (max_blocks < 1) max_blocks = 1;
     const size_t sg = std::min<size_t>((size_t)S, max_blocks);  // streams per launch group
@@ -2627,8 +2572,6 @@ int rr_chain_create(rr_ctx* ctx, const rr_chain_desc* desc, rr_chain** out) {
     if (const char* e = std::getenv("RR_DISABLE_UCACHE")) c->allow_ucache = !(e[0] == '1');
     if (const char* e = std::getenv("RR_DISABLE_SAB")) c->allow_sab = !(e[0] == '1');
     if (const char* e = std::getenv("RR_BIG_OS_SCRATCH_MB")) c->big_os_scratch_bytes = (size_t)std::max(1, std::atoi(e)) << 20;
-    if (const char* e = std::getenv("RR_LONG_OS_GROUP_MB")) c->long_os_group_bytes = (size_t)std::max(1, std::atoi(e)) << 20;
-    if (const char* e = std::getenv("RR_LONG_OS_LANES")) c->long_os_lanes = std::min(8, std::max(1, std::atoi(e)));
     RR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     *out = c.release();
     return RR_OK;
@@ -2657,11 +2600,6 @@ int rr_chain_destroy(rr_chain* c) {
     }
     for (cudaEvent_t e : c->evs) cudaEventDestroy(e);
     if (c->ev_copy) cudaEventDestroy(c->ev_copy);
-    for (int k = 0; k < 8; ++k) {
-        if (c->lane_join[k]) cudaEventDestroy(c->lane_join[k]);
-        if (c->lane_stream[k]) cudaStreamDestroy(c->lane_stream[k]);
-    }
-    if (c->lane_fork) cudaEventDestroy(c->lane_fork);
     if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     if (c->stream) cudaStreamDestroy(c->stream);

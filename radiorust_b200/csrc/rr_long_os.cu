@@ -19,7 +19,7 @@
 // The scratch streams through HBM (11 point transfers per output sample).  The column kernels run at 71-75 % of the DRAM
 // peak, the row kernel at 61 % with the fp32 pipe 66 % busy (two radix-32 passes each way: ~85 flop per point and
 // direction); both floors lie within 1.5 x of each other, so no single change moves the path far.  Measured and not kept:
-// launch groups whose scratch fits L2 going round side streams (rr_chain.cu keeps the switch), the three phases in one
+// launch groups whose scratch fits L2 going round side streams (commit 2f092e5), the three phases in one
 // persistent kernel with teams of CTAs and team barriers (commit 71727ba), the row kernel's next row prefetched by a bulk
 // copy (fewer warps fit; 854 -> 1020 us).  Other sizes keep rr_big_os.cu's kernels.  sm_100a.
 #include <cstdlib>
