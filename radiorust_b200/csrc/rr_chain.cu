@@ -1676,7 +1676,10 @@ int run_filter_down(rr_chain* c, Stage& f, Stage& ds, const FilterIo& io, const 
                         b.m_hi = a.m_hi;
                         b.I_lo = I_first;
                         b.n_blocks = (int)((I_last - I_first) / b.V + 1);
-                        int nbpc = std::max(1, GQ / (int)Qq);
+                        // blocks per CTA: as many as shared memory holds (their parked spectra) while the grid stays at two
+                        // CTAs per SM -- the per-CTA tables are built once and the inverse rounds fill up (measured on C1, 7
+                        // blocks per stream: 1.93 / 1.74 / 1.66 ms with 1 / 2 / 7 blocks per CTA)
+                        int nbpc = b.n_blocks;
                         while (nbpc > 1 && rr::poly_smem_bytes<float>(ds.poly_K, (int)Qq, GQ, nbpc) > (size_t)200 * 1024) --nbpc;
                         while (nbpc > 1 && (long long)S * ((b.n_blocks + nbpc - 1) / nbpc) < 2LL * c->ctx->sm_count) --nbpc;
                         const int nsb = (b.n_blocks + nbpc - 1) / nbpc;
