@@ -343,6 +343,80 @@ __global__ void __launch_bounds__(256) k_upsample_tiled(const cx<T>* __restrict_
     }
 }
 
+// Integer interpolation factors, one output PHASE per thread: output q = p*Q + r is sum_k ir[r + k*Q] * x[p - k],
+// k < NT = ceil(L / Q).  Thread (segment, r) keeps its phase's NT taps in registers and walks UPP consecutive inputs p of
+// its segment: per output one new sample from shared memory (the same address for all lanes of a segment), NT shifts of
+// the sample window (register renaming: the walk is unrolled) and 2*NT multiply-adds -- against one sample load, one tap
+// load and index arithmetic PER TAP in the kernel above.  Same sums in the same order (inputs ascending: k descending,
+// starting from the carried partial sum); taps past the end of ir and inputs outside the push enter as exact zeros.
+constexpr int UPP = 8;  // inputs a thread walks
+template <typename T, int NT>
+__global__ void __launch_bounds__(256) k_upsample_phase(const cx<T>* __restrict__ in, long long in_stride, long long len,
+                                                        const cx<T>* __restrict__ acc_in, cx<T>* __restrict__ acc_out,
+                                                        const T* __restrict__ ir, int L, int Q, int segs, long long j0, long long m0,
+                                                        long long n_out, cx<T>* __restrict__ out, long long out_stride,
+                                                        cx<T>* __restrict__ out2, long long out2_stride, long long out_split) {
+    extern __shared__ __align__(16) unsigned char up_smem[];
+    cx<T>* xs = reinterpret_cast<cx<T>*>(up_smem);  // inputs p_t0 - NT + 1 ... p_t0 + segs*UPP - 1
+    const int s = blockIdx.y;
+    const cx<T>* src = in + (long long)s * in_stride;
+    const long long p_base = m0 / Q;  // input of the push's first output
+    const long long p_t0 = p_base + (long long)blockIdx.x * (segs * UPP);
+    const int n_x = segs * UPP + NT - 1;
+    for (int i = threadIdx.x; i < n_x; i += blockDim.x) {
+        const long long p = p_t0 - (NT - 1) + i;
+        xs[i] = (p >= j0 && p < j0 + len) ? ld_cx(&src[p - j0]) : cx<T>((T)0, (T)0);
+    }
+    const int seg = threadIdx.x / Q, r = threadIdx.x - seg * Q;
+    T h[NT];
+#pragma unroll
+    for (int k = 0; k < NT; ++k) h[k] = (seg < segs && r + k * Q < L) ? ir[r + k * Q] : (T)0;
+    __syncthreads();
+    if (seg >= segs) return;
+    const int x0 = seg * UPP;  // xs index of input (first input of the segment) - (NT - 1)
+    cx<T> w[NT];               // w[k] = x[p - k]
+#pragma unroll
+    for (int k = 1; k < NT; ++k) w[k] = xs[x0 + NT - 1 - k];
+    const long long total = n_out + L;
+#pragma unroll
+    for (int i = 0; i < UPP; ++i) {
+        w[0] = xs[x0 + NT - 1 + i];
+        const long long q = (p_t0 + x0 + i) * Q + r;
+        const long long o = q - m0;
+        if (o >= 0 && o < total) {
+            cx<T> acc = (o < L) ? ld_cx(&acc_in[(long long)s * L + o]) : cx<T>((T)0, (T)0);
+#pragma unroll
+            for (int k = NT - 1; k >= 0; --k) {
+                acc.x = fma(w[k].x, h[k], acc.x);
+                acc.y = fma(w[k].y, h[k], acc.y);
+            }
+            if (o < n_out) {
+                if (out2 != nullptr && o >= out_split) st_cx(&out2[(long long)s * out2_stride + (o - out_split)], acc);
+                else st_cx(&out[(long long)s * out_stride + o], acc);
+            } else {
+                st_cx(&acc_out[(long long)s * L + (o - n_out)], acc);
+            }
+        }
+#pragma unroll
+        for (int k = NT - 1; k >= 1; --k) w[k] = w[k - 1];
+    }
+}
+
+template <typename T, int NT>
+cudaError_t launch_upsample_phase(const void* in, long long in_stride, long long len, const void* acc_in, void* acc_out, const T* ir, int L,
+                                  RateState rate, long long n_out, void* out, long long out_stride, int n_streams, cudaStream_t st, void* out2,
+                                  long long out2_stride, long long out_split) {
+    const int Q = (int)rate.Q, segs = 256 / Q;
+    const long long p_base = rate.m0 / Q, p_last = (rate.m0 + n_out + L - 1) / Q;
+    const long long tiles = (p_last - p_base) / (segs * UPP) + 1;
+    const size_t smem = (size_t)(segs * UPP + NT - 1) * 2 * sizeof(T);
+    dim3 grid((unsigned)tiles, (unsigned)n_streams);
+    k_upsample_phase<T, NT><<<grid, segs * Q, smem, st>>>(reinterpret_cast<const cx<T>*>(in), in_stride, len, reinterpret_cast<const cx<T>*>(acc_in),
+                                                          reinterpret_cast<cx<T>*>(acc_out), ir, L, Q, segs, rate.j0, rate.m0, n_out,
+                                                          reinterpret_cast<cx<T>*>(out), out_stride, reinterpret_cast<cx<T>*>(out2), out2_stride, out_split);
+    return cudaGetLastError();
+}
+
 template <typename T> bool upsample_tiled_supported(RateState rate, int L) {
     if (!(rate.P == 1 && rate.Q >= 1 && rate.Q < (1LL << 30) && L <= 8192)) return false;
     const int x_cap = (int)(UP_TILE / rate.Q + L / rate.Q + 4);
@@ -353,6 +427,14 @@ template <typename T>
 cudaError_t launch_upsample(const void* in, long long in_stride, long long len, const void* acc_in, void* acc_out,
                             const T* ir, int L, RateState rate, long long n_out, void* out, long long out_stride,
                             int n_streams, cudaStream_t st, void* out2, long long out2_stride, long long out_split) {
+    if (rate.P == 1 && rate.Q >= 8 && rate.Q <= 256 && L >= 1 && (L + rate.Q - 1) / rate.Q <= 16 && n_out + L < (1LL << 40)) {
+        // a phase per thread, its taps in registers (rates like 48 kS/s -> 2.4 MS/s: Q = 50, 11 taps per phase)
+        const int nt = (int)((L + rate.Q - 1) / rate.Q);
+        if (nt <= 4) return launch_upsample_phase<T, 4>(in, in_stride, len, acc_in, acc_out, ir, L, rate, n_out, out, out_stride, n_streams, st, out2, out2_stride, out_split);
+        if (nt <= 8) return launch_upsample_phase<T, 8>(in, in_stride, len, acc_in, acc_out, ir, L, rate, n_out, out, out_stride, n_streams, st, out2, out2_stride, out_split);
+        if (nt <= 12) return launch_upsample_phase<T, 12>(in, in_stride, len, acc_in, acc_out, ir, L, rate, n_out, out, out_stride, n_streams, st, out2, out2_stride, out_split);
+        return launch_upsample_phase<T, 16>(in, in_stride, len, acc_in, acc_out, ir, L, rate, n_out, out, out_stride, n_streams, st, out2, out2_stride, out_split);
+    }
     if (rate.P == 1 && rate.Q >= 1 && rate.Q < (1LL << 30) && L <= 8192) {
         // inputs per tile: at most UP_TILE / Q + L / Q + 2
         const int x_cap = (int)(UP_TILE / rate.Q + L / rate.Q + 4);
