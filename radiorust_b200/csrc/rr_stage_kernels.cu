@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(256) k_upsample_tiled(const cx<T>* __restrict_
 // the sample window (register renaming: the walk is unrolled) and 2*NT multiply-adds -- against one sample load, one tap
 // load and index arithmetic PER TAP in the kernel above.  Same sums in the same order (inputs ascending: k descending,
 // starting from the carried partial sum); taps past the end of ir and inputs outside the push enter as exact zeros.
-constexpr int UPP = 8;  // inputs a thread walks
+constexpr int UPP = 32;  // inputs a thread walks
 template <typename T, int NT>
 __global__ void __launch_bounds__(256) k_upsample_phase(const cx<T>* __restrict__ in, long long in_stride, long long len,
                                                         const cx<T>* __restrict__ acc_in, cx<T>* __restrict__ acc_out,

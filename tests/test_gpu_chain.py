@@ -403,6 +403,26 @@ def test_front_end_shared_by_output_phases(ctx, sr, out_rate, ocl, pushes):
         assert orc.rel_l2(got[s], want) <= TOL["f32"]
 
 
+@pytest.mark.parametrize("flt", ["f32", "f64"])
+@pytest.mark.parametrize("sr,out_rate,bw,n", [
+    (48000.0, 2_400_000.0, 20000.0, 1024),   # C5: factor 50, 11 taps per phase (k_upsample_phase)
+    (48000.0, 384000.0, 20000.0, 512),       # factor 8
+    (12000.0, 3_072_000.0, 5000.0, 256),     # factor 256
+    (16000.0, 48000.0, 7000.0, 2048),        # factor 3: the tiled kernel
+    (8000.0, 2_400_000.0, 3000.0, 128),      # factor 300: the tiled kernel
+])
+def test_upsampler_integer_factors(ctx, flt, sr, out_rate, bw, n):
+    """Upsampler at integer interpolation factors, pushes of one, three and two chunks (the carried partial sums cross
+    the push boundaries), two streams."""
+    import radiorust_b200 as rr
+
+    ocl = 4096
+    x = np.stack([noise(5150 + int(out_rate / sr) + s, 6 * n, flt) for s in range(2)])
+    got, want, plan = run_both(ctx, [rr.Upsampler(ocl, out_rate, bw)], flt, sr, x, n, pushes=[1, 3, 2])
+    assert "upsample" in plan
+    check(got, want, flt)
+
+
 def test_poly_filter_down_without_nco_multi_stream(ctx):
     import radiorust_b200 as rr
 
