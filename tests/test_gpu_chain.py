@@ -423,6 +423,18 @@ def test_upsampler_integer_factors(ctx, flt, sr, out_rate, bw, n):
     check(got, want, flt)
 
 
+def test_wide_front_end_without_nco(ctx):
+    """in/out = 1250/3 without a FreqShifter in front: k_front_wide<32> with no NCO (rank 21), two streams."""
+    import radiorust_b200 as rr
+
+    sr, n = 20_000_000.0, 65536
+    x = np.stack([noise(777 + s, 6 * n, "f32") for s in range(2)])
+    stages = [rr.Filter.new(orc.lowpass(3000.0)), rr.Downsampler(128, 48000.0, 6000.0)]
+    got, want, plan = run_both(ctx, stages, "f32", sr, x, n, pushes=[3, 1, 2])
+    assert "front+poly[" in plan, plan
+    check(got, want, "f32")
+
+
 def test_poly_filter_down_without_nco_multi_stream(ctx):
     import radiorust_b200 as rr
 
