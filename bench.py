@@ -348,6 +348,9 @@ def other_configs(torch, rr, ctx, peak):
         lambda: _spot_check(rr, ctx, st2, lambda: [orc.FreqShifter("f32", 1.0, 1_234_567.0), orc.Filter.new("f32", orc.lowpass(3000.0)),
                                                    orc.Downsampler("f32", 128, 48000.0, 6000.0)], "f32", sr, n, 5,
                             orc.synth_noise(20260000 + 200000, 5 * n, "f32")))
+    # ... and 256 replicas: the front end's 128-row tiles come in whole waves of CTAs only with more streams (64 x 7 tiles
+    # = 448 CTAs on 296 resident ones is two rounds, the second half empty)
+    run("C2_batched_256", "f32", sr, n, 256, 16, st2, 8.0 * (1 + 48000.0 / sr), lambda: (out["C2_batched"]["rel_l2"], out["C2_batched"]["spot_check_plan"]))
     # C4: 256 FM stations at 10 MS/s, Filter -> FmDemod -> de-emphasis -> Downsampler(48 kS/s), L = 7500
     sr, n = 10_000_000.0, 65536
     de = deemph_resp(50e-6)
