@@ -292,7 +292,9 @@ const char* rr_chain_kernel_breakdown(rr_chain* chain);
 /* raw cudaStream_t of the chain (for event timing by the caller) */
 void* rr_chain_cuda_stream(rr_chain* chain);
 /* name of the execution plan chosen at the last push (diagnostics), e.g.
- * "fused_os[nco+filter+down]" or "freqshift|big_os|downsample" */
+ * "nco+fused[filter+down]" (k_fused), "nco+front+poly2[filter+down]" (k_front + k_poly2),
+ * "nco+front+poly[filter+down]" (several output phases: k_front / k_front_wide + k_poly on u),
+ * "fused_os[nco+filter+down]" or "big_os|fmdemod|front+poly[filter+down]" */
 const char* rr_chain_plan(rr_chain* chain);
 
 #ifdef __cplusplus
