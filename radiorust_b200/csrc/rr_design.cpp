@@ -205,100 +205,6 @@ int design_poly_tables(const std::vector<std::complex<double>>& h, const std::ve
     return Lmax;
 }
 
-int design_rank_tables(const std::vector<std::complex<double>>& h, const std::vector<double>& ir, long long P, int K, double tol,
-                       int max_rank, int* rank, std::vector<double>* a, std::vector<std::complex<double>>* b, double* discarded) {
-    const long long n = (long long)h.size(), L = (long long)ir.size();
-    const long long Lg = n + L - 1;
-    std::vector<std::complex<double>> g((size_t)Lg, std::complex<double>(0.0, 0.0));
-    for (long long v = 0; v < L; ++v) {
-        const double c = ir[(size_t)(L - 1 - v)];
-        if (c == 0.0) continue;
-        std::complex<double>* dst = g.data() + v;
-        for (long long m = 0; m < n; ++m) dst[m] += c * h[(size_t)m];
-    }
-    const int Lmax = (int)((Lg - 1) / P);
-    const int nl = Lmax + 1, np = (int)P;
-    *rank = 0;
-    if (nl >= K) return Lmax;
-    // W = [Re M^T ; Im M^T]: 2*nl rows, P columns (column p = branch p); Hestenes rotations make the
-    // columns orthogonal, V accumulates them: W_final = W * V, column c = (b_c re | b_c im), a_c = V[:, c]
-    const int rows = 2 * nl;
-    std::vector<double> W((size_t)rows * np, 0.0), V((size_t)np * np, 0.0);
-    for (int p = 0; p < np; ++p) {
-        V[(size_t)p * np + p] = 1.0;
-        for (int l = 0; l < nl; ++l) {
-            const long long idx = P - 1 - p + (long long)l * P;
-            if (idx < 0 || idx >= Lg) continue;
-            W[(size_t)l * np + p] = g[(size_t)idx].real();
-            W[(size_t)(nl + l) * np + p] = g[(size_t)idx].imag();
-        }
-    }
-    double total = 0.0;
-    for (double w : W) total += w * w;
-    if (!(total > 0.0)) return Lmax;
-    for (int sweep = 0; sweep < 60; ++sweep) {
-        double off = 0.0;
-        for (int i = 0; i < np - 1; ++i)
-            for (int j = i + 1; j < np; ++j) {
-                double aii = 0.0, ajj = 0.0, aij = 0.0;
-                for (int r = 0; r < rows; ++r) {
-                    const double wi = W[(size_t)r * np + i], wj = W[(size_t)r * np + j];
-                    aii += wi * wi;
-                    ajj += wj * wj;
-                    aij += wi * wj;
-                }
-                if (aij == 0.0 || std::fabs(aij) <= 1e-17 * std::sqrt(aii * ajj)) continue;
-                off = std::max(off, std::fabs(aij) / std::sqrt(aii * ajj));
-                const double zeta = (ajj - aii) / (2.0 * aij);
-                const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
-                const double cs = 1.0 / std::sqrt(1.0 + t * t), sn = cs * t;
-                for (int r = 0; r < rows; ++r) {
-                    const double wi = W[(size_t)r * np + i], wj = W[(size_t)r * np + j];
-                    W[(size_t)r * np + i] = cs * wi - sn * wj;
-                    W[(size_t)r * np + j] = sn * wi + cs * wj;
-                }
-                for (int r = 0; r < np; ++r) {
-                    const double vi = V[(size_t)r * np + i], vj = V[(size_t)r * np + j];
-                    V[(size_t)r * np + i] = cs * vi - sn * vj;
-                    V[(size_t)r * np + j] = sn * vi + cs * vj;
-                }
-            }
-        if (off < 1e-15) break;
-    }
-    std::vector<double> sig2((size_t)np, 0.0);
-    std::vector<int> order((size_t)np);
-    for (int c = 0; c < np; ++c) {
-        order[(size_t)c] = c;
-        for (int r = 0; r < rows; ++r) sig2[(size_t)c] += W[(size_t)r * np + c] * W[(size_t)r * np + c];
-    }
-    std::sort(order.begin(), order.end(), [&](int x, int y) { return sig2[(size_t)x] > sig2[(size_t)y]; });
-    // smallest rank whose tail is below tol
-    int rk = np;
-    double tail = 0.0;
-    for (int c = np - 1; c >= 0; --c) {
-        const double t2 = tail + sig2[(size_t)order[(size_t)c]];
-        if (std::sqrt(t2 / total) > tol) break;
-        tail = t2;
-        rk = c;
-    }
-    if (discarded) *discarded = std::sqrt(tail / total);
-    if (rk < 1) rk = 1;
-    if (rk > max_rank) return Lmax;
-    *rank = rk;
-    a->assign((size_t)np * (size_t)max_rank, 0.0);
-    b->assign((size_t)max_rank * (size_t)K, std::complex<double>(0.0, 0.0));
-    std::vector<std::complex<double>> buf((size_t)K);
-    for (int c = 0; c < rk; ++c) {
-        const int col = order[(size_t)c];
-        for (int p = 0; p < np; ++p) (*a)[(size_t)p * max_rank + c] = V[(size_t)p * np + col];
-        std::fill(buf.begin(), buf.end(), std::complex<double>(0.0, 0.0));
-        for (int l = 0; l < nl; ++l) buf[(size_t)l] = std::complex<double>(W[(size_t)l * np + col], W[(size_t)(nl + l) * np + col]);
-        fft_pow2(buf, false);
-        std::copy(buf.begin(), buf.end(), b->begin() + (size_t)c * (size_t)K);
-    }
-    return Lmax;
-}
-
 namespace {
 // one-sided Jacobi (Hestenes) on the columns of W (rows x nc, row-major): afterwards the columns are orthogonal,
 // W_final = W * V with V (nc x nc) the accumulated rotations
@@ -390,6 +296,70 @@ int row_space(const std::vector<double>& W, int rows, int np, int rmax, double s
     return r;
 }
 }  // namespace
+
+int design_rank_tables(const std::vector<std::complex<double>>& h, const std::vector<double>& ir, long long P, int K, double tol,
+                       int max_rank, int* rank, std::vector<double>* a, std::vector<std::complex<double>>* b, double* discarded) {
+    const long long n = (long long)h.size(), L = (long long)ir.size();
+    const long long Lg = n + L - 1;
+    std::vector<std::complex<double>> g((size_t)Lg, std::complex<double>(0.0, 0.0));
+    for (long long v = 0; v < L; ++v) {
+        const double c = ir[(size_t)(L - 1 - v)];
+        if (c == 0.0) continue;
+        std::complex<double>* dst = g.data() + v;
+        for (long long m = 0; m < n; ++m) dst[m] += c * h[(size_t)m];
+    }
+    const int Lmax = (int)((Lg - 1) / P);
+    const int nl = Lmax + 1, np = (int)P;
+    *rank = 0;
+    if (nl >= K) return Lmax;
+    // W = [Re M^T ; Im M^T]: 2*nl rows, P columns (column p = branch p); Hestenes rotations make the
+    // columns orthogonal, V accumulates them: W_final = W * V, column c = (b_c re | b_c im), a_c = V[:, c]
+    const int rows = 2 * nl;
+    std::vector<double> W((size_t)rows * np, 0.0), V;
+    for (int p = 0; p < np; ++p)
+        for (int l = 0; l < nl; ++l) {
+            const long long idx = P - 1 - p + (long long)l * P;
+            if (idx < 0 || idx >= Lg) continue;
+            W[(size_t)l * np + p] = g[(size_t)idx].real();
+            W[(size_t)(nl + l) * np + p] = g[(size_t)idx].imag();
+        }
+    double total = 0.0;
+    for (double w : W) total += w * w;
+    if (!(total > 0.0)) return Lmax;
+    hestenes_columns(W, V, rows, np);
+    std::vector<double> sig2((size_t)np, 0.0);
+    std::vector<int> order((size_t)np);
+    for (int c = 0; c < np; ++c) {
+        order[(size_t)c] = c;
+        for (int r = 0; r < rows; ++r) sig2[(size_t)c] += W[(size_t)r * np + c] * W[(size_t)r * np + c];
+    }
+    std::sort(order.begin(), order.end(), [&](int x, int y) { return sig2[(size_t)x] > sig2[(size_t)y]; });
+    // smallest rank whose tail is below tol
+    int rk = np;
+    double tail = 0.0;
+    for (int c = np - 1; c >= 0; --c) {
+        const double t2 = tail + sig2[(size_t)order[(size_t)c]];
+        if (std::sqrt(t2 / total) > tol) break;
+        tail = t2;
+        rk = c;
+    }
+    if (discarded) *discarded = std::sqrt(tail / total);
+    if (rk < 1) rk = 1;
+    if (rk > max_rank) return Lmax;
+    *rank = rk;
+    a->assign((size_t)np * (size_t)max_rank, 0.0);
+    b->assign((size_t)max_rank * (size_t)K, std::complex<double>(0.0, 0.0));
+    std::vector<std::complex<double>> buf((size_t)K);
+    for (int c = 0; c < rk; ++c) {
+        const int col = order[(size_t)c];
+        for (int p = 0; p < np; ++p) (*a)[(size_t)p * max_rank + c] = V[(size_t)p * np + col];
+        std::fill(buf.begin(), buf.end(), std::complex<double>(0.0, 0.0));
+        for (int l = 0; l < nl; ++l) buf[(size_t)l] = std::complex<double>(W[(size_t)l * np + col], W[(size_t)(nl + l) * np + col]);
+        fft_pow2(buf, false);
+        std::copy(buf.begin(), buf.end(), b->begin() + (size_t)c * (size_t)K);
+    }
+    return Lmax;
+}
 
 // The Q > 1 form: the Q phase matrices M_q[p][l] = g[P-1+s_q-p + l*P], l = -1 .. Lmax, side by side share one set of
 // a_c (the front end does not know the phase); the low-rate part has one b_{c,q} per phase.
