@@ -378,6 +378,25 @@ __global__ void __launch_bounds__(256) k_upsample_phase(const cx<T>* __restrict_
 #pragma unroll
     for (int k = 1; k < NT; ++k) w[k] = xs[x0 + NT - 1 - k];
     const long long total = n_out + L;
+    const long long o_first = (p_t0 + x0) * Q + r - m0, o_last = o_first + (long long)(UPP - 1) * Q;
+    if (o_first >= L && o_last < n_out && (out2 == nullptr || o_last < out_split)) {
+        // all of this thread's outputs are whole ones of the first destination: no carried sums, no bounds
+        cx<T>* dst = out + (long long)s * out_stride + o_first;
+#pragma unroll
+        for (int i = 0; i < UPP; ++i) {
+            w[0] = xs[x0 + NT - 1 + i];
+            cx<T> acc((T)0, (T)0);
+#pragma unroll
+            for (int k = NT - 1; k >= 0; --k) {
+                acc.x = fma(w[k].x, h[k], acc.x);
+                acc.y = fma(w[k].y, h[k], acc.y);
+            }
+            st_cx(dst + (long long)i * Q, acc);
+#pragma unroll
+            for (int k = NT - 1; k >= 1; --k) w[k] = w[k - 1];
+        }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < UPP; ++i) {
         w[0] = xs[x0 + NT - 1 + i];
